@@ -1,0 +1,884 @@
+/* rb_oracle.c - CPU oracle for the RigidBodyIntegrator step.
+ *
+ * TEST INFRASTRUCTURE ONLY (see rb_oracle.h).  Plain C11, fp64, single-threaded.  Every routine
+ * restates the arithmetic of the reference plugin's Reference-platform path in the SAME order of
+ * floating-point operations (compile with -ffp-contract=off), so that against the true reference
+ * (oracle/_ref) it agrees to the last bit or very nearly so.  Citations are file:line relative
+ * to /root/reference.
+ *
+ * Parity status: PINNED against oracle/_ref and tests/golden (tests/test_oracle.py).
+ */
+#include "rb_oracle.h"
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EPS DBL_EPSILON
+#define PI_REF 3.14159265358979323846264338328
+
+static _Thread_local char g_error[256];
+const char* orc_last_error(void) { return g_error; }
+
+/* ------------------------------------------------------------------------------------------
+ * 3-vectors and quaternions (OpenMM::Vec3 semantics; openmmapi/src/MatVec.cpp:471-549)
+ * ---------------------------------------------------------------------------------------- */
+static inline double dot3(const double* a, const double* b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2]; }
+static inline void cross3(const double* a, const double* b, double* c) {
+    double x = a[1]*b[2] - a[2]*b[1], y = a[2]*b[0] - a[0]*b[2], z = a[0]*b[1] - a[1]*b[0];
+    c[0] = x; c[1] = y; c[2] = z;
+}
+static inline double dot4(const double* a, const double* b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2] + a[3]*b[3]; }
+
+/* Quat::B  MatVec.cpp:495-500 */
+static inline void quatB(const double* q, const double* x, double* o) {
+    double o0 = -q[1]*x[0] - q[2]*x[1] - q[3]*x[2];
+    double o1 =  q[0]*x[0] - q[3]*x[1] + q[2]*x[2];
+    double o2 =  q[3]*x[0] + q[0]*x[1] - q[1]*x[2];
+    double o3 = -q[2]*x[0] + q[1]*x[1] + q[0]*x[2];
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+}
+/* Quat::C  MatVec.cpp:503-508 */
+static inline void quatC(const double* q, const double* x, double* o) {
+    double o0 = -q[1]*x[0] - q[2]*x[1] - q[3]*x[2];
+    double o1 =  q[0]*x[0] + q[3]*x[1] - q[2]*x[2];
+    double o2 = -q[3]*x[0] + q[0]*x[1] + q[1]*x[2];
+    double o3 =  q[2]*x[0] - q[1]*x[1] + q[0]*x[2];
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+}
+/* Quat::Bt  MatVec.cpp:511-515 */
+static inline void quatBt(const double* q, const double* y, double* o) {
+    double o0 = -q[1]*y[0] + q[0]*y[1] + q[3]*y[2] - q[2]*y[3];
+    double o1 = -q[2]*y[0] - q[3]*y[1] + q[0]*y[2] + q[1]*y[3];
+    double o2 = -q[3]*y[0] + q[2]*y[1] - q[1]*y[2] + q[0]*y[3];
+    o[0] = o0; o[1] = o1; o[2] = o2;
+}
+/* Quat::Ct  MatVec.cpp:518-522 */
+static inline void quatCt(const double* q, const double* y, double* o) {
+    double o0 = -q[1]*y[0] + q[0]*y[1] - q[3]*y[2] + q[2]*y[3];
+    double o1 = -q[2]*y[0] + q[3]*y[1] + q[0]*y[2] - q[1]*y[3];
+    double o2 = -q[3]*y[0] - q[2]*y[1] + q[1]*y[2] + q[0]*y[3];
+    o[0] = o0; o[1] = o1; o[2] = o2;
+}
+/* Quat::A = Bt(C(x)), Quat::At = Ct(B(x))  MatVec.cpp:541-549 */
+static inline void quatA(const double* q, const double* x, double* o) { double t[4]; quatC(q, x, t); quatBt(q, t, o); }
+static inline void quatAt(const double* q, const double* x, double* o) { double t[4]; quatB(q, x, t); quatCt(q, t, o); }
+/* Quat::B1/B2/B3  MatVec.cpp:526-539 */
+static inline void quatBk(int k, const double* q, double* o) {
+    double a = q[0], b = q[1], c = q[2], d = q[3];
+    if (k == 0)      { o[0] = -b; o[1] =  a; o[2] =  d; o[3] = -c; }
+    else if (k == 1) { o[0] = -c; o[1] = -d; o[2] =  a; o[3] =  b; }
+    else             { o[0] = -d; o[1] =  c; o[2] = -b; o[3] =  a; }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Elliptic functions (openmmapi/include/internal/ellipticFunctions.h)
+ * ---------------------------------------------------------------------------------------- */
+static inline int sgn(double x) { return x >= 0 ? 1 : -1; }                    /* SIGN, :26 */
+static inline double dmin(double a, double b) { return (b < a) ? b : a; }       /* std::min  */
+static inline double dmax(double a, double b) { return (a < b) ? b : a; }       /* std::max  */
+
+/* jacobi  ellipticFunctions.h:34-88 : sn, cn, dn by arithmetic-geometric mean + descending Landen */
+void orc_jacobi(double u, double m, double* sn, double* cn, double* dn) {
+    if (fabs(m) > 1.0) { *sn = *cn = *dn = NAN; return; }
+    if (fabs(m) < 2.0*EPS) { *sn = sin(u); *cn = cos(u); *dn = 1.0; return; }
+    if (fabs(m - 1.0) < 2.0*EPS) { *sn = tanh(u); *cn = 1.0/cosh(u); *dn = *cn; return; }
+    double mu[16], nu[16], c[16], d[16];
+    int n = 0;
+    mu[0] = 1.0;
+    nu[0] = sqrt(1.0 - m);
+    while (fabs(mu[n] - nu[n]) > 4.0*EPS*fabs(mu[n] + nu[n])) {
+        mu[n+1] = 0.5*(mu[n] + nu[n]);
+        nu[n+1] = sqrt(mu[n]*nu[n]);
+        ++n;
+        if (n >= 15) { *sn = *cn = *dn = NAN; return; }
+    }
+    double s = sin(u*mu[n]), co = cos(u*mu[n]);
+    if (fabs(s) < fabs(co)) {
+        double t = s/co;
+        c[n] = mu[n]*t;
+        d[n] = 1.0;
+        while (n > 0) {
+            n--;
+            c[n] = d[n+1]*c[n+1];
+            double r = (c[n+1]*c[n+1])/mu[n+1];
+            d[n] = (r + nu[n])/(r + mu[n]);
+        }
+        *dn = sqrt(1.0 - m)/d[n];
+        *cn = (*dn)*sgn(co)/hypot(1.0, c[n]);
+        *sn = (*cn)*c[n]/sqrt(1.0 - m);
+    }
+    else {
+        double t = co/s;
+        c[n] = mu[n]*t;
+        d[n] = 1.0;
+        while (n > 0) {
+            --n;
+            c[n] = d[n+1]*c[n+1];
+            double r = (c[n+1]*c[n+1])/mu[n+1];
+            d[n] = (r + nu[n])/(r + mu[n]);
+        }
+        *dn = d[n];
+        *sn = sgn(s)/hypot(1.0, c[n]);
+        *cn = c[n]*(*sn);
+    }
+}
+
+/* carlsonRC  ellipticFunctions.h:93-122 */
+double orc_carlson_rc(double x, double y) {
+    const double lolim = 5.0*DBL_MIN, uplim = 0.2*DBL_MAX, errtol = 0.001;
+    if (x < 0.0 || y < 0.0 || x + y < lolim || x > uplim || y > uplim) return NAN;
+    const double c1 = 1.0/7.0, c2 = 9.0/22.0;
+    double xn = x, yn = y, mu, sn;
+    int n = 0;
+    for (;;) {
+        mu = (xn + yn + yn)/3.0;
+        sn = (yn + mu)/mu - 2.0;
+        if (fabs(sn) < errtol) break;
+        double lamda = 2.0*sqrt(xn)*sqrt(yn) + yn;
+        xn = (xn + lamda)*0.25;
+        yn = (yn + lamda)*0.25;
+        if (++n == 10000) return NAN;
+    }
+    double s = sn*sn*(0.3 + sn*(c1 + sn*(0.375 + sn*c2)));
+    return (1.0 + s)/sqrt(mu);
+}
+
+/* carlsonRF  ellipticFunctions.h:127-171 */
+double orc_carlson_rf(double x, double y, double z) {
+    const double lolim = 5.0*DBL_MIN, uplim = 0.2*DBL_MAX, errtol = 0.001;
+    if (x < 0.0 || y < 0.0 || z < 0.0 || x + y < lolim || x + z < lolim || y + z < lolim ||
+        x > uplim || y > uplim || z > uplim) return NAN;
+    const double c1 = 1.0/24.0, c2 = 3.0/44.0, c3 = 1.0/14.0;
+    double xn = x, yn = y, zn = z, mu, xd, yd, zd;
+    int n = 0;
+    for (;;) {
+        mu = (xn + yn + zn)/3.0;
+        xd = 2.0 - (mu + xn)/mu;
+        yd = 2.0 - (mu + yn)/mu;
+        zd = 2.0 - (mu + zn)/mu;
+        double epslon = dmax(fabs(xd), dmax(fabs(yd), fabs(zd)));
+        if (epslon < errtol) break;
+        double xr = sqrt(xn), yr = sqrt(yn), zr = sqrt(zn);
+        double lamda = xr*(yr + zr) + yr*zr;
+        xn = (xn + lamda)*0.25;
+        yn = (yn + lamda)*0.25;
+        zn = (zn + lamda)*0.25;
+        if (++n == 10000) return NAN;
+    }
+    double e2 = xd*yd - zd*zd;
+    double e3 = xd*yd*zd;
+    double s = 1.0 + (c1*e2 - 0.1 - c2*e3)*e2 + c3*e3;
+    return s/sqrt(mu);
+}
+
+/* carlsonRJ  ellipticFunctions.h:176-240 */
+double orc_carlson_rj(double x, double y, double z, double p) {
+    const double lolim = pow(5.0*DBL_MIN, 1.0/3.0);
+    const double uplim = 0.3*pow(0.2*DBL_MAX, 1.0/3.0);
+    const double errtol = 0.001;
+    if (x < 0.0 || y < 0.0 || z < 0.0 || x + y < lolim || x + z < lolim || y + z < lolim || p < lolim ||
+        x > uplim || y > uplim || z > uplim || p > uplim) return NAN;
+    const double c1 = 3.0/14.0, c2 = 1.0/3.0, c3 = 3.0/22.0, c4 = 3.0/26.0;
+    double xn = x, yn = y, zn = z, pn = p, sigma = 0.0, power4 = 1.0;
+    double mu, xd, yd, zd, pd;
+    int n = 0;
+    for (;;) {
+        mu = (xn + yn + zn + pn + pn)*0.2;
+        xd = (mu - xn)/mu;
+        yd = (mu - yn)/mu;
+        zd = (mu - zn)/mu;
+        pd = (mu - pn)/mu;
+        double epslon = dmax(dmax(fabs(xd), fabs(yd)), dmax(fabs(zd), fabs(pd)));
+        if (epslon < errtol) break;
+        double xr = sqrt(xn), yr = sqrt(yn), zr = sqrt(zn);
+        double lamda = xr*(yr + zr) + yr*zr;
+        double alfa = pn*(xr + yr + zr) + xr*yr*zr;
+        alfa = alfa*alfa;
+        double beta = pn*(pn + lamda)*(pn + lamda);
+        double rc = orc_carlson_rc(alfa, beta);
+        if (isnan(rc)) return NAN;
+        sigma += power4*rc;
+        power4 *= 0.25;
+        xn = (xn + lamda)*0.25;
+        yn = (yn + lamda)*0.25;
+        zn = (zn + lamda)*0.25;
+        pn = (pn + lamda)*0.25;
+        if (++n == 10000) return NAN;
+    }
+    double ea = xd*(yd + zd) + yd*zd;
+    double eb = xd*yd*zd;
+    double ec = pd*pd;
+    double e2 = ea - 3.0*ec;
+    double e3 = eb + 2.0*pd*(ea - ec);
+    double s1 = 1.0 + e2*(-c1 + 0.75*c3*e2 - 1.5*c4*e3);
+    double s2 = eb*(0.5*c2 + pd*(-c3 - c3 + pd*c4));
+    double s3 = pd*ea*(c2 - pd*c3) - c2*pd*ec;
+    return 3.0*sigma + power4*(s1 + s2 + s3)/(mu*sqrt(mu));
+}
+
+/* Omega  ellipticFunctions.h:242-245 */
+static double omega_fn(double x, double n, double m) {
+    double x2 = x*x;
+    return (-1.0/3.0)*n*x*x2*orc_carlson_rj(1.0 - x2, 1.0 - m*x2, 1.0, 1.0 + n*x2);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Rotations (openmmapi/src/RigidBody.cpp:189-308)
+ * ---------------------------------------------------------------------------------------- */
+
+/* uniaxialRotationAxis{1,2,3}  RigidBody.cpp:189-214 (k = 0,1,2) */
+static void uniaxial(int k, double dt, const double* invI, double* q, double* pi) {
+    double Bq[4], Bp[4];
+    quatBk(k, q, Bq);
+    double w = 0.25*dot4(pi, Bq)*dt*invI[k];
+    double vs = sin(w), vc = cos(w);
+    quatBk(k, pi, Bp);
+    for (int c = 0; c < 4; c++) q[c] = q[c]*vc + Bq[c]*vs;
+    for (int c = 0; c < 4; c++) pi[c] = pi[c]*vc + Bp[c]*vs;
+}
+
+/* noSquishRotation  RigidBody.cpp:220-231 */
+void orc_nosquish_rotation(double dt, int n, int dof, const double* invI, double* q, double* pi) {
+    double h = dt/n, hh = 0.5*h;
+    int axis3 = (dof == 6);
+    for (int i = 0; i < n; i++) {
+        if (axis3) uniaxial(2, hh, invI, q, pi);
+        uniaxial(1, hh, invI, q, pi);
+        uniaxial(0, h, invI, q, pi);
+        uniaxial(1, hh, invI, q, pi);
+        if (axis3) uniaxial(2, hh, invI, q, pi);
+    }
+}
+
+static inline int stair_case(double x) {                                        /* RigidBody.cpp:238 */
+    return x > 0 ? (int) ceil(x - 0.5) : (int) floor(x + 0.5);
+}
+
+/* exactRotation  RigidBody.cpp:241-308.  invI is recomputed as the caller stores it. */
+static void exact_rotation(double dt, const double* I, const double* invI, double* q, double* pi) {
+    double Iw[3], w0[3];
+    quatBt(q, pi, Iw);
+    for (int c = 0; c < 3; c++) Iw[c] = Iw[c]*0.5;
+    for (int c = 0; c < 3; c++) w0[c] = invI[c]*Iw[c];
+    double Lsq = Iw[1]*Iw[1] + Iw[2]*Iw[2];
+    if (Lsq < EPS) { uniaxial(0, dt, invI, q, pi); return; }
+    Lsq += Iw[0]*Iw[0];
+    double L = sqrt(Lsq);
+    double twoKr = dot3(Iw, w0);
+    double z0[4] = {Iw[2], Iw[1], L - Iw[0], 0.0};
+    double r1 = Lsq - twoKr*I[2];
+    double r3 = twoKr*I[0] - Lsq;
+    double l1 = r1*invI[1]/(I[1] - I[2]);
+    double l3 = r3*invI[1]/(I[0] - I[1]);
+    double lmin = dmin(l1, l3);
+    double c13 = 1.0/(I[0] - I[2]);
+    double a[3] = {sgn(w0[0])*sqrt(r1*invI[0]*c13), sqrt(lmin), sgn(w0[2])*sqrt(r3*invI[2]*c13)};
+    double m = lmin/dmax(l1, l3);
+    double K = orc_carlson_rf(0.0, 1.0 - m, 1.0);
+    double inv2K = 0.5/K;
+    double s0 = w0[1]/a[1];
+    double c0, u0;
+    int i0;
+    if (fabs(s0) < 1.0) {
+        c0 = l1 < l3 ? w0[0]/a[0] : w0[2]/a[2];
+        u0 = s0*orc_carlson_rf(1.0 - s0*s0, 1.0 - m*s0*s0, 1.0);
+        i0 = stair_case(u0*inv2K);
+    }
+    else {
+        a[1] = fabs(w0[1]);
+        s0 = sgn(s0);
+        c0 = 0.0;
+        u0 = s0*K;
+        i0 = 0;
+    }
+    double wp = -invI[1]*a[0]*a[2]/(a[1]*c13);
+    double u = wp*dt + u0;
+    int jump = stair_case(u*inv2K) - i0;
+    double sn, cn, dn, deltaF;
+    orc_jacobi(u, m, &sn, &cn, &dn);
+    double alpha = I[0]*a[0]/L;
+    double eta = alpha*alpha;
+    eta /= 1.0 - eta;
+    double Ia[3] = {I[0]*a[0], I[1]*a[1], I[2]*a[2]};
+    if (l1 < l3) {
+        double C = sqrt(m + eta);
+        deltaF = u - u0 + sgn(cn)*omega_fn(sn, eta, m) - sgn(c0)*omega_fn(s0, eta, m)
+                        + (alpha/C)*(atan(C*sn/dn) - atan(C*s0*a[2]/w0[2]));
+        if (jump != 0) deltaF += jump*2.0*omega_fn(1.0, eta, m);
+        Iw[0] = Ia[0]*cn; Iw[1] = Ia[1]*sn; Iw[2] = Ia[2]*dn;
+    }
+    else {
+        double k2eta = m*eta;
+        double C = sqrt(1.0 + k2eta);
+        deltaF = u - u0 + sgn(cn)*omega_fn(sn, k2eta, m) - sgn(c0)*omega_fn(s0, k2eta, m)
+                        + (alpha/C)*(atan(C*sn/cn) - atan(C*s0/c0));
+        if (jump != 0) deltaF += jump*(2.0*omega_fn(1.0, k2eta, m) + (alpha/C)*PI_REF);
+        Iw[0] = Ia[0]*dn; Iw[1] = Ia[1]*sn; Iw[2] = Ia[2]*cn;
+    }
+    deltaF *= 1.0 + eta;
+    double theta = (Lsq*(u - u0) + r3*deltaF)/(2.0*L*I[0]*wp);
+    double ct = cos(theta), st = sin(theta);
+    double za[4] = {Iw[2], Iw[1], L - Iw[0], 0.0};
+    double zb[4] = {-Iw[1], Iw[2], 0.0, L - Iw[0]};
+    double z[4];
+    for (int c = 0; c < 4; c++) z[c] = za[c]*ct + zb[c]*st;
+    double z0q = dot4(z0, q);
+    double t3[3], t4[4];
+    quatCt(z0, q, t3);
+    quatC(z, t3, t4);
+    for (int c = 0; c < 4; c++) q[c] = z[c]*z0q + t4[c];
+    double scale = 1.0/sqrt(dot4(q, q));
+    for (int c = 0; c < 4; c++) q[c] *= scale;
+    double twoIw[3] = {Iw[0]*2.0, Iw[1]*2.0, Iw[2]*2.0};
+    quatB(q, twoIw, pi);
+}
+
+void orc_exact_rotation(double dt, const double* I, double* q, double* pi) {
+    double invI[3] = {1.0/I[0], 1.0/I[1], 1.0/I[2]};
+    exact_rotation(dt, I, invI, q, pi);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * 3x3 symmetric eigen-decomposition (openmmapi/src/eigenDecomposition.cpp)
+ * Matrices are double[3][3], rows first.
+ * ---------------------------------------------------------------------------------------- */
+
+/* eigenvalues  eigenDecomposition.cpp:72-103 : descending order */
+static void sym_eigenvalues(double A[3][3], double* w) {
+    double p1 = A[0][1]*A[0][1] + A[0][2]*A[0][2] + A[1][2]*A[1][2];
+    if (p1 < EPS) {
+        double t;
+        w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
+        if (w[0] < w[1]) { t = w[0]; w[0] = w[1]; w[1] = t; }
+        if (w[0] < w[2]) { t = w[0]; w[0] = w[2]; w[2] = t; }
+        if (w[1] < w[2]) { t = w[1]; w[1] = w[2]; w[2] = t; }
+        return;
+    }
+    double d[3] = {A[0][0], A[1][1], A[2][2]};
+    double TrA = d[0] + d[1] + d[2];
+    double q = TrA/3.0;
+    d[0] -= q; d[1] -= q; d[2] -= q;
+    double p2 = dot3(d, d) + 2.0*p1;
+    double p = sqrt(p2/6.0);
+    /* det(A - q*1)  MatVec.cpp:154-162 */
+    double a0[3] = {A[0][0] - q, A[0][1], A[0][2]};
+    double a1[3] = {A[1][0], A[1][1] - q, A[1][2]};
+    double a2[3] = {A[2][0], A[2][1], A[2][2] - q};
+    double det = a0[0]*(a1[1]*a2[2] - a2[1]*a1[2]) - a0[1]*(a1[0]*a2[2] - a2[0]*a1[2]) + a0[2]*(a1[0]*a2[1] - a2[0]*a1[1]);
+    double r = det*(3.0/(p*p2));
+    double phi;
+    if (r <= -1.0) phi = PI_REF/3.0;
+    else if (r >= 1.0) phi = 0.0;
+    else phi = acos(r)/3.0;
+    double w0 = q + 2.0*p*cos(phi);
+    double w2 = q + 2.0*p*cos(phi + 2.0*PI_REF/3.0);
+    w[0] = w0; w[1] = TrA - (w0 + w2); w[2] = w2;
+}
+
+/* computeEigenvector  eigenDecomposition.cpp:36-68 */
+static void eigvec_fix(double* q, double a[3][3], double n1tmp, double n2tmp, double thresh) {
+    double norm = dot3(q, q);
+    double n1 = n1tmp + a[0][0]*a[0][0];
+    double n2 = n2tmp + a[1][1]*a[1][1];
+    double error = n1*n2;
+    if (n1 <= thresh) { q[0] = 1.0; q[1] = 0.0; q[2] = 0.0; }
+    else if (n2 <= thresh) { q[0] = 0.0; q[1] = 1.0; q[2] = 0.0; }
+    else if (norm < 4096.0*EPS*EPS*error) {
+        double t = fabs(a[0][1]);
+        double f = -a[0][0]/a[0][1];
+        if (fabs(a[1][1]) > t) { t = fabs(a[1][1]); f = -a[0][1]/a[1][1]; }
+        if (fabs(a[1][2]) > t) f = -a[0][2]/a[1][2];
+        norm = 1.0/sqrt(1.0 + f*f);
+        q[0] = norm; q[1] = f*norm; q[2] = 0.0;
+    }
+    else {
+        double s = sqrt(1.0/norm);
+        q[0] *= s; q[1] *= s; q[2] *= s;
+    }
+}
+
+/* eigenvectors  eigenDecomposition.cpp:107-176 : rows of Aout are the eigenvectors */
+static void sym_eigenvectors(double Ain[3][3], const double* w, double Aout[3][3]) {
+    double wmax8eps = 8.0*EPS*fabs(w[0]);
+    double thresh = wmax8eps*wmax8eps;
+    double a[3][3];
+    memcpy(a, Ain, sizeof(a));
+    a[1][0] = a[0][1]; a[2][0] = a[0][2]; a[2][1] = a[1][2];           /* symmetric()  MatVec.cpp:139-145 */
+    double q0[3], q1[3];
+    double n1 = a[0][1]*a[0][1] + a[0][2]*a[0][2];
+    double n2 = a[0][1]*a[0][1] + a[1][2]*a[1][2];
+    q0[0] = a[0][1]*a[1][2] - a[0][2]*a[1][1];
+    q1[0] = q0[0];
+    q0[1] = a[0][2]*a[0][1] - a[1][2]*a[0][0];
+    q1[1] = q0[1];
+    q1[2] = a[0][1]*a[0][1];
+    a[0][0] -= w[0];
+    a[1][1] -= w[0];
+    q0[0] = q1[0] + a[0][2]*w[0];
+    q0[1] = q1[1] + a[1][2]*w[0];
+    q0[2] = a[0][0]*a[1][1] - q1[2];
+    eigvec_fix(q0, a, n1, n2, thresh);
+    double t = w[0] - w[1];
+    if (fabs(t) > wmax8eps) {
+        a[0][0] += t;
+        a[1][1] += t;
+        double x = q1[0] + a[0][2]*w[1], y = q1[1] + a[1][2]*w[1], z = a[0][0]*a[1][1] - q1[2];
+        q1[0] = x; q1[1] = y; q1[2] = z;
+        eigvec_fix(q1, a, n1, n2, thresh);
+    }
+    else {
+        a[0][0] += w[0];
+        a[1][1] += w[0];
+        int success = 0;
+        for (int i = 0; i < 3 && !success; i++) {
+            a[i][i] -= w[1];
+            double ai[3] = {a[0][i], a[1][i], a[2][i]};
+            n1 = dot3(ai, ai);
+            success = n1 > thresh;
+            if (success) {
+                cross3(q0, ai, q1);
+                double norm = dot3(q1, q1);
+                success = norm > 65536.0*EPS*EPS*n1;
+                if (success) { double s = sqrt(1.0/norm); q1[0] *= s; q1[1] *= s; q1[2] *= s; }
+            }
+        }
+        if (!success) {                       /* any vector orthogonal to q0; reference indexing kept */
+            int i = 0;
+            while (i < 2 && q0[i] == 0.0) i++;
+            int j = i % 3;
+            double norm = 1.0/sqrt(q0[i]*q0[i] + q0[j]*q0[j]);
+            q1[i] = q0[j]*norm;
+            q1[j] = -q0[i]*norm;
+            if (i + 1 < 3) q1[i+1] = 0.0;
+        }
+    }
+    for (int c = 0; c < 3; c++) { Aout[0][c] = q0[c]; Aout[1][c] = q1[c]; }
+    cross3(q0, q1, Aout[2]);
+}
+
+/* Quat(const Mat3&)  MatVec.cpp:344-373 : Shepperd's rotation-matrix -> unit quaternion */
+static void quat_from_matrix(double A[3][3], double* q) {
+    double a11 = A[0][0], a22 = A[1][1], a33 = A[2][2];
+    double Q2[4] = {1.0 + a11 + a22 + a33, 1.0 + a11 - a22 - a33, 1.0 - a11 + a22 - a33, 1.0 - a11 - a22 + a33};
+    int imax = 0;
+    double vmax = Q2[0];
+    for (int i = 1; i < 4; i++) if (Q2[i] > vmax) { vmax = Q2[i]; imax = i; }
+    double Q2max = Q2[imax];
+    double f = 0.5/sqrt(Q2max);
+    if (imax == 0) {
+        q[1] = (A[1][2] - A[2][1])*f; q[2] = (A[2][0] - A[0][2])*f; q[3] = (A[0][1] - A[1][0])*f;
+    }
+    else if (imax == 1) {
+        q[0] = (A[1][2] - A[2][1])*f; q[2] = (A[0][1] + A[1][0])*f; q[3] = (A[0][2] + A[2][0])*f;
+    }
+    else if (imax == 2) {
+        q[0] = (A[2][0] - A[0][2])*f; q[1] = (A[0][1] + A[1][0])*f; q[3] = (A[1][2] + A[2][1])*f;
+    }
+    else {
+        q[0] = (A[0][1] - A[1][0])*f; q[1] = (A[0][2] + A[2][0])*f; q[2] = (A[1][2] + A[2][1])*f;
+    }
+    q[imax] = Q2max*f;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * System of rigid bodies + free atoms (openmmapi/src/RigidBodySystem.cpp, RigidBody.cpp:26-183)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int N, dof, loc;
+    double mass, invMass, I[3], invI[3], rcm[3], pcm[3], q[4], pi[4], force[3], torque[4], twoKt, twoKr;
+} body_t;
+
+typedef struct {
+    int numAtoms, numBodies, numFree, numActualAtoms, numBodyAtoms, numDOF, numConstraints, mode;
+    int *bodyIndex, *atomIndex;
+    double* mass;
+    unsigned char* isVirtual;
+    body_t* body;
+    double *d, *delta;                 /* body-frame coordinates and space-frame displacements, 3 per body atom */
+    double *freeInvMass, *savedPos;
+    double *R, *V, *F;
+    int tether;
+    double k, E[3], *charge, *x0;
+} sys_t;
+
+/* cleanBodyIndices  RigidBodySystem.cpp:28-49 : distinct positive labels -> 1..nB in ascending label order */
+static int clean_body_indices(int n, const int* in, int* out) {
+    int maxIndex = in[0];
+    for (int i = 1; i < n; i++) if (in[i] > maxIndex) maxIndex = in[i];
+    if (maxIndex < 0) return -1;                 /* reference: vector(maxIndex) length error */
+    int* rank = (int*) calloc((size_t) maxIndex + 1, sizeof(int));
+    for (int i = 0; i < n; i++) if (in[i] > 0) rank[in[i]] = 1;
+    int body = 0;
+    for (int v = 1; v <= maxIndex; v++) if (rank[v]) rank[v] = ++body;
+    for (int i = 0; i < n; i++) out[i] = in[i] > 0 ? rank[in[i]] : 0;
+    free(rank);
+    return body;
+}
+
+void* orc_create(int numAtoms, const int* bodyIndices, const double* masses, const unsigned char* isVirtual,
+                 int numConstraints, const int* constraintAtoms, int rotationMode) {
+    sys_t* s = (sys_t*) calloc(1, sizeof(sys_t));
+    s->numAtoms = numAtoms;
+    s->mode = rotationMode;
+    s->numConstraints = numConstraints;
+    s->bodyIndex = (int*) calloc((size_t) numAtoms, sizeof(int));
+    s->mass = (double*) malloc(sizeof(double)*(size_t) numAtoms);
+    s->isVirtual = (unsigned char*) calloc((size_t) numAtoms, 1);
+    memcpy(s->mass, masses, sizeof(double)*(size_t) numAtoms);
+    if (isVirtual) memcpy(s->isVirtual, isVirtual, (size_t) numAtoms);
+    s->numBodies = clean_body_indices(numAtoms, bodyIndices, s->bodyIndex);
+    if (s->numBodies < 0) {
+        snprintf(g_error, sizeof g_error, "bodyIndices has no non-negative entry");
+        orc_destroy(s);
+        return NULL;
+    }
+    /* RigidBodySystem::initialize  RigidBodySystem.cpp:55-114 */
+    s->numActualAtoms = numAtoms;
+    for (int i = 0; i < numAtoms; i++) if (s->isVirtual[i]) s->numActualAtoms--;
+    s->atomIndex = (int*) calloc((size_t) s->numActualAtoms + 1, sizeof(int));
+    s->body = (body_t*) calloc((size_t) s->numBodies + 1, sizeof(body_t));
+    for (int i = 0; i < numAtoms; i++)
+        if (!(s->isVirtual[i] || s->mass[i] == 0.0)) {
+            int ib = s->bodyIndex[i];
+            if (ib == 0) s->atomIndex[s->numFree++] = i;
+            else s->body[ib-1].N++;
+        }
+    s->numBodyAtoms = s->numActualAtoms - s->numFree;
+    s->d = (double*) calloc(3*(size_t) s->numBodyAtoms + 3, sizeof(double));
+    s->delta = (double*) calloc(3*(size_t) s->numBodyAtoms + 3, sizeof(double));
+    s->freeInvMass = (double*) calloc((size_t) s->numFree + 1, sizeof(double));
+    s->savedPos = (double*) calloc(3*(size_t) s->numFree + 3, sizeof(double));
+    for (int k = 0; k < s->numFree; k++) s->freeInvMass[k] = 1.0/s->mass[s->atomIndex[k]];
+    int loc = 0;
+    for (int b = 0; b < s->numBodies; b++) { s->body[b].loc = loc; loc += s->body[b].N; }
+    int* fill = (int*) calloc((size_t) s->numBodies + 1, sizeof(int));
+    for (int i = 0; i < numAtoms; i++) {
+        int ib = s->bodyIndex[i];
+        if (ib > 0) {
+            int slot = s->numFree + s->body[ib-1].loc + fill[ib-1]++;
+            if (slot < s->numActualAtoms) s->atomIndex[slot] = i;
+        }
+    }
+    free(fill);
+    for (int c = 0; c < numConstraints; c++)
+        if (s->bodyIndex[constraintAtoms[2*c]] != 0 || s->bodyIndex[constraintAtoms[2*c+1]] != 0) {
+            snprintf(g_error, sizeof g_error, "Constraints involving rigid-body atoms are not allowed");
+            orc_destroy(s);
+            return NULL;
+        }
+    s->R = (double*) calloc(3*(size_t) numAtoms, sizeof(double));
+    s->V = (double*) calloc(3*(size_t) numAtoms, sizeof(double));
+    s->F = (double*) calloc(3*(size_t) numAtoms, sizeof(double));
+    return s;
+}
+
+void orc_destroy(void* h) {
+    sys_t* s = (sys_t*) h;
+    if (!s) return;
+    free(s->bodyIndex); free(s->atomIndex); free(s->mass); free(s->isVirtual); free(s->body);
+    free(s->d); free(s->delta); free(s->freeInvMass); free(s->savedPos);
+    free(s->R); free(s->V); free(s->F); free(s->charge); free(s->x0);
+    free(s);
+}
+
+void orc_counts(void* h, int* out) {
+    sys_t* s = (sys_t*) h;
+    out[0] = s->numBodies; out[1] = s->numFree; out[2] = s->numActualAtoms;
+    out[3] = s->numBodyAtoms; out[4] = s->numDOF; out[5] = s->numAtoms;
+}
+void orc_body_index(void* h, int* out) { sys_t* s = (sys_t*) h; memcpy(out, s->bodyIndex, sizeof(int)*(size_t) s->numAtoms); }
+void orc_atom_index(void* h, int* out) { sys_t* s = (sys_t*) h; memcpy(out, s->atomIndex, sizeof(int)*(size_t) s->numActualAtoms); }
+
+void orc_set_state(void* h, const double* R, const double* V, const double* F) {
+    sys_t* s = (sys_t*) h;
+    size_t n = sizeof(double)*3*(size_t) s->numAtoms;
+    if (R) memcpy(s->R, R, n);
+    if (V) memcpy(s->V, V, n);
+    if (F) memcpy(s->F, F, n);
+}
+void orc_get_state(void* h, double* R, double* V, double* F) {
+    sys_t* s = (sys_t*) h;
+    size_t n = sizeof(double)*3*(size_t) s->numAtoms;
+    if (R) memcpy(R, s->R, n);
+    if (V) memcpy(V, s->V, n);
+    if (F) memcpy(F, s->F, n);
+}
+
+void orc_set_tether(void* h, double k, const double* E, const double* charge, const double* x0) {
+    sys_t* s = (sys_t*) h;
+    s->tether = 1; s->k = k;
+    for (int c = 0; c < 3; c++) s->E[c] = E[c];
+    free(s->charge); free(s->x0);
+    s->charge = (double*) malloc(sizeof(double)*(size_t) s->numAtoms);
+    s->x0 = (double*) malloc(sizeof(double)*3*(size_t) s->numAtoms);
+    memcpy(s->charge, charge, sizeof(double)*(size_t) s->numAtoms);
+    memcpy(s->x0, x0, sizeof(double)*3*(size_t) s->numAtoms);
+}
+
+/* Analytic test potential U = sum 1/2 k |x-x0|^2 - c E.x (same op order as oracle/ref_driver.cpp) */
+double orc_compute_forces(void* h) {
+    sys_t* s = (sys_t*) h;
+    if (!s->tether) return 0.0;
+    double U = 0.0;
+    for (int i = 0; i < s->numAtoms; i++) {
+        double dx[3], *x = s->R + 3*i;
+        for (int c = 0; c < 3; c++) dx[c] = x[c] - s->x0[3*i+c];
+        for (int c = 0; c < 3; c++) s->F[3*i+c] = dx[c]*(-s->k) + s->E[c]*s->charge[i];
+        U += 0.5*s->k*dot3(dx, dx) - s->charge[i]*dot3(s->E, x);
+    }
+    return U;
+}
+
+/* forceAndTorque  RigidBody.cpp:174-183 */
+static void force_and_torque(sys_t* s, body_t* b) {
+    const int* atom = s->atomIndex + s->numFree + b->loc;
+    double tau[3] = {0.0, 0.0, 0.0};
+    b->force[0] = b->force[1] = b->force[2] = 0.0;
+    for (int j = 0; j < b->N; j++) {
+        const double* f = s->F + 3*atom[j];
+        double t[3];
+        for (int c = 0; c < 3; c++) b->force[c] += f[c];
+        cross3(s->delta + 3*(b->loc + j), f, t);
+        for (int c = 0; c < 3; c++) tau[c] += t[c];
+    }
+    quatC(b->q, tau, b->torque);
+}
+
+/* collinear  RigidBody.cpp:26-45 */
+static int collinear(int N, const double* delta, const double* d2, double* u) {
+    const double TOL = 1.0E-5;
+    double d0d0 = d2[0], d2max = d2[0];
+    int jmax = 0;
+    for (int j = 1; j < N; j++) if (d2[j] > d0d0) { jmax = j; d2max = d2[j]; }
+    double scale = 1.0/sqrt(d2max);
+    for (int c = 0; c < 3; c++) u[c] = delta[3*jmax+c]*scale;
+    int is = 1;
+    for (int j = 0; is && j < N; j++) {
+        double djdj = d2[j];
+        double udj = dot3(u, delta + 3*j);
+        is = is && (djdj < TOL*d2max || fabs(udj*udj/djdj - 1.0) < TOL);
+    }
+    return is;
+}
+
+/* buildGeometry  RigidBody.cpp:65-116 */
+static void build_geometry(sys_t* s, body_t* b) {
+    const int* atom = s->atomIndex + s->numFree + b->loc;
+    double* delta = s->delta + 3*b->loc;
+    double* d = s->d + 3*b->loc;
+    int N = b->N;
+    b->mass = 0.0;
+    b->rcm[0] = b->rcm[1] = b->rcm[2] = 0.0;
+    for (int j = 0; j < N; j++) {
+        int i = atom[j];
+        b->mass += s->mass[i];
+        for (int c = 0; c < 3; c++) b->rcm[c] += s->R[3*i+c]*s->mass[i];
+    }
+    double sc = 1.0/b->mass;
+    for (int c = 0; c < 3; c++) b->rcm[c] *= sc;
+    b->invMass = 1.0/b->mass;
+    double* d2 = (double*) malloc(sizeof(double)*(size_t) (N > 0 ? N : 1));
+    for (int j = 0; j < N; j++) {
+        for (int c = 0; c < 3; c++) delta[3*j+c] = s->R[3*atom[j]+c] - b->rcm[c];
+        d2[j] = dot3(delta + 3*j, delta + 3*j);
+    }
+    double u[3], A[3][3];
+    if (collinear(N, delta, d2, u)) {
+        double MoI = 0.0;
+        for (int j = 0; j < N; j++) MoI += s->mass[atom[j]]*d2[j];
+        b->I[0] = MoI; b->I[1] = MoI; b->I[2] = 0.0;
+        b->invI[0] = 1.0/MoI; b->invI[1] = 1.0/MoI; b->invI[2] = 0.0;
+        /* orthonormal  RigidBody.cpp:51-58 */
+        int imin = u[0] < u[1] ? 0 : 1;
+        if (u[2] < u[imin]) imin = 2;
+        double e[3] = {0.0, 0.0, 0.0}, P[3][3], v[3], w[3];
+        e[imin] = 1.0;
+        double utu = dot3(u, u);
+        for (int r = 0; r < 3; r++) {                         /* Projection  MatVec.cpp:555-564 */
+            for (int c = 0; c < 3; c++) P[r][c] = (-u[c])*u[r];
+            P[r][r] += utu;
+        }
+        for (int r = 0; r < 3; r++) v[r] = dot3(P[r], e);
+        double vs = 1.0/sqrt(dot3(v, v));
+        for (int c = 0; c < 3; c++) v[c] *= vs;
+        cross3(u, v, w);
+        for (int r = 0; r < 3; r++) { A[r][0] = v[r]; A[r][1] = w[r]; A[r][2] = u[r]; }   /* Mat3(v,u x v,u).t() */
+        b->dof = 5;
+    }
+    else {
+        double inertia[3][3] = {{0.0}};
+        for (int j = 0; j < N; j++) {
+            const double* x = delta + 3*j;
+            double xtx = dot3(x, x), mj = s->mass[atom[j]];
+            for (int r = 0; r < 3; r++) {
+                double row[3] = {(-x[0])*x[r], (-x[1])*x[r], (-x[2])*x[r]};
+                row[r] += xtx;
+                for (int c = 0; c < 3; c++) inertia[r][c] += row[c]*mj;
+            }
+        }
+        sym_eigenvalues(inertia, b->I);
+        for (int c = 0; c < 3; c++) b->invI[c] = 1.0/b->I[c];
+        sym_eigenvectors(inertia, b->I, A);
+        b->dof = 6;
+    }
+    quat_from_matrix(A, b->q);
+    for (int j = 0; j < N; j++)
+        for (int r = 0; r < 3; r++) d[3*j+r] = dot3(A[r], delta + 3*j);
+    free(d2);
+    force_and_torque(s, b);
+}
+
+/* buildDynamics  RigidBody.cpp:123-142 (pcm accumulates, as in the reference) */
+static void build_dynamics(sys_t* s, body_t* b) {
+    const int* atom = s->atomIndex + s->numFree + b->loc;
+    for (int j = 0; j < b->N; j++) {
+        int i = atom[j];
+        for (int c = 0; c < 3; c++) b->pcm[c] += s->V[3*i+c]*s->mass[i];
+    }
+    double sc = 1.0/b->mass, vcm[3];
+    for (int c = 0; c < 3; c++) vcm[c] = b->pcm[c]*sc;
+    b->twoKt = dot3(b->pcm, vcm);
+    double L[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < b->N; j++) {
+        int i = atom[j];
+        double rel[3], bodyv[3], t[3];
+        for (int c = 0; c < 3; c++) rel[c] = s->V[3*i+c] - vcm[c];
+        quatA(b->q, rel, bodyv);
+        for (int c = 0; c < 3; c++) bodyv[c] *= s->mass[i];
+        cross3(s->d + 3*(b->loc + j), bodyv, t);
+        for (int c = 0; c < 3; c++) L[c] += t[c];
+    }
+    quatB(b->q, L, b->pi);
+    for (int c = 0; c < 4; c++) b->pi[c] *= 2.0;
+    double w[3] = {b->invI[0]*L[0], b->invI[1]*L[1], b->invI[2]*L[2]};
+    b->twoKr = dot3(L, w);
+}
+
+/* RigidBodySystem::update  RigidBodySystem.cpp:120-142 */
+void orc_update(void* h, int geometry, int velocities) {
+    sys_t* s = (sys_t*) h;
+    if (geometry) {
+        s->numDOF = s->numFree - s->numConstraints;
+        for (int b = 0; b < s->numBodies; b++) { build_geometry(s, &s->body[b]); s->numDOF += s->body[b].dof; }
+    }
+    if (velocities)
+        for (int b = 0; b < s->numBodies; b++) build_dynamics(s, &s->body[b]);
+}
+
+/* integratePart1  RigidBodySystem.cpp:170-187 */
+void orc_part1(void* h, double dt) {
+    sys_t* s = (sys_t*) h;
+    double halfDt = 0.5*dt;
+    for (int k = 0; k < s->numFree; k++) {
+        int i = s->atomIndex[k];
+        for (int c = 0; c < 3; c++) {
+            s->V[3*i+c] += s->F[3*i+c]*s->freeInvMass[k]*halfDt;
+            s->R[3*i+c] += s->V[3*i+c]*dt;
+            s->savedPos[3*k+c] = s->R[3*i+c];
+        }
+    }
+    for (int ib = 0; ib < s->numBodies; ib++) {
+        body_t* b = &s->body[ib];
+        for (int c = 0; c < 3; c++) b->pcm[c] += b->force[c]*halfDt;
+        for (int c = 0; c < 4; c++) b->pi[c] += b->torque[c]*dt;
+        double f = b->invMass*dt;
+        for (int c = 0; c < 3; c++) b->rcm[c] += b->pcm[c]*f;
+        if (s->mode == 0) exact_rotation(dt, b->I, b->invI, b->q, b->pi);
+        else orc_nosquish_rotation(dt, s->mode, b->dof, b->invI, b->q, b->pi);
+        /* updateAtomicPositions  RigidBody.cpp:148-153 */
+        const int* atom = s->atomIndex + s->numFree + b->loc;
+        for (int j = 0; j < b->N; j++) {
+            double* dl = s->delta + 3*(b->loc + j);
+            quatAt(b->q, s->d + 3*(b->loc + j), dl);
+            for (int c = 0; c < 3; c++) s->R[3*atom[j]+c] = b->rcm[c] + dl[c];
+        }
+    }
+}
+
+/* integratePart2  RigidBodySystem.cpp:193-204 */
+void orc_part2(void* h, double dt) {
+    sys_t* s = (sys_t*) h;
+    double halfDt = 0.5*dt, invDt = 1.0/dt;
+    for (int k = 0; k < s->numFree; k++) {
+        int i = s->atomIndex[k];
+        for (int c = 0; c < 3; c++)
+            s->V[3*i+c] += s->F[3*i+c]*s->freeInvMass[k]*halfDt + (s->R[3*i+c] - s->savedPos[3*k+c])*invDt;
+    }
+    for (int ib = 0; ib < s->numBodies; ib++) {
+        body_t* b = &s->body[ib];
+        force_and_torque(s, b);
+        for (int c = 0; c < 3; c++) b->pcm[c] += b->force[c]*halfDt;
+        for (int c = 0; c < 4; c++) b->pi[c] += b->torque[c]*dt;
+        /* updateAtomicVelocities  RigidBody.cpp:159-168 */
+        double L[3], w[3], ws[3], vcm[3];
+        quatBt(b->q, b->pi, L);
+        for (int c = 0; c < 3; c++) L[c] *= 0.5;
+        for (int c = 0; c < 3; c++) w[c] = b->invI[c]*L[c];
+        quatAt(b->q, w, ws);
+        for (int c = 0; c < 3; c++) vcm[c] = b->pcm[c]*b->invMass;
+        const int* atom = s->atomIndex + s->numFree + b->loc;
+        for (int j = 0; j < b->N; j++) {
+            double t[3];
+            cross3(ws, s->delta + 3*(b->loc + j), t);
+            for (int c = 0; c < 3; c++) s->V[3*atom[j]+c] = vcm[c] + t[c];
+        }
+        b->twoKt = dot3(b->pcm, vcm);
+        b->twoKr = dot3(L, w);
+    }
+}
+
+/* ReferenceIntegrateRigidBodyStepKernel::execute without constraints / virtual sites
+ * (platforms/reference/src/ReferenceRigidBodyKernels.cpp:82-108) */
+void orc_step(void* h, double dt, int steps) {
+    sys_t* s = (sys_t*) h;
+    for (int i = 0; i < steps; i++) {
+        orc_part1(h, dt);
+        if (s->tether) orc_compute_forces(h);
+        orc_part2(h, dt);
+    }
+}
+
+/* computeKineticEnergies  RigidBodySystem.cpp:210-220 */
+void orc_kinetic(void* h, double* out) {
+    sys_t* s = (sys_t*) h;
+    double kt = 0.0, kr = 0.0;
+    for (int k = 0; k < s->numFree; k++) {
+        const double* v = s->V + 3*s->atomIndex[k];
+        kt += dot3(v, v)/s->freeInvMass[k];
+    }
+    for (int b = 0; b < s->numBodies; b++) { kt += s->body[b].twoKt; kr += s->body[b].twoKr; }
+    out[0] = kt*0.5;
+    out[1] = kr*0.5;
+}
+
+void orc_get_bodies(void* h, int* N, int* dof, int* loc, double* mass, double* I, double* invI, double* rcm,
+                    double* pcm, double* q, double* pi, double* force, double* torque, double* twoK) {
+    sys_t* s = (sys_t*) h;
+    for (int b = 0; b < s->numBodies; b++) {
+        const body_t* B = &s->body[b];
+        if (N) N[b] = B->N;
+        if (dof) dof[b] = B->dof;
+        if (loc) loc[b] = B->loc;
+        if (mass) mass[b] = B->mass;
+        for (int c = 0; c < 3; c++) {
+            if (I) I[3*b+c] = B->I[c];
+            if (invI) invI[3*b+c] = B->invI[c];
+            if (rcm) rcm[3*b+c] = B->rcm[c];
+            if (pcm) pcm[3*b+c] = B->pcm[c];
+            if (force) force[3*b+c] = B->force[c];
+        }
+        for (int c = 0; c < 4; c++) {
+            if (q) q[4*b+c] = B->q[c];
+            if (pi) pi[4*b+c] = B->pi[c];
+            if (torque) torque[4*b+c] = B->torque[c];
+        }
+        if (twoK) { twoK[2*b] = B->twoKt; twoK[2*b+1] = B->twoKr; }
+    }
+}
+
+void orc_get_body_fixed(void* h, double* d) {
+    sys_t* s = (sys_t*) h;
+    memcpy(d, s->d, sizeof(double)*3*(size_t) s->numBodyAtoms);
+}
