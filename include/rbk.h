@@ -1,0 +1,126 @@
+/* rbk.h - C ABI of librbk.so: the B200-native RigidBodyIntegrator step.
+ *
+ * This is the drop-in boundary for ONE hot path of craabreu/openmm_rigidbody_plugin: what its
+ * IntegrateRigidBodyStepKernel implementations do (openmmapi/include/RigidBodyKernels.h:47-99).
+ * Plain C, plain pointers and sizes; no C++ or torch types cross it.  Every entry point returns
+ * 0 on success or a non-zero RBK_E* code, with a thread-local message in rbk_last_error()
+ * (the reference throws OpenMM::OpenMMException; no exception crosses this boundary).
+ *
+ * Each function cites the reference interface it replaces (file:line relative to the reference
+ * tree).  INTEGRATION.md shows the C++ glue (a KernelImpl subclass + kernel factory) that a
+ * maintainer of the reference would add to call it.
+ *
+ * Threading/streams: no internal threads, no hidden synchronisation in rbk_part1/rbk_part2;
+ * all device work is enqueued on the cudaStream_t passed as `stream` (void*, NULL = default
+ * stream).  There is NO CPU fallback: without a CUDA device every device entry point fails.
+ */
+#ifndef RBK_H_
+#define RBK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBK_VERSION 1
+
+/* error codes */
+#define RBK_OK            0
+#define RBK_EINVAL        1   /* bad argument (also: negative rotation mode)                       */
+#define RBK_ECONSTRAINT   2   /* "Constraints involving rigid-body atoms are not allowed"          */
+#define RBK_ECUDA         3   /* CUDA runtime error / no device                                     */
+#define RBK_ESTATE        4   /* call order violated (e.g. part1 before upload)                    */
+#define RBK_ENOMEM        5
+
+/* atom-array layouts accepted by the device entry points (element type: double) */
+#define RBK_LAYOUT_VEC3   0   /* xyzxyz...  = std::vector<OpenMM::Vec3>, the Reference platform's  */
+#define RBK_LAYOUT_SOA    1   /* x[stride] y[stride] z[stride] planes                              */
+
+typedef struct rbk_system rbk_system;
+
+int         rbk_version(void);
+const char* rbk_last_error(void);
+
+/* ---- host model -------------------------------------------------------------------------- */
+
+/* RigidBodySystem::initialize (openmmapi/src/RigidBodySystem.cpp:55-114) incl. cleanBodyIndices
+ * (:28-49): compacts bodyIndices (<=0 -> free; distinct positive labels -> 1..nB in ascending
+ * label order), counts free atoms / body sizes, lays out atomIndex = [free..., body 1..., ...]
+ * and rejects constraints that touch body atoms.  isVirtual may be NULL (no virtual sites);
+ * constraintAtoms holds 2*numConstraints atom indices.  rotationMode: 0 = exact, n>0 = NO-SQUISH
+ * with n sub-steps (RigidBodyIntegrator::setRotationMode, openmmapi/src/RigidBodyIntegrator.cpp:26-32). */
+int rbk_create(int numAtoms, const int* bodyIndices, const double* masses, const unsigned char* isVirtual,
+               int numConstraints, const int* constraintAtoms, int rotationMode, rbk_system** out);
+void rbk_destroy(rbk_system* sys);
+
+/* out[5] = numBodies, numFree, numActualAtoms, numBodyAtoms, numDOF
+ * (RigidBodySystem::getNum*, openmmapi/include/RigidBodySystem.h:37-42; numDOF is valid after
+ * the first rbk_update with geometry != 0, RigidBodySystem.cpp:130-134). */
+int rbk_get_counts(const rbk_system* sys, int* out);
+int rbk_get_body_index(const rbk_system* sys, int* out);   /* [numAtoms]       cleaned index       */
+int rbk_get_atom_index(const rbk_system* sys, int* out);   /* [numActualAtoms] RigidBodySystem::getAtomIndex */
+
+/* RigidBodySystem::update (RigidBodySystem.cpp:120-142) = what RigidBodyIntegrator::stateChanged
+ * triggers (RigidBodyIntegrator.cpp:63-74): rebuild body geometry (buildGeometry, RigidBody.cpp:65-116)
+ * and/or dynamics (buildDynamics, :123-142) on the HOST model from host arrays R,V,F in
+ * RBK_LAYOUT_VEC3 (any of them may be NULL when not needed by the requested parts). */
+int rbk_update(rbk_system* sys, const double* R, const double* V, const double* F, int geometry, int velocities);
+
+/* Host model dump (RigidBodySystem::getRigidBody / getBodyFixedPosition).  Arrays are per body,
+ * row-major [nB][3|4]; any pointer may be NULL.  twoK = [nB][2] (2Kt, 2Kr). */
+int rbk_get_host_bodies(const rbk_system* sys, int* N, int* dof, int* loc, double* mass, double* I, double* invI,
+                        double* rcm, double* pcm, double* q, double* pi, double* force, double* torque, double* twoK);
+int rbk_get_body_fixed(const rbk_system* sys, double* d);  /* [numBodyAtoms][3] */
+
+/* ---- device ------------------------------------------------------------------------------- */
+
+/* IntegrateRigidBodyStepKernel::uploadBodySystem (RigidBodyKernels.h:66; CUDA platform:
+ * platforms/cuda/src/CudaRigidBodyKernels.cpp:293-372): (re)allocate device state on first use and
+ * copy the whole host body model to the device in SoA form. */
+int rbk_upload(rbk_system* sys, void* stream);
+
+/* Replace the plugin-order -> caller-order atom map (CUDA platform's atomLocation,
+ * CudaRigidBodyKernels.cpp:277-284 and ReorderListener :69-113).  location[i] is the index in the
+ * caller's pos/vel/force arrays of plugin atom i (i indexes rbk_get_atom_index order).
+ * NULL restores the default location[i] = atomIndex[i]. */
+int rbk_set_atom_location(rbk_system* sys, const int* location, void* stream);
+
+/* RigidBodySystem::integratePart1 (RigidBodySystem.cpp:170-187): free atoms half-kick + drift,
+ * bodies half-kick, drift, rotation (exactRotation RigidBody.cpp:241-308 | noSquishRotation :220-231)
+ * and atom-position reconstruction (updateAtomicPositions :148-153).
+ * pos/vel/force are DEVICE pointers in `layout` (stride = plane stride in elements for SOA). */
+int rbk_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force,
+              int layout, long long stride, void* stream);
+
+/* RigidBodySystem::integratePart2 (RigidBodySystem.cpp:193-204): free atoms second half-kick
+ * (+ constraint displacement term), bodies forceAndTorque (RigidBody.cpp:174-183), second half
+ * kick and atom-velocity reconstruction (updateAtomicVelocities :159-168). */
+int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const double* force,
+              int layout, long long stride, void* stream);
+
+/* RigidBodySystem::computeKineticEnergies (RigidBodySystem.cpp:210-220) =
+ * IntegrateRigidBodyStepKernel::getKineticEnergies (RigidBodyKernels.h:86): out[0] = translational,
+ * out[1] = rotational kinetic energy.  Synchronises `stream` once to return the two doubles. */
+int rbk_kinetic(rbk_system* sys, const double* vel, int layout, long long stride, double* out, void* stream);
+
+/* Device body state -> host arrays [nB][3|4] (any pointer may be NULL); synchronises `stream`.
+ * torque is the quaternion-frame 4-vector C(q)tau as the reference stores it (RigidBody.h:40). */
+int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, double* pi,
+                        double* force, double* torque, void* stream);
+
+/* ---- host-buffer step (the reference-facing call measured as `e2e`) ------------------------ */
+
+/* Force provider for rbk_execute_host: given positions R (host, VEC3) fill F (host, VEC3). */
+typedef void (*rbk_force_fn)(const double* R, double* F, int numAtoms, void* user);
+
+/* ReferenceIntegrateRigidBodyStepKernel::execute (platforms/reference/src/ReferenceRigidBodyKernels.cpp:82-108)
+ * with HOST buffers, `steps` times: Part 1 on the device, positions copied to R, forces obtained
+ * from `forces` (NULL = keep F as is) and copied to the device, Part 2, velocities copied to V.
+ * R,V,F: host arrays in RBK_LAYOUT_VEC3 (pinned memory makes the copies asynchronous); on the first
+ * call R,V,F are uploaded in full.  Uses device mirrors owned by the handle. */
+int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F,
+                     rbk_force_fn forces, void* user, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBK_H_ */

@@ -1,0 +1,10 @@
+"""B200-native RigidBodyIntegrator step (drop-in for one hot path of craabreu/openmm_rigidbody_plugin).
+
+The arithmetic lives in lib/librbk.so (hand-written CUDA for sm_100a behind the C ABI in
+include/rbk.h); this package is the host-side mirror of the reference's interface.  Importing the
+package does not load the library; constructing any system does, and fails loudly if it is missing.
+"""
+from ._lib import RBK_LAYOUT_SOA, RBK_LAYOUT_VEC3, RbkError  # noqa: F401
+from .system import DeviceRigidBodySystem  # noqa: F401
+
+__all__ = ["DeviceRigidBodySystem", "RbkError", "RBK_LAYOUT_VEC3", "RBK_LAYOUT_SOA"]

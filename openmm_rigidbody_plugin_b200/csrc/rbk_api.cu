@@ -1,0 +1,427 @@
+// rbk_api.cu - the C ABI declared in include/rbk.h: handle, device memory, error plumbing.
+// There is no CPU fallback: every device entry point fails with RBK_ECUDA when no GPU is usable.
+#include "../../include/rbk.h"
+#include "rbk_device.hpp"
+#include "rbk_host.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using rbk::AtomView;
+using rbk::DeviceSystem;
+using rbk::HostBody;
+using rbk::HostModel;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+#define RBK_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(RBK_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+template <class T> cudaError_t devAlloc(T*& p, size_t count) {
+    p = nullptr;
+    return count ? cudaMalloc((void**) &p, count*sizeof(T)) : cudaSuccess;
+}
+
+size_t padTo(size_t n, size_t m) { return (n + m - 1)/m*m; }
+
+} // namespace
+
+struct rbk_system {
+    HostModel host;
+    DeviceSystem dev{};
+    bool allocated = false, uploaded = false;
+    // device allocations
+    double* dState = nullptr;
+    double* dDxyz = nullptr;
+    uint8_t* dLocalBody = nullptr;
+    int* dLoc = nullptr;
+    int* dTile = nullptr;
+    int* dAtomLoc = nullptr;
+    double* dFreeInvMass = nullptr;
+    double* dSavedPos = nullptr;
+    double* dKinPartial = nullptr;
+    unsigned* dKinCounter = nullptr;
+    double* dKinOut = nullptr;
+    double* hKinOut = nullptr;       // pinned
+    // device mirrors for rbk_execute_host
+    double* mPos = nullptr;
+    double* mVel = nullptr;
+    double* mForce = nullptr;
+    bool mirrorsLoaded = false;
+    std::vector<double> staging;
+
+    ~rbk_system() {
+        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTile);
+        cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dKinPartial);
+        cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce);
+        if (hKinOut) cudaFreeHost(hKinOut);
+    }
+};
+
+namespace {
+
+// Cut the body list into tiles (<= kBlock bodies, <= kTileAtoms atoms unless one body is larger) and
+// allocate + fill everything that does not change between uploads.
+int allocateDevice(rbk_system* sys, cudaStream_t st) {
+    HostModel& h = sys->host;
+    DeviceSystem& d = sys->dev;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(RBK_ECUDA, "librbk needs a CUDA device (there is no CPU fallback)");
+
+    const int nB = h.numBodies, nA = h.numBodyAtoms, nF = h.numFree;
+    std::vector<int> loc((size_t) nB + 1, 0), tile;
+    std::vector<uint8_t> local((size_t) std::max(nA, 1), 0);
+    int maxSize = 0;
+    for (int b = 0; b < nB; b++) {
+        loc[b] = h.body[b].loc;
+        maxSize = std::max(maxSize, h.body[b].N);
+    }
+    loc[nB] = nB ? h.body[nB-1].loc + h.body[nB-1].N : 0;
+    tile.push_back(0);
+    int inTile = 0, atomsInTile = 0;
+    for (int b = 0; b < nB; b++) {
+        const int n = h.body[b].N;
+        if (inTile > 0 && (inTile == rbk::kBlock || atomsInTile + n > rbk::kTileAtoms)) {
+            tile.push_back(b);
+            inTile = 0;
+            atomsInTile = 0;
+        }
+        for (int j = 0; j < n; j++) local[(size_t) loc[b] + j] = (uint8_t) inTile;
+        inTile++;
+        atomsInTile += n;
+    }
+    if (nB) tile.push_back(nB);
+
+    d.numBodies = nB;
+    d.numFree = nF;
+    d.numBodyAtoms = nA;
+    d.numTiles = nB ? (int) tile.size() - 1 : 0;
+    d.numFreeBlocks = (nF + rbk::kFreePerBlock - 1)/rbk::kFreePerBlock;
+    d.rotationMode = h.rotationMode;
+    d.maxBodySize = maxSize;
+    d.bodyStride = padTo((size_t) std::max(nB, 1), 32);
+    d.atomStride = padTo((size_t) std::max(nA, 1), 32);
+    d.freeStride = padTo((size_t) std::max(nF, 1), 32);
+
+    RBK_CUDA(devAlloc(sys->dState, d.bodyStride*rbk::NPLANES));
+    RBK_CUDA(devAlloc(sys->dDxyz, d.atomStride*3));
+    RBK_CUDA(devAlloc(sys->dLocalBody, local.size()));
+    RBK_CUDA(devAlloc(sys->dLoc, loc.size()));
+    RBK_CUDA(devAlloc(sys->dTile, tile.size()));
+    RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
+    RBK_CUDA(devAlloc(sys->dFreeInvMass, (size_t) std::max(nF, 1)));
+    RBK_CUDA(devAlloc(sys->dSavedPos, d.freeStride*3));
+    RBK_CUDA(devAlloc(sys->dKinPartial, (size_t) 2*rbk::kKineticBlocks));
+    RBK_CUDA(devAlloc(sys->dKinCounter, 1));
+    RBK_CUDA(devAlloc(sys->dKinOut, 2));
+    RBK_CUDA(cudaMallocHost((void**) &sys->hKinOut, 2*sizeof(double)));
+    RBK_CUDA(cudaMemsetAsync(sys->dKinCounter, 0, sizeof(unsigned), st));
+    RBK_CUDA(cudaMemsetAsync(sys->dSavedPos, 0, d.freeStride*3*sizeof(double), st));
+    RBK_CUDA(cudaMemcpyAsync(sys->dLocalBody, local.data(), local.size(), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaMemcpyAsync(sys->dLoc, loc.data(), loc.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaMemcpyAsync(sys->dTile, tile.data(), tile.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+    if (nF) RBK_CUDA(cudaMemcpyAsync(sys->dFreeInvMass, h.freeInvMass.data(), (size_t) nF*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaStreamSynchronize(st));       // the host vectors above die at scope exit
+
+    d.state = sys->dState;
+    d.dxyz = sys->dDxyz;
+    d.localBody = sys->dLocalBody;
+    d.loc = sys->dLoc;
+    d.tileBody = sys->dTile;
+    d.atomLoc = nullptr;
+    d.freeInvMass = sys->dFreeInvMass;
+    d.savedPos = sys->dSavedPos;
+    sys->allocated = true;
+    return RBK_OK;
+}
+
+int setLocation(rbk_system* sys, const int* location, cudaStream_t st) {
+    const HostModel& h = sys->host;
+    const int n = h.numFree + h.numBodyAtoms;        // slots actually addressed by the kernels
+    const int* src = location ? location : h.atomIndex.data();
+    bool identity = true;
+    for (int i = 0; i < n && identity; i++) identity = src[i] == i;
+    if (identity) {
+        sys->dev.atomLoc = nullptr;
+        return RBK_OK;
+    }
+    for (int i = 0; i < n; i++)
+        if (src[i] < 0 || (location == nullptr && src[i] >= h.numAtoms))
+            return fail(RBK_EINVAL, "rbk_set_atom_location: negative or out-of-range location");
+    RBK_CUDA(cudaMemcpyAsync(sys->dAtomLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    sys->dev.atomLoc = sys->dAtomLoc;
+    return RBK_OK;
+}
+
+int viewOf(const void* p, int layout, long long stride, AtomView& v) {
+    v.p = (double*) p;
+    if (layout == RBK_LAYOUT_VEC3) { v.sa = 3; v.sc = 1; }
+    else if (layout == RBK_LAYOUT_SOA) {
+        if (stride <= 0) return fail(RBK_EINVAL, "RBK_LAYOUT_SOA needs a positive plane stride");
+        v.sa = 1; v.sc = stride;
+    }
+    else return fail(RBK_EINVAL, "unknown atom layout");
+    return RBK_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int rbk_version(void) { return RBK_VERSION; }
+const char* rbk_last_error(void) { return g_error.c_str(); }
+
+int rbk_create(int numAtoms, const int* bodyIndices, const double* masses, const unsigned char* isVirtual,
+               int numConstraints, const int* constraintAtoms, int rotationMode, rbk_system** out) {
+    if (!out) return fail(RBK_EINVAL, "rbk_create: out is NULL");
+    *out = nullptr;
+    if (numConstraints < 0 || (numConstraints > 0 && !constraintAtoms)) return fail(RBK_EINVAL, "rbk_create: bad constraint list");
+    rbk_system* sys = new (std::nothrow) rbk_system();
+    if (!sys) return fail(RBK_ENOMEM, "rbk_create: out of memory");
+    std::string err;
+    try {
+        err = sys->host.initialize(numAtoms, bodyIndices, masses, isVirtual, numConstraints, constraintAtoms, rotationMode);
+    }
+    catch (const std::exception& e) {
+        delete sys;
+        return fail(RBK_ENOMEM, std::string("rbk_create: ") + e.what());
+    }
+    if (!err.empty()) {
+        delete sys;
+        return fail(err.find("Constraints") == 0 ? RBK_ECONSTRAINT : RBK_EINVAL, err);
+    }
+    *out = sys;
+    return RBK_OK;
+}
+
+void rbk_destroy(rbk_system* sys) { delete sys; }
+
+int rbk_get_counts(const rbk_system* sys, int* out) {
+    if (!sys || !out) return fail(RBK_EINVAL, "rbk_get_counts: NULL argument");
+    const HostModel& h = sys->host;
+    out[0] = h.numBodies; out[1] = h.numFree; out[2] = h.numActualAtoms; out[3] = h.numBodyAtoms; out[4] = h.numDOF;
+    return RBK_OK;
+}
+
+int rbk_get_body_index(const rbk_system* sys, int* out) {
+    if (!sys || !out) return fail(RBK_EINVAL, "rbk_get_body_index: NULL argument");
+    std::memcpy(out, sys->host.bodyIndex.data(), sys->host.bodyIndex.size()*sizeof(int));
+    return RBK_OK;
+}
+
+int rbk_get_atom_index(const rbk_system* sys, int* out) {
+    if (!sys || !out) return fail(RBK_EINVAL, "rbk_get_atom_index: NULL argument");
+    std::memcpy(out, sys->host.atomIndex.data(), sys->host.atomIndex.size()*sizeof(int));
+    return RBK_OK;
+}
+
+int rbk_update(rbk_system* sys, const double* R, const double* V, const double* F, int geometry, int velocities) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_update: NULL system");
+    if (geometry && (!R || !F)) return fail(RBK_EINVAL, "rbk_update: geometry needs positions and forces");
+    if (velocities && !V) return fail(RBK_EINVAL, "rbk_update: velocities needed");
+    if (velocities && !geometry && sys->host.numBodies > 0 && sys->host.body[0].mass == 0.0)
+        return fail(RBK_ESTATE, "rbk_update: velocities before any geometry build");
+    sys->host.update(R, V, F, geometry != 0, velocities != 0);
+    return RBK_OK;
+}
+
+int rbk_get_host_bodies(const rbk_system* sys, int* N, int* dof, int* loc, double* mass, double* I, double* invI,
+                        double* rcm, double* pcm, double* q, double* pi, double* force, double* torque, double* twoK) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_get_host_bodies: NULL system");
+    const HostModel& h = sys->host;
+    for (int b = 0; b < h.numBodies; b++) {
+        const HostBody& B = h.body[b];
+        if (N) N[b] = B.N;
+        if (dof) dof[b] = B.dof;
+        if (loc) loc[b] = B.loc;
+        if (mass) mass[b] = B.mass;
+        for (int c = 0; c < 3; c++) {
+            if (I) I[3*b+c] = B.I[c];
+            if (invI) invI[3*b+c] = B.invI[c];
+            if (rcm) rcm[3*b+c] = B.rcm[c];
+            if (pcm) pcm[3*b+c] = B.pcm[c];
+            if (force) force[3*b+c] = B.force[c];
+        }
+        for (int c = 0; c < 4; c++) {
+            if (q) q[4*b+c] = B.q[c];
+            if (pi) pi[4*b+c] = B.pi[c];
+            if (torque) torque[4*b+c] = B.torque[c];
+        }
+        if (twoK) { twoK[2*b] = B.twoKt; twoK[2*b+1] = B.twoKr; }
+    }
+    return RBK_OK;
+}
+
+int rbk_get_body_fixed(const rbk_system* sys, double* d) {
+    if (!sys || !d) return fail(RBK_EINVAL, "rbk_get_body_fixed: NULL argument");
+    std::memcpy(d, sys->host.d.data(), sys->host.d.size()*sizeof(double));
+    return RBK_OK;
+}
+
+int rbk_upload(rbk_system* sys, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_upload: NULL system");
+    cudaStream_t st = (cudaStream_t) stream;
+    if (!sys->allocated) {
+        int rc = allocateDevice(sys, st);
+        if (rc != RBK_OK) return rc;
+        rc = setLocation(sys, nullptr, st);
+        if (rc != RBK_OK) return rc;
+    }
+    const HostModel& h = sys->host;
+    const DeviceSystem& d = sys->dev;
+    const size_t ld = d.bodyStride;
+    std::vector<double>& buf = sys->staging;
+    buf.assign(std::max(ld*rbk::NPLANES, d.atomStride*3), 0.0);
+    for (int b = 0; b < h.numBodies; b++) {
+        const HostBody& B = h.body[b];
+        for (int c = 0; c < 3; c++) {
+            buf[(rbk::PL_R + c)*ld + b] = B.rcm[c];
+            buf[(rbk::PL_P + c)*ld + b] = B.pcm[c];
+            buf[(rbk::PL_F + c)*ld + b] = B.force[c];
+            buf[(rbk::PL_TAU + c)*ld + b] = B.tau[c];
+            buf[(rbk::PL_I + c)*ld + b] = B.I[c];
+            buf[(rbk::PL_INVI + c)*ld + b] = B.invI[c];
+        }
+        for (int c = 0; c < 4; c++) {
+            buf[(rbk::PL_Q + c)*ld + b] = B.q[c];
+            buf[(rbk::PL_PI + c)*ld + b] = B.pi[c];
+        }
+        buf[rbk::PL_INVM*ld + b] = B.invMass;
+    }
+    RBK_CUDA(cudaMemcpyAsync(sys->dState, buf.data(), ld*rbk::NPLANES*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    const size_t as = d.atomStride;
+    for (int a = 0; a < h.numBodyAtoms; a++)
+        for (int c = 0; c < 3; c++) buf[c*as + a] = h.d[3*(size_t) a + c];
+    RBK_CUDA(cudaMemcpyAsync(sys->dDxyz, buf.data(), as*3*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    sys->uploaded = true;
+    sys->mirrorsLoaded = false;
+    return RBK_OK;
+}
+
+int rbk_set_atom_location(rbk_system* sys, const int* location, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_set_atom_location: NULL system");
+    if (!sys->allocated) return fail(RBK_ESTATE, "rbk_set_atom_location: call rbk_upload first");
+    return setLocation(sys, location, (cudaStream_t) stream);
+}
+
+int rbk_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force, int layout, long long stride,
+              void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_part1: NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part1: body system not uploaded");
+    AtomView p, v, f;
+    if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
+    RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const double* force, int layout,
+              long long stride, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_part2: NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2: body system not uploaded");
+    AtomView p, v, f;
+    if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
+    RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_kinetic(rbk_system* sys, const double* vel, int layout, long long stride, double* out, void* stream) {
+    if (!sys || !out) return fail(RBK_EINVAL, "rbk_kinetic: NULL argument");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_kinetic: body system not uploaded");
+    cudaStream_t st = (cudaStream_t) stream;
+    AtomView v;
+    if (viewOf(vel, layout, stride, v)) return RBK_EINVAL;
+    RBK_CUDA(rbk::launchKinetic(sys->dev, v, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
+    RBK_CUDA(cudaMemcpyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    out[0] = sys->hKinOut[0];
+    out[1] = sys->hKinOut[1];
+    return RBK_OK;
+}
+
+int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, double* pi, double* force,
+                        double* torque, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_download_bodies: NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_download_bodies: body system not uploaded");
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t ld = sys->dev.bodyStride;
+    std::vector<double>& buf = sys->staging;
+    buf.resize(std::max(buf.size(), ld*rbk::NPLANES));
+    RBK_CUDA(cudaMemcpyAsync(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < sys->host.numBodies; b++) {
+        double qq[4], tt[3];
+        for (int c = 0; c < 3; c++) {
+            if (rcm) rcm[3*b+c] = buf[(rbk::PL_R + c)*ld + b];
+            if (pcm) pcm[3*b+c] = buf[(rbk::PL_P + c)*ld + b];
+            if (force) force[3*b+c] = buf[(rbk::PL_F + c)*ld + b];
+            tt[c] = buf[(rbk::PL_TAU + c)*ld + b];
+        }
+        for (int c = 0; c < 4; c++) {
+            qq[c] = buf[(rbk::PL_Q + c)*ld + b];
+            if (q) q[4*b+c] = qq[c];
+            if (pi) pi[4*b+c] = buf[(rbk::PL_PI + c)*ld + b];
+        }
+        if (torque) {                                   // C(q) tau, the form the reference stores
+            torque[4*b+0] = -qq[1]*tt[0] - qq[2]*tt[1] - qq[3]*tt[2];
+            torque[4*b+1] =  qq[0]*tt[0] + qq[3]*tt[1] - qq[2]*tt[2];
+            torque[4*b+2] = -qq[3]*tt[0] + qq[0]*tt[1] + qq[1]*tt[2];
+            torque[4*b+3] =  qq[2]*tt[0] - qq[1]*tt[1] + qq[0]*tt[2];
+        }
+    }
+    return RBK_OK;
+}
+
+int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F, rbk_force_fn forces,
+                     void* user, void* stream) {
+    if (!sys || !R || !V || !F) return fail(RBK_EINVAL, "rbk_execute_host: NULL argument");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_execute_host: body system not uploaded");
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
+    if (!sys->mPos) {
+        RBK_CUDA(cudaMalloc((void**) &sys->mPos, bytes));
+        RBK_CUDA(cudaMalloc((void**) &sys->mVel, bytes));
+        RBK_CUDA(cudaMalloc((void**) &sys->mForce, bytes));
+    }
+    if (!sys->mirrorsLoaded) {
+        RBK_CUDA(cudaMemcpyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
+        RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+        RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
+        sys->mirrorsLoaded = true;
+    }
+    const AtomView p{sys->mPos, 3, 1}, v{sys->mVel, 3, 1}, f{sys->mForce, 3, 1};
+    for (int i = 0; i < steps; i++) {
+        RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, f, st));
+        RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
+        if (forces) {
+            RBK_CUDA(cudaStreamSynchronize(st));
+            forces(R, F, sys->host.numAtoms, user);
+        }
+        RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
+        RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, st));
+        RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    RBK_CUDA(cudaStreamSynchronize(st));
+    return RBK_OK;
+}
+
+} // extern "C"

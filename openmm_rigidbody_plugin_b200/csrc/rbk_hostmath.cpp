@@ -1,0 +1,45 @@
+// rbk_hostmath.cpp - compiles the PRODUCT's device arithmetic (rbk_math.cuh / rbk_step.cuh) for the
+// host, so that the CPU test-suite can check it against the oracle without a GPU
+// (tests/test_device_math_host.py).  Not part of librbk.so and not a fallback: nothing in the
+// product calls this library.
+#include "rbk_step.cuh"
+
+using namespace rbk;
+
+extern "C" {
+
+void rbkh_jacobi(double u, double m, double* sn, double* cn, double* dn) { jacobiSnCnDn(u, m, *sn, *cn, *dn); }
+double rbkh_rf(double x, double y, double z) { return carlsonRF(x, y, z); }
+double rbkh_rj(double x, double y, double z, double p) { return carlsonRJ(x, y, z, p); }
+double rbkh_rc(double x, double y) { return carlsonRC(x, y); }
+
+void rbkh_exact_rotation(double dt, const double* I, double* q, double* pi, int elliptic_only) {
+    d3 Iv = {I[0], I[1], I[2]}, inv = {1.0/I[0], 1.0/I[1], 1.0/I[2]};
+    d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};
+    if (elliptic_only) exactRotationElliptic(dt, Iv, inv, qq, pp);
+    else exactRotation(dt, Iv, inv, qq, pp);
+    q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z;
+    pi[0] = pp.w; pi[1] = pp.x; pi[2] = pp.y; pi[3] = pp.z;
+}
+
+void rbkh_nosquish(double dt, int n, const double* invI, double* q, double* pi) {
+    d3 inv = {invI[0], invI[1], invI[2]};
+    d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};
+    noSquish(dt, n, inv, qq, pp);
+    q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z;
+    pi[0] = pp.w; pi[1] = pp.x; pi[2] = pp.y; pi[3] = pp.z;
+}
+
+// One body through Part 1 (mode 0 or n) exactly as the kernel's thread-per-body phase does it.
+void rbkh_body_part1(int mode, double dt, const double* F, const double* tau, double invm, const double* I,
+                     const double* invI, double* r, double* p, double* q, double* pi) {
+    d3 rr = {r[0], r[1], r[2]}, pp = {p[0], p[1], p[2]};
+    d4 qq = {q[0], q[1], q[2], q[3]}, pq = {pi[0], pi[1], pi[2], pi[3]};
+    d3 Fv = {F[0], F[1], F[2]}, tv = {tau[0], tau[1], tau[2]}, Iv = {I[0], I[1], I[2]}, inv = {invI[0], invI[1], invI[2]};
+    if (mode == 0) bodyPart1<true>(dt, 0, Fv, tv, invm, Iv, inv, rr, pp, qq, pq);
+    else bodyPart1<false>(dt, mode, Fv, tv, invm, Iv, inv, rr, pp, qq, pq);
+    r[0] = rr.x; r[1] = rr.y; r[2] = rr.z; p[0] = pp.x; p[1] = pp.y; p[2] = pp.z;
+    q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z; pi[0] = pq.w; pi[1] = pq.x; pi[2] = pq.y; pi[3] = pq.z;
+}
+
+} // extern "C"

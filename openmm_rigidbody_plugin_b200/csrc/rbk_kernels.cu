@@ -1,0 +1,325 @@
+// rbk_kernels.cu - hand-written CUDA kernels (sm_100a) of the RigidBodyIntegrator step.
+//
+// Work decomposition (DESIGN.md "Kernels"): bodies are cut into TILES of <=128 consecutive bodies
+// (<= ~1024 atoms); one 128-thread CTA owns a tile and alternates between two thread mappings
+//   thread-per-BODY : coalesced SoA loads of the body state, half kick / rotation / second kick
+//   thread-per-ATOM : coalesced loads of body-frame coordinates + atom forces, position / velocity
+//                     reconstruction, warp-shuffle segmented reduction of force and torque
+// exchanging per-body quantities (q, r, v_cm, omega) through shared memory, so the rotation update
+// and the atom scatter are ONE kernel and nothing per-body is re-read from HBM.  CTAs past the last
+// tile integrate the free atoms (velocity Verlet).  No atomics anywhere: results are bit-reproducible.
+//
+// Reference behaviour reproduced: RigidBodySystem::integratePart1/2, computeKineticEnergies
+// (openmmapi/src/RigidBodySystem.cpp:170-220); this is NOT a port of platforms/cuda/src/kernels/*.cu
+// (one thread per body, AoS, serial atom loops, host-side energy sums).
+#include "rbk_device.hpp"
+#include "rbk_step.cuh"
+
+namespace rbk {
+namespace {
+
+constexpr int kWarps = kBlock/32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ d3 loadPlane3(const double* base, size_t stride) {
+    return {base[0], base[stride], base[2*stride]};
+}
+__device__ __forceinline__ d4 loadPlane4(const double* base, size_t stride) {
+    return {base[0], base[stride], base[2*stride], base[3*stride]};
+}
+__device__ __forceinline__ void storePlane3(double* base, size_t stride, d3 v) {
+    base[0] = v.x; base[stride] = v.y; base[2*stride] = v.z;
+}
+__device__ __forceinline__ void storePlane4(double* base, size_t stride, d4 v) {
+    base[0] = v.w; base[stride] = v.x; base[2*stride] = v.y; base[3*stride] = v.z;
+}
+__device__ __forceinline__ d3 loadAtom(const AtomView& A, long long i) {
+    const double* p = A.p + i*A.sa;
+    return {p[0], p[A.sc], p[2*A.sc]};
+}
+__device__ __forceinline__ void storeAtom(const AtomView& A, long long i, d3 v) {
+    double* p = A.p + i*A.sa;
+    p[0] = v.x; p[A.sc] = v.y; p[2*A.sc] = v.z;
+}
+// plugin-order atom slot -> index in the caller's arrays
+__device__ __forceinline__ long long atomSlot(const DeviceSystem& S, int pluginIndex) {
+    return S.atomLoc ? (long long) S.atomLoc[pluginIndex] : (long long) pluginIndex;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Part 1: half kick, drift, rotation, position reconstruction (+ free atoms: half kick, drift)
+// ------------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(kBlock) part1Kernel(const DeviceSystem S, const double dt, const AtomView pos,
+                                                     const AtomView vel, const AtomView force) {
+    __shared__ double sQ[4][kBlock];
+    __shared__ double sR[3][kBlock];
+    const int tid = threadIdx.x;
+    if ((int) blockIdx.x < S.numTiles) {
+        const int b0 = S.tileBody[blockIdx.x], b1 = S.tileBody[blockIdx.x + 1];
+        if (tid < b1 - b0) {                                   // ---- thread per body
+            const size_t ld = S.bodyStride;
+            double* s = S.state + (size_t) (b0 + tid);
+            d3 r = loadPlane3(s + PL_R*ld, ld);
+            d3 p = loadPlane3(s + PL_P*ld, ld);
+            d4 q = loadPlane4(s + PL_Q*ld, ld);
+            d4 pi = loadPlane4(s + PL_PI*ld, ld);
+            const d3 F = loadPlane3(s + PL_F*ld, ld);
+            const d3 tau = loadPlane3(s + PL_TAU*ld, ld);
+            const double invm = s[PL_INVM*ld];
+            const d3 invI = loadPlane3(s + PL_INVI*ld, ld);
+            d3 I = invI;
+            if (EXACT) I = loadPlane3(s + PL_I*ld, ld);
+            bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, I, invI, r, p, q, pi);
+            storePlane3(s + PL_R*ld, ld, r);
+            storePlane3(s + PL_P*ld, ld, p);
+            storePlane4(s + PL_Q*ld, ld, q);
+            storePlane4(s + PL_PI*ld, ld, pi);
+            sQ[0][tid] = q.w; sQ[1][tid] = q.x; sQ[2][tid] = q.y; sQ[3][tid] = q.z;
+            sR[0][tid] = r.x; sR[1][tid] = r.y; sR[2][tid] = r.z;
+        }
+        __syncthreads();
+        const int a0 = S.loc[b0], a1 = S.loc[b1];              // ---- thread per atom
+        const size_t as = S.atomStride;
+        for (int a = a0 + tid; a < a1; a += kBlock) {
+            const int lb = S.localBody[a];
+            const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+            const d4 q = {sQ[0][lb], sQ[1][lb], sQ[2][lb], sQ[3][lb]};
+            const d3 r = {sR[0][lb], sR[1][lb], sR[2][lb]};
+            storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+        }
+    }
+    else {                                                     // ---- free atoms
+        const int base = ((int) blockIdx.x - S.numTiles)*kFreePerBlock + tid;
+#pragma unroll
+        for (int j = 0; j < kFreePerBlock/kBlock; j++) {
+            const int k = base + j*kBlock;
+            if (k < S.numFree) {
+                const long long gi = atomSlot(S, k);
+                d3 x = loadAtom(pos, gi), v = loadAtom(vel, gi);
+                freePart1(dt, loadAtom(force, gi), S.freeInvMass[k], x, v);
+                storeAtom(vel, gi, v);
+                storeAtom(pos, gi, x);
+                storePlane3(S.savedPos + k, S.freeStride, x);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Part 2: force/torque segmented reduction, second half kick, velocity reconstruction
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) part2Kernel(const DeviceSystem S, const double dt, const AtomView pos,
+                                                     const AtomView vel, const AtomView force) {
+    __shared__ double sQ[4][kBlock];
+    __shared__ double sAcc[6][kBlock];        // (F, tau) per body, later (v_cm, omega_space)
+    __shared__ double sHead[kWarps][6];       // partial sums of a body that started in an earlier warp's range
+    __shared__ int sHeadKey[kWarps];
+    __shared__ int sLoc[kBlock + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if ((int) blockIdx.x < S.numTiles) {
+        const int b0 = S.tileBody[blockIdx.x], b1 = S.tileBody[blockIdx.x + 1];
+        const int nb = b1 - b0;
+        const size_t ld = S.bodyStride;
+        double* s = S.state + (size_t) (b0 + tid);
+        if (tid < nb) {                                        // ---- A: thread per body, stage q
+            const d4 q = loadPlane4(s + PL_Q*ld, ld);
+            sQ[0][tid] = q.w; sQ[1][tid] = q.x; sQ[2][tid] = q.y; sQ[3][tid] = q.z;
+        }
+        if (tid < nb) sLoc[tid] = S.loc[b0 + tid];
+        if (tid == 0) sLoc[nb] = S.loc[b1];
+#pragma unroll
+        for (int k = 0; k < 6; k++) sAcc[k][tid] = 0.0;
+        if (tid < kWarps*6) sHead[tid/6][tid%6] = 0.0;
+        __syncthreads();
+
+        // ---- B: thread per atom.  Each warp walks a contiguous range of the tile's atoms in steps of
+        // 32, so that partial sums of one body are always added in the same order (deterministic).
+        const int a0 = sLoc[0], a1 = sLoc[nb];
+        const size_t as = S.atomStride;
+        const int per = ((a1 - a0 + kBlock - 1)/kBlock)*32;
+        const int wBeg = a0 + warp*per;
+        const int wEnd = min(wBeg + per, a1);
+        int firstKey = -1;
+        if (wBeg < wEnd) {
+            const int k0 = S.localBody[wBeg];
+            if (sLoc[k0] < wBeg) firstKey = k0;                // this body began in an earlier warp's range
+        }
+        if (lane == 0) sHeadKey[warp] = firstKey;
+        for (int base = wBeg; base < wEnd; base += 32) {
+            const int a = base + lane;
+            const bool valid = a < wEnd;
+            int key = 0x7fffffff;
+            double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (valid) {
+                key = S.localBody[a];
+                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+                const d3 f = loadAtom(force, atomSlot(S, S.numFree + a));
+                const d4 q = {sQ[0][key], sQ[1][key], sQ[2][key], sQ[3][key]};
+                const d3 t = cross(bodyToSpace(q, d), f);
+                v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = t.x; v[4] = t.y; v[5] = t.z;
+            }
+            // inclusive segmented scan over lanes (keys are sorted, so equal keys are contiguous)
+            for (int off = 1; off < 32 && off < S.maxBodySize; off <<= 1) {
+                const int kp = __shfl_up_sync(kFull, key, off);
+                const bool take = lane >= off && kp == key;
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const double t = __shfl_up_sync(kFull, v[k], off);
+                    if (take) v[k] += t;
+                }
+            }
+            const int kn = __shfl_down_sync(kFull, key, 1);
+            if (valid && (lane == 31 || kn != key)) {          // last lane of a segment owns its sum
+                if (key == firstKey) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) sHead[warp][k] += v[k];
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) sAcc[k][key] += v[k];
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+
+        if (tid < nb) {                                        // ---- C: thread per body, second kick
+            double sum[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) sum[k] = sAcc[k][tid];
+#pragma unroll
+            for (int w = 1; w < kWarps; w++)
+                if (sHeadKey[w] == tid) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) sum[k] += sHead[w][k];
+                }
+            const d3 F = {sum[0], sum[1], sum[2]}, tau = {sum[3], sum[4], sum[5]};
+            d3 p = loadPlane3(s + PL_P*ld, ld);
+            d4 pi = loadPlane4(s + PL_PI*ld, ld);
+            const double invm = s[PL_INVM*ld];
+            const d3 invI = loadPlane3(s + PL_INVI*ld, ld);
+            const d4 q = {sQ[0][tid], sQ[1][tid], sQ[2][tid], sQ[3][tid]};
+            d3 vcm, om;
+            bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
+            storePlane3(s + PL_P*ld, ld, p);
+            storePlane4(s + PL_PI*ld, ld, pi);
+            storePlane3(s + PL_F*ld, ld, F);
+            storePlane3(s + PL_TAU*ld, ld, tau);
+            sAcc[0][tid] = vcm.x; sAcc[1][tid] = vcm.y; sAcc[2][tid] = vcm.z;
+            sAcc[3][tid] = om.x; sAcc[4][tid] = om.y; sAcc[5][tid] = om.z;
+        }
+        __syncthreads();
+
+        for (int a = a0 + tid; a < a1; a += kBlock) {          // ---- D: thread per atom, velocities
+            const int lb = S.localBody[a];
+            const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+            const d4 q = {sQ[0][lb], sQ[1][lb], sQ[2][lb], sQ[3][lb]};
+            const d3 vcm = {sAcc[0][lb], sAcc[1][lb], sAcc[2][lb]};
+            const d3 om = {sAcc[3][lb], sAcc[4][lb], sAcc[5][lb]};
+            storeAtom(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
+        }
+    }
+    else {                                                     // ---- free atoms
+        const int base = ((int) blockIdx.x - S.numTiles)*kFreePerBlock + tid;
+#pragma unroll
+        for (int j = 0; j < kFreePerBlock/kBlock; j++) {
+            const int k = base + j*kBlock;
+            if (k < S.numFree) {
+                const long long gi = atomSlot(S, k);
+                d3 v = loadAtom(vel, gi);
+                freePart2(dt, loadAtom(force, gi), S.freeInvMass[k], loadAtom(pos, gi),
+                          loadPlane3(S.savedPos + k, S.freeStride), v);
+                storeAtom(vel, gi, v);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kinetic energies: fixed-shape two-level tree (warp shuffles -> shared -> last CTA), no atomics
+// on the data path, so the two doubles are bit-reproducible from run to run.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKinThreads = 256;
+
+__device__ __forceinline__ void blockSum2(double& a, double& b, double (*scratch)[2]) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(kFull, a, off);
+        b += __shfl_xor_sync(kFull, b, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { scratch[warp][0] = a; scratch[warp][1] = b; }
+    __syncthreads();
+    a = 0.0; b = 0.0;
+    for (int w = 0; w < kKinThreads/32; w++) { a += scratch[w][0]; b += scratch[w][1]; }
+}
+
+__global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem S, const AtomView vel, double* partial,
+                                                            unsigned* counter, double* out) {
+    __shared__ double scratch[kKinThreads/32][2];
+    __shared__ bool isLast;
+    const int g = blockIdx.x*kKinThreads + threadIdx.x, T = gridDim.x*kKinThreads;
+    double kt = 0.0, kr = 0.0;
+    const size_t ld = S.bodyStride;
+    for (int b = g; b < S.numBodies; b += T) {
+        const double* s = S.state + b;
+        double t2, r2;
+        bodyKinetic(loadPlane3(s + PL_P*ld, ld), loadPlane4(s + PL_Q*ld, ld), loadPlane4(s + PL_PI*ld, ld),
+                    s[PL_INVM*ld], loadPlane3(s + PL_INVI*ld, ld), t2, r2);
+        kt += t2;
+        kr += r2;
+    }
+    for (int k = g; k < S.numFree; k += T)
+        kt += freeKinetic(loadAtom(vel, atomSlot(S, k)), S.freeInvMass[k]);
+    blockSum2(kt, kr, scratch);
+    if (threadIdx.x == 0) {
+        partial[2*blockIdx.x] = kt;
+        partial[2*blockIdx.x + 1] = kr;
+        __threadfence();
+        isLast = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (isLast) {
+        __threadfence();
+        kt = 0.0; kr = 0.0;
+        for (int i = threadIdx.x; i < (int) gridDim.x; i += kKinThreads) {
+            kt += __ldcg(partial + 2*i);
+            kr += __ldcg(partial + 2*i + 1);
+        }
+        blockSum2(kt, kr, scratch);
+        if (threadIdx.x == 0) {
+            out[0] = 0.5*kt;
+            out[1] = 0.5*kr;
+            *counter = 0u;
+        }
+    }
+}
+
+int gridFor(const DeviceSystem& S) { return S.numTiles + S.numFreeBlocks; }
+
+} // namespace
+
+cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    const int grid = gridFor(S);
+    if (grid == 0) return cudaSuccess;
+    if (S.rotationMode == 0) part1Kernel<true><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    else part1Kernel<false><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    return cudaGetLastError();
+}
+
+cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    const int grid = gridFor(S);
+    if (grid == 0) return cudaSuccess;
+    part2Kernel<<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    return cudaGetLastError();
+}
+
+cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out,
+                          cudaStream_t st) {
+    kineticKernel<<<kKineticBlocks, kKinThreads, 0, st>>>(S, vel, partial, counter, out);
+    return cudaGetLastError();
+}
+
+} // namespace rbk

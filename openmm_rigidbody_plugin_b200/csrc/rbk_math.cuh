@@ -1,0 +1,328 @@
+// rbk_math.cuh - device math of the rigid-body step: quaternion algebra, NO-SQUISH and exact
+// free-rotor propagation.  fp64 throughout, IEEE division/sqrt (never compile with fast-math:
+// symmetric tops rely on x/0 = inf semantics, cf. openmmapi/src/RigidBody.cpp:254-259).
+//
+// What is computed follows the reference's host arithmetic (the parity target):
+//   quaternion operators      openmmapi/src/MatVec.cpp:495-549
+//   uniaxial / NO-SQUISH      openmmapi/src/RigidBody.cpp:189-231
+//   exact rotation            openmmapi/src/RigidBody.cpp:241-308
+//   Jacobi / Carlson          openmmapi/include/internal/ellipticFunctions.h:34-245
+// How it is computed is organised for the GPU (registers instead of heap objects, fixed-size
+// state, reciprocal reuse); results agree with the reference to rounding level.
+#pragma once
+#include <cfloat>
+#include <math.h>
+
+// The same source is compiled for the device by nvcc and (for CPU unit tests of the arithmetic
+// only, tests/test_device_math_host.py) for the host by g++.
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define RBK_HD __host__ __device__ __forceinline__
+#define RBK_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RBK_HD inline
+#define RBK_HD_NOINLINE inline
+#endif
+
+namespace rbk {
+
+RBK_HD double rsqrtd(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0/sqrt(x);
+#endif
+}
+
+struct d3 { double x, y, z; };
+struct d4 { double w, x, y, z; };     // scalar-first quaternion (q0,q1,q2,q3)
+
+RBK_HD d3 operator+(d3 a, d3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+RBK_HD d3 operator-(d3 a, d3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+RBK_HD d3 operator*(d3 a, double s) { return {a.x*s, a.y*s, a.z*s}; }
+RBK_HD double dot(d3 a, d3 b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
+RBK_HD d3 cross(d3 a, d3 b) { return {a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x}; }
+RBK_HD d4 operator+(d4 a, d4 b) { return {a.w + b.w, a.x + b.x, a.y + b.y, a.z + b.z}; }
+RBK_HD d4 operator*(d4 a, double s) { return {a.w*s, a.x*s, a.y*s, a.z*s}; }
+RBK_HD double dot(d4 a, d4 b) { return a.w*b.w + a.x*b.x + a.y*b.y + a.z*b.z; }
+
+// B(q)v = q (x) (0,v),  C(q)v = (0,v) (x) q  and their transposes
+RBK_HD d4 quatB(d4 q, d3 v) {
+    return {-q.x*v.x - q.y*v.y - q.z*v.z,
+             q.w*v.x - q.z*v.y + q.y*v.z,
+             q.z*v.x + q.w*v.y - q.x*v.z,
+            -q.y*v.x + q.x*v.y + q.w*v.z};
+}
+RBK_HD d4 quatC(d4 q, d3 v) {
+    return {-q.x*v.x - q.y*v.y - q.z*v.z,
+             q.w*v.x + q.z*v.y - q.y*v.z,
+            -q.z*v.x + q.w*v.y + q.x*v.z,
+             q.y*v.x - q.x*v.y + q.w*v.z};
+}
+RBK_HD d3 quatBt(d4 q, d4 y) {
+    return {-q.x*y.w + q.w*y.x + q.z*y.y - q.y*y.z,
+            -q.y*y.w - q.z*y.x + q.w*y.y + q.x*y.z,
+            -q.z*y.w + q.y*y.x - q.x*y.y + q.w*y.z};
+}
+RBK_HD d3 quatCt(d4 q, d4 y) {
+    return {-q.x*y.w + q.w*y.x - q.z*y.y + q.y*y.z,
+            -q.y*y.w + q.z*y.x + q.w*y.y - q.x*y.z,
+            -q.z*y.w - q.y*y.x + q.x*y.y + q.w*y.z};
+}
+// body frame -> space frame: A^T(q) v = C^T(q) B(q) v
+RBK_HD d3 bodyToSpace(d4 q, d3 v) { return quatCt(q, quatB(q, v)); }
+
+// permutation operators B_k q (k = 0,1,2 for principal axes 1,2,3)
+template <int K> RBK_HD d4 quatPerm(d4 q) {
+    if (K == 0) return {-q.x,  q.w,  q.z, -q.y};
+    if (K == 1) return {-q.y, -q.z,  q.w,  q.x};
+    return {-q.z,  q.y, -q.x,  q.w};
+}
+
+// One uniaxial free rotation about principal axis K for time h.
+template <int K> RBK_HD void uniaxial(double h, double invIk, d4& q, d4& pi) {
+    d4 Bq = quatPerm<K>(q);
+    double phi = 0.25*dot(pi, Bq)*h*invIk;
+    double s, c;
+    sincos(phi, &s, &c);
+    d4 Bp = quatPerm<K>(pi);
+    q = q*c + Bq*s;
+    pi = pi*c + Bp*s;
+}
+
+// NO-SQUISH: n sub-steps of R3(h/2) R2(h/2) R1(h) R2(h/2) R3(h/2); axis 3 skipped for linear bodies.
+RBK_HD void noSquish(double dt, int n, d3 invI, d4& q, d4& pi) {
+    const double h = dt/n, hh = 0.5*h;
+    const bool axis3 = invI.z != 0.0;            // dof == 6 (linear bodies carry invI.z = 0)
+    for (int i = 0; i < n; i++) {
+        if (axis3) uniaxial<2>(hh, invI.z, q, pi);
+        uniaxial<1>(hh, invI.y, q, pi);
+        uniaxial<0>(h, invI.x, q, pi);
+        uniaxial<1>(hh, invI.y, q, pi);
+        if (axis3) uniaxial<2>(hh, invI.z, q, pi);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Elliptic functions
+// ---------------------------------------------------------------------------------------------
+RBK_HD double sgn(double x) { return x >= 0.0 ? 1.0 : -1.0; }
+
+// sn, cn, dn (u | m) by the arithmetic-geometric-mean scale + descending Landen recurrence.
+RBK_HD_NOINLINE void jacobiSnCnDn(double u, double m, double& sn, double& cn, double& dn) {
+    const double EPS = DBL_EPSILON;
+    if (fabs(m) > 1.0) { sn = cn = dn = nan(""); return; }
+    if (fabs(m) < 2.0*EPS) { sincos(u, &sn, &cn); dn = 1.0; return; }
+    if (fabs(m - 1.0) < 2.0*EPS) { sn = tanh(u); cn = 1.0/cosh(u); dn = cn; return; }
+    double mu[16], nu[16];
+    int n = 0;
+    mu[0] = 1.0;
+    nu[0] = sqrt(1.0 - m);
+    const double kp = nu[0];
+    while (fabs(mu[n] - nu[n]) > 4.0*EPS*fabs(mu[n] + nu[n])) {
+        mu[n+1] = 0.5*(mu[n] + nu[n]);
+        nu[n+1] = sqrt(mu[n]*nu[n]);
+        ++n;
+        if (n >= 15) { sn = cn = dn = nan(""); return; }
+    }
+    double s, co;
+    sincos(u*mu[n], &s, &co);
+    const bool small = fabs(s) < fabs(co);
+    double c = mu[n]*(small ? s/co : co/s);
+    double d = 1.0;
+    while (n > 0) {
+        n--;
+        double r = (c*c)/mu[n+1];
+        c = d*c;
+        d = (r + nu[n])/(r + mu[n]);
+    }
+    const double h = rsqrtd(1.0 + c*c);            // 1/hypot(1,c); |c| <= 1 here
+    if (small) {
+        dn = kp/d;
+        cn = dn*sgn(co)*h;
+        sn = cn*c/kp;
+    }
+    else {
+        dn = d;
+        sn = sgn(s)*h;
+        cn = c*sn;
+    }
+}
+
+// Carlson's degenerate integral RC(x,y) by duplication (tolerance as the reference: 1e-3 -> ~1e-18 truncation)
+RBK_HD double carlsonRC(double x, double y) {
+    if (x < 0.0 || y < 0.0 || x + y < 5.0*DBL_MIN || x > 0.2*DBL_MAX || y > 0.2*DBL_MAX) return nan("");
+    double mu, sn;
+    for (int it = 0; ; ) {
+        mu = (x + y + y)/3.0;
+        sn = (y + mu)/mu - 2.0;
+        if (fabs(sn) < 0.001) break;
+        double lam = 2.0*sqrt(x)*sqrt(y) + y;
+        x = (x + lam)*0.25;
+        y = (y + lam)*0.25;
+        if (++it == 10000) return nan("");
+    }
+    double s = sn*sn*(0.3 + sn*(1.0/7.0 + sn*(0.375 + sn*(9.0/22.0))));
+    return (1.0 + s)*rsqrtd(mu);
+}
+
+// Carlson's RF(x,y,z) by duplication
+RBK_HD_NOINLINE double carlsonRF(double x, double y, double z) {
+    const double lolim = 5.0*DBL_MIN, uplim = 0.2*DBL_MAX;
+    if (x < 0.0 || y < 0.0 || z < 0.0 || x + y < lolim || x + z < lolim || y + z < lolim ||
+        x > uplim || y > uplim || z > uplim) return nan("");
+    double mu, xd, yd, zd;
+    for (int it = 0; ; ) {
+        mu = (x + y + z)/3.0;
+        const double rmu = 1.0/mu;
+        xd = 2.0 - (mu + x)*rmu;
+        yd = 2.0 - (mu + y)*rmu;
+        zd = 2.0 - (mu + z)*rmu;
+        if (fmax(fabs(xd), fmax(fabs(yd), fabs(zd))) < 0.001) break;
+        double xr = sqrt(x), yr = sqrt(y), zr = sqrt(z);
+        double lam = xr*(yr + zr) + yr*zr;
+        x = (x + lam)*0.25;
+        y = (y + lam)*0.25;
+        z = (z + lam)*0.25;
+        if (++it == 10000) return nan("");
+    }
+    double e2 = xd*yd - zd*zd;
+    double e3 = xd*yd*zd;
+    double s = 1.0 + ((1.0/24.0)*e2 - 0.1 - (3.0/44.0)*e3)*e2 + (1.0/14.0)*e3;
+    return s*rsqrtd(mu);
+}
+
+// Carlson's RJ(x,y,z,p) by duplication
+RBK_HD_NOINLINE double carlsonRJ(double x, double y, double z, double p) {
+    const double lolim = 4.809554074311741e-103;      // (5 DBL_MIN)^(1/3)
+    const double uplim = 9.901548214916537e+101;      // 0.3 (0.2 DBL_MAX)^(1/3)
+    if (x < 0.0 || y < 0.0 || z < 0.0 || x + y < lolim || x + z < lolim || y + z < lolim || p < lolim ||
+        x > uplim || y > uplim || z > uplim || p > uplim) return nan("");
+    const double c1 = 3.0/14.0, c2 = 1.0/3.0, c3 = 3.0/22.0, c4 = 3.0/26.0;
+    double sigma = 0.0, power4 = 1.0, mu, xd, yd, zd, pd;
+    for (int it = 0; ; ) {
+        mu = (x + y + z + p + p)*0.2;
+        const double rmu = 1.0/mu;
+        xd = (mu - x)*rmu;
+        yd = (mu - y)*rmu;
+        zd = (mu - z)*rmu;
+        pd = (mu - p)*rmu;
+        if (fmax(fmax(fabs(xd), fabs(yd)), fmax(fabs(zd), fabs(pd))) < 0.001) break;
+        double xr = sqrt(x), yr = sqrt(y), zr = sqrt(z);
+        double lam = xr*(yr + zr) + yr*zr;
+        double alfa = p*(xr + yr + zr) + xr*yr*zr;
+        alfa = alfa*alfa;
+        double beta = p*(p + lam)*(p + lam);
+        double rc = carlsonRC(alfa, beta);
+        if (isnan(rc)) return nan("");
+        sigma += power4*rc;
+        power4 *= 0.25;
+        x = (x + lam)*0.25;
+        y = (y + lam)*0.25;
+        z = (z + lam)*0.25;
+        p = (p + lam)*0.25;
+        if (++it == 10000) return nan("");
+    }
+    double ea = xd*(yd + zd) + yd*zd;
+    double eb = xd*yd*zd;
+    double ec = pd*pd;
+    double e2 = ea - 3.0*ec;
+    double e3 = eb + 2.0*pd*(ea - ec);
+    double s1 = 1.0 + e2*(-c1 + 0.75*c3*e2 - 1.5*c4*e3);
+    double s2 = eb*(0.5*c2 + pd*(-c3 - c3 + pd*c4));
+    double s3 = pd*ea*(c2 - pd*c3) - c2*pd*ec;
+    return 3.0*sigma + power4*(s1 + s2 + s3)/(mu*sqrt(mu));
+}
+
+// Omega(x; n, m) = Pi(n; asin x | m) - F(asin x | m) expressed through RJ
+RBK_HD double omegaRJ(double x, double n, double m) {
+    const double x2 = x*x;
+    return (-1.0/3.0)*n*x*x2*carlsonRJ(1.0 - x2, 1.0 - m*x2, 1.0, 1.0 + n*x2);
+}
+
+RBK_HD int roundHalfIn(double x) {       // nearest integer, halves towards zero
+    return x > 0.0 ? (int) ceil(x - 0.5) : (int) floor(x + 0.5);
+}
+
+// Exact torque-free rotation of an asymmetric top over dt (general path through the complete set of
+// elliptic integrals).  I, invI: principal moments (descending) and inverses; q, pi updated in place.
+RBK_HD_NOINLINE void exactRotationElliptic(double dt, d3 I, d3 invI, d4& q, d4& pi) {
+    d3 Iw = quatBt(q, pi)*0.5;
+    const d3 w0 = {invI.x*Iw.x, invI.y*Iw.y, invI.z*Iw.z};
+    double Lsq = Iw.y*Iw.y + Iw.z*Iw.z;
+    if (Lsq < DBL_EPSILON) { uniaxial<0>(dt, invI.x, q, pi); return; }
+    Lsq += Iw.x*Iw.x;
+    const double L = sqrt(Lsq);
+    const double twoKr = dot(Iw, w0);
+    const d4 z0 = {Iw.z, Iw.y, L - Iw.x, 0.0};
+    const double r1 = Lsq - twoKr*I.z;
+    const double r3 = twoKr*I.x - Lsq;
+    const double l1 = r1*invI.y/(I.y - I.z);
+    const double l3 = r3*invI.y/(I.x - I.y);
+    const bool lowBranch = l1 < l3;
+    const double lmin = (l3 < l1) ? l3 : l1;
+    const double lmax = (l1 < l3) ? l3 : l1;
+    const double c13 = 1.0/(I.x - I.z);
+    double a0 = sgn(w0.x)*sqrt(r1*invI.x*c13);
+    double a1 = sqrt(lmin);
+    double a2 = sgn(w0.z)*sqrt(r3*invI.z*c13);
+    const double m = lmin/lmax;
+    const double K = carlsonRF(0.0, 1.0 - m, 1.0);
+    const double inv2K = 0.5/K;
+    double s0 = w0.y/a1, c0, u0;
+    int i0;
+    if (fabs(s0) < 1.0) {
+        c0 = lowBranch ? w0.x/a0 : w0.z/a2;
+        u0 = s0*carlsonRF(1.0 - s0*s0, 1.0 - m*s0*s0, 1.0);
+        i0 = roundHalfIn(u0*inv2K);
+    }
+    else {
+        a1 = fabs(w0.y);
+        s0 = sgn(s0);
+        c0 = 0.0;
+        u0 = s0*K;
+        i0 = 0;
+    }
+    const double wp = -invI.y*a0*a2/(a1*c13);
+    const double u = wp*dt + u0;
+    const int jump = roundHalfIn(u*inv2K) - i0;
+    double sn, cn, dn, deltaF;
+    jacobiSnCnDn(u, m, sn, cn, dn);
+    const double alpha = I.x*a0/L;
+    double eta = alpha*alpha;
+    eta /= 1.0 - eta;
+    const d3 Ia = {I.x*a0, I.y*a1, I.z*a2};
+    if (lowBranch) {
+        const double C = sqrt(m + eta);
+        deltaF = u - u0 + sgn(cn)*omegaRJ(sn, eta, m) - sgn(c0)*omegaRJ(s0, eta, m)
+                        + (alpha/C)*(atan(C*sn/dn) - atan(C*s0*a2/w0.z));
+        if (jump != 0) deltaF += jump*2.0*omegaRJ(1.0, eta, m);
+        Iw = {Ia.x*cn, Ia.y*sn, Ia.z*dn};
+    }
+    else {
+        const double k2eta = m*eta;
+        const double C = sqrt(1.0 + k2eta);
+        deltaF = u - u0 + sgn(cn)*omegaRJ(sn, k2eta, m) - sgn(c0)*omegaRJ(s0, k2eta, m)
+                        + (alpha/C)*(atan(C*sn/cn) - atan(C*s0/c0));
+        if (jump != 0) deltaF += jump*(2.0*omegaRJ(1.0, k2eta, m) + (alpha/C)*3.14159265358979323846264338328);
+        Iw = {Ia.x*dn, Ia.y*sn, Ia.z*cn};
+    }
+    deltaF *= 1.0 + eta;
+    const double theta = (Lsq*(u - u0) + r3*deltaF)/(2.0*L*I.x*wp);
+    double st, ct;
+    sincos(theta, &st, &ct);
+    const d4 za = {Iw.z, Iw.y, L - Iw.x, 0.0};
+    const d4 zb = {-Iw.y, Iw.z, 0.0, L - Iw.x};
+    const d4 z = za*ct + zb*st;
+    d4 qn = z*dot(z0, q) + quatC(z, quatCt(z0, q));
+    qn = qn*(1.0/sqrt(dot(qn, qn)));
+    q = qn;
+    pi = quatB(qn, Iw*2.0);
+}
+
+// Mode 0 entry point used by the step.
+RBK_HD void exactRotation(double dt, d3 I, d3 invI, d4& q, d4& pi) {
+    exactRotationElliptic(dt, I, invI, q, pi);
+}
+
+} // namespace rbk

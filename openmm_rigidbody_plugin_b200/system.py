@@ -1,0 +1,160 @@
+"""Thin object wrapper over the C ABI: one `DeviceRigidBodySystem` = one rbk_system handle.
+
+Device arrays are passed as torch CUDA tensors (float64) or raw device pointers; torch is only the
+allocator / stream provider here, the arithmetic is librbk's CUDA kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import RBK_LAYOUT_SOA, RBK_LAYOUT_VEC3, RbkError, check  # noqa: F401
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _host(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(t):
+    """Device (or pinned host) pointer of a torch tensor / int / None."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(stream):
+    if stream is None:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        except ImportError:
+            pass
+        return None
+    return C.c_void_p(int(stream))
+
+
+def _layout(t, layout):
+    """(layout, stride) for a tensor: [N,3] contiguous -> VEC3; [3,N] contiguous -> SOA with stride N."""
+    if layout is not None:
+        return layout
+    shape = tuple(t.shape)
+    if len(shape) == 2 and shape[1] == 3:
+        return (RBK_LAYOUT_VEC3, 0)
+    if len(shape) == 2 and shape[0] == 3:
+        return (RBK_LAYOUT_SOA, shape[1])
+    raise ValueError("atom arrays must be [N,3] (Vec3) or [3,N] (SoA planes)")
+
+
+class DeviceRigidBodySystem:
+    def __init__(self, bodyIndices, masses, rotationMode=0, isVirtual=None, constraints=None):
+        self.lib = _lib.load()
+        bi = np.ascontiguousarray(bodyIndices, dtype=np.int32)
+        ms = np.ascontiguousarray(masses, dtype=np.float64)
+        if bi.ndim != 1 or bi.shape != ms.shape:
+            raise ValueError("bodyIndices and masses must be 1-D and of equal length")
+        self.numAtoms = int(bi.shape[0])
+        iv = None if isVirtual is None else np.ascontiguousarray(isVirtual, dtype=np.uint8).tobytes()
+        cons = np.zeros((0, 2), np.int32) if constraints is None else np.ascontiguousarray(constraints, dtype=np.int32).reshape(-1, 2)
+        h = C.c_void_p()
+        check(self.lib.rbk_create(self.numAtoms, _i(bi), _d(ms), iv, int(cons.shape[0]), _i(cons), int(rotationMode), C.byref(h)))
+        self.h = h
+        self.rotationMode = int(rotationMode)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rbk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host model
+    def counts(self):
+        out = np.zeros(5, np.int32)
+        check(self.lib.rbk_get_counts(self.h, _i(out)))
+        return dict(zip(["numBodies", "numFree", "numActualAtoms", "numBodyAtoms", "numDOF"], out.tolist()))
+
+    def body_index(self):
+        out = np.zeros(self.numAtoms, np.int32)
+        check(self.lib.rbk_get_body_index(self.h, _i(out)))
+        return out
+
+    def atom_index(self):
+        out = np.zeros(self.counts()["numActualAtoms"], np.int32)
+        check(self.lib.rbk_get_atom_index(self.h, _i(out)))
+        return out
+
+    def update(self, R=None, V=None, F=None, geometry=True, velocities=True):
+        R, V, F = _host(R), _host(V), _host(F)
+        check(self.lib.rbk_update(self.h, _d(R), _d(V), _d(F), int(geometry), int(velocities)))
+
+    def host_bodies(self):
+        nb = self.counts()["numBodies"]
+        o = {
+            "N": np.zeros(nb, np.int32), "dof": np.zeros(nb, np.int32), "loc": np.zeros(nb, np.int32),
+            "mass": np.zeros(nb), "I": np.zeros((nb, 3)), "invI": np.zeros((nb, 3)), "rcm": np.zeros((nb, 3)),
+            "pcm": np.zeros((nb, 3)), "q": np.zeros((nb, 4)), "pi": np.zeros((nb, 4)), "force": np.zeros((nb, 3)),
+            "torque": np.zeros((nb, 4)), "twoK": np.zeros((nb, 2)),
+        }
+        check(self.lib.rbk_get_host_bodies(self.h, _i(o["N"]), _i(o["dof"]), _i(o["loc"]),
+                                           *[_d(o[k]) for k in ("mass", "I", "invI", "rcm", "pcm", "q", "pi", "force", "torque", "twoK")]))
+        return o
+
+    def body_fixed(self):
+        d = np.zeros((self.counts()["numBodyAtoms"], 3))
+        check(self.lib.rbk_get_body_fixed(self.h, _d(d)))
+        return d
+
+    # ---- device
+    def upload(self, stream=None):
+        check(self.lib.rbk_upload(self.h, _stream(stream)))
+
+    def set_atom_location(self, location=None, stream=None):
+        loc = None if location is None else np.ascontiguousarray(location, dtype=np.int32)
+        check(self.lib.rbk_set_atom_location(self.h, _i(loc), _stream(stream)))
+
+    def part1(self, dt, pos, vel, force, layout=None, stream=None):
+        lay, stride = _layout(pos, layout)
+        check(self.lib.rbk_part1(self.h, float(dt), _ptr(pos), _ptr(vel), _ptr(force), lay, stride, _stream(stream)))
+
+    def part2(self, dt, pos, vel, force, layout=None, stream=None):
+        lay, stride = _layout(pos, layout)
+        check(self.lib.rbk_part2(self.h, float(dt), _ptr(pos), _ptr(vel), _ptr(force), lay, stride, _stream(stream)))
+
+    def kinetic(self, vel, layout=None, stream=None):
+        lay, stride = _layout(vel, layout)
+        out = np.zeros(2)
+        check(self.lib.rbk_kinetic(self.h, _ptr(vel), lay, stride, _d(out), _stream(stream)))
+        return out
+
+    def download_bodies(self, stream=None):
+        nb = self.counts()["numBodies"]
+        o = {"rcm": np.zeros((nb, 3)), "pcm": np.zeros((nb, 3)), "q": np.zeros((nb, 4)), "pi": np.zeros((nb, 4)),
+             "force": np.zeros((nb, 3)), "torque": np.zeros((nb, 4))}
+        check(self.lib.rbk_download_bodies(self.h, *[_d(o[k]) for k in ("rcm", "pcm", "q", "pi", "force", "torque")], _stream(stream)))
+        return o
+
+    def execute_host(self, dt, steps, R, V, F, forces=None, stream=None):
+        """R, V, F: host float64 buffers [N,3] (numpy arrays or pinned torch CPU tensors), updated in place."""
+        cb = _lib.FORCE_FN(forces) if forces is not None else C.cast(None, _lib.FORCE_FN)
+        check(self.lib.rbk_execute_host(self.h, float(dt), int(steps), _ptr(R), _ptr(V), _ptr(F), cb, None, _stream(stream)))

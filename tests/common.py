@@ -90,3 +90,130 @@ def edge_cases():
     cases["symmetric_top"] = (mk([1] * 6, masses=[3.0] * 4 + [12.0] * 2, R=Rrot), [0, 2])
     # massless-free handling is reference-undefined; virtual sites are covered by a separate test
     return cases
+
+
+class GpuStepper:
+    """Same call protocol as oracle.checkers.CpuStepper, but every step runs librbk's CUDA kernels
+    through the C ABI.  layout: 'vec3' ([N,3] like std::vector<Vec3>) or 'soa' ([3,N] planes).
+    shuffle=True stores the atoms in a permuted order and hands the permutation to
+    rbk_set_atom_location (the CUDA platform's atom reordering)."""
+
+    def __init__(self, bodyIndices, masses, mode=0, layout="vec3", shuffle=False, isVirtual=None, constraints=None, seed=5):
+        import torch
+        from openmm_rigidbody_plugin_b200 import DeviceRigidBodySystem
+        self.torch = torch
+        self.dev = torch.device("cuda:0")
+        self.sys = DeviceRigidBodySystem(bodyIndices, masses, mode, isVirtual=isVirtual, constraints=constraints)
+        self.n = len(masses)
+        self.layout = layout
+        self.perm = None
+        if shuffle:
+            self.perm = np.random.Generator(np.random.Philox(key=seed)).permutation(self.n)   # atom i lives at perm[i]
+        self.hR = np.zeros((self.n, 3))
+        self.hV = np.zeros((self.n, 3))
+        self.hF = np.zeros((self.n, 3))
+        self.dR = self.dV = self.dF = None
+        self.tether = None
+        self.uploaded = False
+
+    # host <-> device helpers -------------------------------------------------------------
+    def _to_dev(self, a):
+        t = self.torch
+        if self.perm is not None:
+            b = np.empty_like(a)
+            b[self.perm] = a
+            a = b
+        x = t.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        return x.t().contiguous() if self.layout == "soa" else x.contiguous()
+
+    def _to_host(self, x):
+        a = (x.t() if self.layout == "soa" else x).contiguous().cpu().numpy()
+        return a[self.perm] if self.perm is not None else a
+
+    def _natural(self, x):
+        """device tensor as [N,3] in ORIGINAL atom order (torch, on device)"""
+        a = x.t() if self.layout == "soa" else x
+        if self.perm is not None:
+            a = a[self.torch.from_numpy(self.perm).to(self.dev)]
+        return a
+
+    def set_state(self, R=None, V=None, F=None):
+        if R is not None:
+            self.hR = np.array(R, dtype=np.float64)
+            self.dR = self._to_dev(self.hR)
+        if V is not None:
+            self.hV = np.array(V, dtype=np.float64)
+            self.dV = self._to_dev(self.hV)
+        if F is not None:
+            self.hF = np.array(F, dtype=np.float64)
+            self.dF = self._to_dev(self.hF)
+
+    def get_state(self):
+        return self._to_host(self.dR), self._to_host(self.dV), self._to_host(self.dF)
+
+    def set_tether(self, k, E, charges, x0):
+        t = self.torch
+        self.tether = (float(k), t.tensor(np.asarray(E), dtype=t.float64, device=self.dev),
+                       t.from_numpy(np.ascontiguousarray(charges)).to(self.dev),
+                       t.from_numpy(np.ascontiguousarray(x0)).to(self.dev))
+
+    def compute_forces(self):
+        """Analytic test potential evaluated on the device with the same operation order as the CPU checkers."""
+        k, E, ch, x0 = self.tether
+        x = self._natural(self.dR)
+        dx = x - x0
+        F = dx * (-k) + E[None, :] * ch[:, None]
+        U = (0.5 * k * (dx * dx).sum(1) - ch * (x * E[None, :]).sum(1)).sum()
+        Fh = F
+        if self.perm is not None:
+            inv = self.torch.empty_like(F)
+            inv[self.torch.from_numpy(self.perm).to(self.dev)] = F
+            Fh = inv
+        self.dF.copy_(Fh.t() if self.layout == "soa" else Fh)
+        return float(U)
+
+    def update(self, geometry=True, velocities=True):
+        R, V, F = self.get_state() if self.dR is not None else (self.hR, self.hV, self.hF)
+        self.sys.update(R, V, F, geometry, velocities)
+        self.sys.upload()
+        if self.perm is not None:
+            loc = self.perm[self.sys.atom_index()].astype(np.int32)
+            self.sys.set_atom_location(loc)
+        self.uploaded = True
+
+    def part1(self, dt):
+        self.sys.part1(dt, self.dR, self.dV, self.dF)
+
+    def part2(self, dt):
+        self.sys.part2(dt, self.dR, self.dV, self.dF)
+
+    def step(self, dt, steps=1):
+        for _ in range(steps):
+            self.sys.part1(dt, self.dR, self.dV, self.dF)
+            if self.tether is not None:
+                self.compute_forces()
+            self.sys.part2(dt, self.dR, self.dV, self.dF)
+
+    def kinetic(self):
+        return self.sys.kinetic(self.dV)
+
+    def counts(self):
+        return self.sys.counts()
+
+    def body_index(self):
+        return self.sys.body_index()
+
+    def atom_index(self):
+        return self.sys.atom_index()
+
+    def bodies(self):
+        b = self.sys.host_bodies()
+        if self.uploaded:
+            b.update(self.sys.download_bodies())
+        return b
+
+    def body_fixed(self):
+        return self.sys.body_fixed()
+
+    def close(self):
+        self.sys.close()
