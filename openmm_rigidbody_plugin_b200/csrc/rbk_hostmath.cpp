@@ -17,9 +17,29 @@ void rbkh_exact_rotation(double dt, const double* I, double* q, double* pi, int 
     d3 Iv = {I[0], I[1], I[2]}, inv = {1.0/I[0], 1.0/I[1], 1.0/I[2]};
     d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};
     if (elliptic_only) exactRotationElliptic(dt, Iv, inv, qq, pp);
-    else exactRotation(dt, Iv, inv, qq, pp);
+    else exactRotation(dt, inv, qq, pp);
     q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z;
     pi[0] = pp.w; pi[1] = pp.x; pi[2] = pp.y; pi[3] = pp.z;
+}
+
+// Series fast path alone with a chosen order; returns 1 when its truncation check passed.
+int rbkh_exact_series(int order, double dt, const double* I, double* q, double* pi) {
+    d3 inv = {1.0/I[0], 1.0/I[1], 1.0/I[2]};
+    d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};
+    bool ok = false;
+    switch (order) {
+    case 6: ok = exactRotationSeries<6>(dt, inv, qq, pp); break;
+    case 8: ok = exactRotationSeries<8>(dt, inv, qq, pp); break;
+    case 10: ok = exactRotationSeries<10>(dt, inv, qq, pp); break;
+    case 12: ok = exactRotationSeries<12>(dt, inv, qq, pp); break;
+    case 14: ok = exactRotationSeries<14>(dt, inv, qq, pp); break;
+    case 16: ok = exactRotationSeries<16>(dt, inv, qq, pp); break;
+    case 20: ok = exactRotationSeries<20>(dt, inv, qq, pp); break;
+    default: return -1;
+    }
+    q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z;
+    pi[0] = pp.w; pi[1] = pp.x; pi[2] = pp.y; pi[3] = pp.z;
+    return ok ? 1 : 0;
 }
 
 void rbkh_nosquish(double dt, int n, const double* invI, double* q, double* pi) {
@@ -36,8 +56,9 @@ void rbkh_body_part1(int mode, double dt, const double* F, const double* tau, do
     d3 rr = {r[0], r[1], r[2]}, pp = {p[0], p[1], p[2]};
     d4 qq = {q[0], q[1], q[2], q[3]}, pq = {pi[0], pi[1], pi[2], pi[3]};
     d3 Fv = {F[0], F[1], F[2]}, tv = {tau[0], tau[1], tau[2]}, Iv = {I[0], I[1], I[2]}, inv = {invI[0], invI[1], invI[2]};
-    if (mode == 0) bodyPart1<true>(dt, 0, Fv, tv, invm, Iv, inv, rr, pp, qq, pq);
-    else bodyPart1<false>(dt, mode, Fv, tv, invm, Iv, inv, rr, pp, qq, pq);
+    (void) Iv;
+    if (mode == 0) bodyPart1<true>(dt, 0, Fv, tv, invm, inv, rr, pp, qq, pq);
+    else bodyPart1<false>(dt, mode, Fv, tv, invm, inv, rr, pp, qq, pq);
     r[0] = rr.x; r[1] = rr.y; r[2] = rr.z; p[0] = pp.x; p[1] = pp.y; p[2] = pp.z;
     q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z; pi[0] = pq.w; pi[1] = pq.x; pi[2] = pq.y; pi[3] = pq.z;
 }

@@ -68,9 +68,7 @@ __global__ void __launch_bounds__(kBlock) part1Kernel(const DeviceSystem S, cons
             const d3 tau = loadPlane3(s + PL_TAU*ld, ld);
             const double invm = s[PL_INVM*ld];
             const d3 invI = loadPlane3(s + PL_INVI*ld, ld);
-            d3 I = invI;
-            if (EXACT) I = loadPlane3(s + PL_I*ld, ld);
-            bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, I, invI, r, p, q, pi);
+            bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
             storePlane3(s + PL_R*ld, ld, r);
             storePlane3(s + PL_P*ld, ld, p);
             storePlane4(s + PL_Q*ld, ld, q);

@@ -320,8 +320,84 @@ RBK_HD_NOINLINE void exactRotationElliptic(double dt, d3 I, d3 invI, d4& q, d4& 
     pi = quatB(qn, Iw*2.0);
 }
 
-// Mode 0 entry point used by the step.
-RBK_HD void exactRotation(double dt, d3 I, d3 invI, d4& q, d4& pi) {
+// ---------------------------------------------------------------------------------------------
+// Exact torque-free rotation, fast path: Taylor series of Euler's equations.
+//
+// In the body frame the angular momentum l(t) obeys dl/dt = l x (l/I) (quadratic right-hand side), so
+// its Taylor coefficients in s = t/dt follow from three Cauchy products per order.  The reference's
+// rotation angle (RigidBody.cpp:286-302) is, after inserting its Omega/atan terms and simplifying with
+// 1+eta = 1/(1-alpha^2) and alpha*cn (resp. alpha*dn) = l0/L, nothing but
+//        theta(dt) = 1/2 * Int_0^dt [ L/I0 + (2T - L^2/I0) / (L - l0(t)) ] dt
+// in BOTH of its branches, so theta needs only the reciprocal series of L - l0(s), integrated term by
+// term.  No elliptic function, no division inside the recurrences, no data-dependent loop: ~2 K^2 FMAs.
+// The series are mathematically exact; truncation is checked at run time from the size of the last
+// terms and the caller falls back to exactRotationElliptic when the check fails (large |omega| dt).
+// Also valid where the elliptic route is not (symmetric, spherical and linear tops).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
+    const d3 l0 = quatBt(q, pi)*0.5;
+    if (l0.y*l0.y + l0.z*l0.z < DBL_EPSILON) { uniaxial<0>(dt, invI.x, q, pi); return true; }
+    const double Lsq = l0.y*l0.y + l0.z*l0.z + l0.x*l0.x;
+    const double L = sqrt(Lsq);
+    const double twoT = l0.x*l0.x*invI.x + l0.y*l0.y*invI.y + l0.z*l0.z*invI.z;
+    double x[K + 1], y[K + 1], z[K + 1], r[K + 1];
+    x[0] = l0.x; y[0] = l0.y; z[0] = l0.z;
+    const double ca = dt*(invI.z - invI.y), cb = dt*(invI.x - invI.z), cc = dt*(invI.y - invI.x);
+    r[0] = 1.0/(L - x[0]);
+    double sx = x[0], sy = y[0], sz = z[0], sr = r[0];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double px = 0.0, py = 0.0, pz = 0.0;
+#pragma unroll
+        for (int j = 0; j <= k; j++) {
+            px = fma(y[j], z[k - j], px);
+            py = fma(z[j], x[k - j], py);
+            pz = fma(x[j], y[k - j], pz);
+        }
+        const double f = 1.0/(k + 1);
+        x[k + 1] = (ca*f)*px;
+        y[k + 1] = (cb*f)*py;
+        z[k + 1] = (cc*f)*pz;
+        double pr = 0.0;
+#pragma unroll
+        for (int j = 1; j <= k + 1; j++) pr = fma(x[j], r[k + 1 - j], pr);
+        r[k + 1] = pr*r[0];
+        sx += x[k + 1]; sy += y[k + 1]; sz += z[k + 1];
+        sr = fma(r[k + 1], 1.0/(k + 2), sr);
+    }
+    // truncation check on the last two orders of every series (relative to L, resp. r[0])
+    const double tailL = fabs(x[K]) + fabs(y[K]) + fabs(z[K]) + fabs(x[K - 1]) + fabs(y[K - 1]) + fabs(z[K - 1]);
+    const double tailR = fabs(r[K]) + fabs(r[K - 1]);
+    if (!(tailL <= 2.0e-16*L && tailR <= 2.0e-16*fabs(r[0]))) return false;
+    const double theta = 0.5*dt*(L*invI.x + (twoT - Lsq*invI.x)*sr);
+    double st, ct;
+    sincos(theta, &st, &ct);
+    const d4 z0 = {l0.z, l0.y, L - l0.x, 0.0};
+    const d4 za = {sz, sy, L - sx, 0.0};
+    const d4 zb = {-sy, sz, 0.0, L - sx};
+    const d4 zz = za*ct + zb*st;
+    d4 qn = zz*dot(z0, q) + quatC(zz, quatCt(z0, q));
+    qn = qn*rsqrtd(dot(qn, qn));
+    q = qn;
+    pi = quatB(qn, d3{sx, sy, sz}*2.0);
+    return true;
+}
+
+constexpr int kSeriesOrder = 16;
+
+// Mode 0 entry point used by the step.  Order-16 series over dt; if its truncation check fails
+// (fast rotor / long step) four quarter steps - the composition of exact flows is exact and the tail
+// shrinks by 4^16 - and only then the elliptic-integral route, which needs I = 1/invI.
+RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
+    for (int n = 1; n <= 4; n <<= 2) {
+        d4 q1 = q, p1 = pi;
+        const double h = dt/n;
+        bool ok = true;
+        for (int i = 0; i < n && ok; i++) ok = exactRotationSeries<kSeriesOrder>(h, invI, q1, p1);
+        if (ok) { q = q1; pi = p1; return; }
+    }
+    const d3 I = {1.0/invI.x, 1.0/invI.y, 1.0/invI.z};
     exactRotationElliptic(dt, I, invI, q, pi);
 }
 

@@ -17,12 +17,12 @@ namespace rbk {
 // quaternion-frame torque the reference stores is C(q) tau with the SAME q (q does not change
 // between Part 2 and the next Part 1), so it is rebuilt here instead of being stored.
 template <bool EXACT>
-RBK_HD void bodyPart1(double dt, int nSplit, d3 F, d3 tau, double invm, d3 I, d3 invI, d3& r, d3& p, d4& q, d4& pi) {
+RBK_HD void bodyPart1(double dt, int nSplit, d3 F, d3 tau, double invm, d3 invI, d3& r, d3& p, d4& q, d4& pi) {
     const double halfDt = 0.5*dt;
     p = p + F*halfDt;
     pi = pi + quatC(q, tau)*dt;
     r = r + p*(invm*dt);
-    if (EXACT) exactRotation(dt, I, invI, q, pi);
+    if (EXACT) exactRotation(dt, invI, q, pi);
     else noSquish(dt, nSplit, invI, q, pi);
 }
 
