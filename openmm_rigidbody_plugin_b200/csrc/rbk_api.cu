@@ -51,6 +51,7 @@ struct rbk_system {
     uint8_t* dLocalBody = nullptr;
     int* dLoc = nullptr;
     int* dTile = nullptr;
+    int4* dTileMeta = nullptr;
     int* dAtomLoc = nullptr;
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
@@ -66,7 +67,7 @@ struct rbk_system {
     std::vector<double> staging;
 
     ~rbk_system() {
-        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTile);
+        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTile); cudaFree(dTileMeta);
         cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce);
         if (hKinOut) cudaFreeHost(hKinOut);
@@ -87,7 +88,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
 
     const int nB = h.numBodies, nA = h.numBodyAtoms, nF = h.numFree;
     std::vector<int> loc((size_t) nB + 1, 0), tile;
-    std::vector<uint8_t> local((size_t) std::max(nA, 1), 0);
+    std::vector<uint8_t> local(padTo((size_t) std::max(nA, 1) + 4, 16), 0);   // +4: staged in 4-byte granules
     int maxSize = 0;
     for (int b = 0; b < nB; b++) {
         loc[b] = h.body[b].loc;
@@ -116,6 +117,9 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.numFreeBlocks = (nF + rbk::kFreePerBlock - 1)/rbk::kFreePerBlock;
     d.rotationMode = h.rotationMode;
     d.maxBodySize = maxSize;
+    int device = 0;
+    RBK_CUDA(cudaGetDevice(&device));
+    RBK_CUDA(cudaDeviceGetAttribute(&d.numSMs, cudaDevAttrMultiProcessorCount, device));
     d.bodyStride = padTo((size_t) std::max(nB, 1), 32);
     d.atomStride = padTo((size_t) std::max(nA, 1), 32);
     d.freeStride = padTo((size_t) std::max(nF, 1), 32);
@@ -125,6 +129,11 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(devAlloc(sys->dLocalBody, local.size()));
     RBK_CUDA(devAlloc(sys->dLoc, loc.size()));
     RBK_CUDA(devAlloc(sys->dTile, tile.size()));
+    std::vector<int4> meta((size_t) std::max(d.numTiles, 1));
+    for (int t = 0; t < d.numTiles; t++)
+        meta[t] = make_int4(tile[t], tile[t+1] - tile[t], loc[tile[t]], loc[tile[t+1]] - loc[tile[t]]);
+    RBK_CUDA(devAlloc(sys->dTileMeta, meta.size()));
+    RBK_CUDA(cudaMemcpyAsync(sys->dTileMeta, meta.data(), meta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
     RBK_CUDA(devAlloc(sys->dFreeInvMass, (size_t) std::max(nF, 1)));
     RBK_CUDA(devAlloc(sys->dSavedPos, d.freeStride*3));
@@ -145,6 +154,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.localBody = sys->dLocalBody;
     d.loc = sys->dLoc;
     d.tileBody = sys->dTile;
+    d.tileMeta = sys->dTileMeta;
     d.atomLoc = nullptr;
     d.freeInvMass = sys->dFreeInvMass;
     d.savedPos = sys->dSavedPos;

@@ -19,18 +19,19 @@ enum Plane : int {
 };
 
 constexpr int kBlock = 128;            // threads per CTA = max bodies per tile
-constexpr int kTileAtoms = 1024;       // soft cap of body atoms per tile (a single larger body gets its own tile)
+constexpr int kTileAtoms = 768;        // soft cap of body atoms per tile = staged d capacity (a single larger body gets its own tile)
 constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
 
 struct DeviceSystem {
     int numBodies, numFree, numBodyAtoms, numTiles, numFreeBlocks;
-    int rotationMode, maxBodySize;
+    int rotationMode, maxBodySize, numSMs;
     size_t bodyStride, atomStride, freeStride;
     double* state;
     const double* dxyz;
     const uint8_t* localBody;
     const int* loc;
     const int* tileBody;
+    const int4* tileMeta;        // per tile: first body, #bodies, first body-atom, #atoms
     const int* atomLoc;
     const double* freeInvMass;
     double* savedPos;

@@ -48,47 +48,150 @@ __device__ __forceinline__ long long atomSlot(const DeviceSystem& S, int pluginI
 
 // ------------------------------------------------------------------------------------------------
 // Part 1: half kick, drift, rotation, position reconstruction (+ free atoms: half kick, drift)
+//
+// Persistent CTAs (grid = SMs x resident CTAs) walk the tile list.  The 24 body-state planes of the
+// NEXT tile are brought into shared memory with cp.async (LDGSTS) while the current tile's rotation
+// update runs (double buffer); the tile's body-frame coordinates are requested at the start of the
+// tile and consumed in its atom phase.  The long fp64 phase therefore never waits on HBM.
 // ------------------------------------------------------------------------------------------------
+// Resident CTAs per SM.  Exact mode: the order-16 series keeps ~70 doubles live, 246 registers without
+// spills -> 2 CTAs (3 CTAs at 168 registers spill and measured slower).  NO-SQUISH needs ~100 -> 3 CTAs
+// (then shared memory, 66 KB per CTA, is the limit).
+#ifndef RBK_P1_MINBLOCKS_EXACT
+#define RBK_P1_MINBLOCKS_EXACT 2
+#endif
+#ifndef RBK_P1_MINBLOCKS_SPLIT
+#define RBK_P1_MINBLOCKS_SPLIT 3
+#endif
+constexpr int kP1Planes = 24;                       // r3 p3 q4 pi4 F3 tau3 invm invI3
+
+struct Part1Smem {
+    double body[2][kP1Planes][kBlock];
+    double d[3][kTileAtoms];
+    unsigned char localBody[kTileAtoms + 16];
+    int4 meta[3];                                   // ring: tile descriptors of the current, next and next-but-one tile
+};
+
+__device__ __forceinline__ void cpAsync8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsync4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// smem plane k of a stage <-> global state plane (the I planes 21..23 are not needed on the device path)
+__device__ __forceinline__ int globalPlane(int k) { return k < 21 ? k : k + 3; }
+
 template <bool EXACT>
-__global__ void __launch_bounds__(kBlock) part1Kernel(const DeviceSystem S, const double dt, const AtomView pos,
-                                                     const AtomView vel, const AtomView force) {
-    __shared__ double sQ[4][kBlock];
-    __shared__ double sR[3][kBlock];
+__global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT) part1Kernel(const DeviceSystem S, const double dt, const AtomView pos,
+                                                                       const AtomView vel, const AtomView force) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    Part1Smem& sm = *reinterpret_cast<Part1Smem*>(smemRaw);
     const int tid = threadIdx.x;
-    if ((int) blockIdx.x < S.numTiles) {
-        const int b0 = S.tileBody[blockIdx.x], b1 = S.tileBody[blockIdx.x + 1];
-        if (tid < b1 - b0) {                                   // ---- thread per body
-            const size_t ld = S.bodyStride;
-            double* s = S.state + (size_t) (b0 + tid);
-            d3 r = loadPlane3(s + PL_R*ld, ld);
-            d3 p = loadPlane3(s + PL_P*ld, ld);
-            d4 q = loadPlane4(s + PL_Q*ld, ld);
-            d4 pi = loadPlane4(s + PL_PI*ld, ld);
-            const d3 F = loadPlane3(s + PL_F*ld, ld);
-            const d3 tau = loadPlane3(s + PL_TAU*ld, ld);
-            const double invm = s[PL_INVM*ld];
-            const d3 invI = loadPlane3(s + PL_INVI*ld, ld);
+    const int G = gridDim.x;
+    const size_t ld = S.bodyStride, as = S.atomStride;
+
+    // Everything a tile needs is requested with cp.async one tile ahead (descriptor: two tiles ahead),
+    // so no value loaded from HBM is ever held in a register across the long rotation phase.
+    auto requestBody = [&](int4 m, int stage) {
+        if (tid < m.y) {
+            const double* g = S.state + (size_t) (m.x + tid);
+#pragma unroll
+            for (int k = 0; k < kP1Planes; k++) cpAsync8(&sm.body[stage][k][tid], g + globalPlane(k)*ld);
+        }
+    };
+    auto requestAtoms = [&](int4 m) {
+        if (m.w > kTileAtoms) return;
+        for (int j = tid; j < m.w; j += kBlock) {
+            const double* g = S.dxyz + (size_t) (m.z + j);
+            cpAsync8(&sm.d[0][j], g);
+            cpAsync8(&sm.d[1][j], g + as);
+            cpAsync8(&sm.d[2][j], g + 2*as);
+        }
+        const int first = m.z & ~3;                            // 4-byte granules of the byte array
+        for (int w = tid; 4*w < m.z + m.w - first; w += kBlock)
+            cpAsync4(&sm.localBody[4*w], S.localBody + first + 4*w);
+    };
+
+    const int tile0 = blockIdx.x;
+    if (tile0 >= S.numTiles) goto freeAtoms;
+    if (tid == 0) {
+        sm.meta[0] = S.tileMeta[tile0];
+        if (tile0 + G < S.numTiles) sm.meta[1] = S.tileMeta[tile0 + G];
+    }
+    __syncthreads();
+    requestBody(sm.meta[0], 0);
+    cpCommit();
+    for (int tile = tile0, it = 0; tile < S.numTiles; tile += G, it++) {
+        const int stage = it & 1;
+        const int4 m = sm.meta[it % 3];
+        requestAtoms(m);
+        cpCommit();
+        cpWait<1>();                                           // body state of this tile (+ descriptor of the next) landed
+        __syncthreads();
+        if (tile + G < S.numTiles) {
+            requestBody(sm.meta[(it + 1) % 3], stage ^ 1);
+            if (tid == 0 && tile + 2*G < S.numTiles) cpAsync16(&sm.meta[(it + 2) % 3], S.tileMeta + tile + 2*G);
+        }
+        cpCommit();
+
+        double (*B)[kBlock] = sm.body[stage];
+        if (tid < m.y) {                                       // ---- thread per body
+            d3 r = {B[0][tid], B[1][tid], B[2][tid]};
+            d3 p = {B[3][tid], B[4][tid], B[5][tid]};
+            d4 q = {B[6][tid], B[7][tid], B[8][tid], B[9][tid]};
+            d4 pi = {B[10][tid], B[11][tid], B[12][tid], B[13][tid]};
+            const d3 F = {B[14][tid], B[15][tid], B[16][tid]};
+            const d3 tau = {B[17][tid], B[18][tid], B[19][tid]};
+            const double invm = B[20][tid];
+            const d3 invI = {B[21][tid], B[22][tid], B[23][tid]};
             bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
+            double* s = S.state + (size_t) (m.x + tid);
             storePlane3(s + PL_R*ld, ld, r);
             storePlane3(s + PL_P*ld, ld, p);
             storePlane4(s + PL_Q*ld, ld, q);
             storePlane4(s + PL_PI*ld, ld, pi);
-            sQ[0][tid] = q.w; sQ[1][tid] = q.x; sQ[2][tid] = q.y; sQ[3][tid] = q.z;
-            sR[0][tid] = r.x; sR[1][tid] = r.y; sR[2][tid] = r.z;
+            B[0][tid] = r.x; B[1][tid] = r.y; B[2][tid] = r.z;         // hand r, q to the atom phase
+            B[6][tid] = q.w; B[7][tid] = q.x; B[8][tid] = q.y; B[9][tid] = q.z;
         }
+        cpWait<1>();                                           // this tile's coordinates have landed
         __syncthreads();
-        const int a0 = S.loc[b0], a1 = S.loc[b1];              // ---- thread per atom
-        const size_t as = S.atomStride;
-        for (int a = a0 + tid; a < a1; a += kBlock) {
-            const int lb = S.localBody[a];
-            const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-            const d4 q = {sQ[0][lb], sQ[1][lb], sQ[2][lb], sQ[3][lb]};
-            const d3 r = {sR[0][lb], sR[1][lb], sR[2][lb]};
-            storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+
+        if (m.w <= kTileAtoms) {                               // ---- thread per atom
+            const int shift = m.z & 3;
+            for (int j = tid; j < m.w; j += kBlock) {
+                const int k = sm.localBody[j + shift];
+                const d3 d = {sm.d[0][j], sm.d[1][j], sm.d[2][j]};
+                const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
+                const d3 r = {B[0][k], B[1][k], B[2][k]};
+                storeAtom(pos, atomSlot(S, S.numFree + m.z + j), atomPosition(r, q, d));
+            }
         }
+        else {                                                 // one body larger than the staging buffer
+            for (int a = m.z + tid; a < m.z + m.w; a += kBlock) {
+                const int k = S.localBody[a];
+                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+                const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
+                const d3 r = {B[0][k], B[1][k], B[2][k]};
+                storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+            }
+        }
+        __syncthreads();                                       // buffers are reused by the next tile
     }
-    else {                                                     // ---- free atoms
-        const int base = ((int) blockIdx.x - S.numTiles)*kFreePerBlock + tid;
+    cpWait<0>();
+
+freeAtoms:
+    // ---- free atoms: velocity-Verlet half kick + drift, grid-stride over chunks
+    for (int c = blockIdx.x; c < S.numFreeBlocks; c += gridDim.x) {
+        const int base = c*kFreePerBlock + tid;
 #pragma unroll
         for (int j = 0; j < kFreePerBlock/kBlock; j++) {
             const int k = base + j*kBlock;
@@ -300,10 +403,20 @@ int gridFor(const DeviceSystem& S) { return S.numTiles + S.numFreeBlocks; }
 } // namespace
 
 cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    const int grid = gridFor(S);
-    if (grid == 0) return cudaSuccess;
-    if (S.rotationMode == 0) part1Kernel<true><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
-    else part1Kernel<false><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(part1Kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Part1Smem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(part1Kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Part1Smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    // persistent CTAs: one wave that fills every SM
+    const int work = S.numTiles > 0 ? S.numTiles : S.numFreeBlocks;
+    const int resident = S.numSMs*(S.rotationMode == 0 ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
+    const int grid = work < resident ? work : resident;
+    if (S.rotationMode == 0) part1Kernel<true><<<grid, kBlock, sizeof(Part1Smem), st>>>(S, dt, pos, vel, force);
+    else part1Kernel<false><<<grid, kBlock, sizeof(Part1Smem), st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 

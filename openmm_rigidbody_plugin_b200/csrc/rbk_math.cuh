@@ -72,6 +72,22 @@ RBK_HD d3 quatCt(d4 q, d4 y) {
 // body frame -> space frame: A^T(q) v = C^T(q) B(q) v
 RBK_HD d3 bodyToSpace(d4 q, d3 v) { return quatCt(q, quatB(q, v)); }
 
+// sin and cos for the small angles of a single time step: the classic minimax kernels on [-pi/4, pi/4]
+// (error < 1 ulp) without range reduction; anything larger takes the library routine.
+RBK_HD void sincosStep(double x, double* s, double* c) {
+    if (fabs(x) <= 0.78539816339744830962) {
+        const double z = x*x;
+        const double ps = -1.66666666666666324348e-01 + z*(8.33333333332248946124e-03 + z*(-1.98412698298579493134e-04
+                        + z*(2.75573137070700676789e-06 + z*(-2.50507602534068634195e-08 + z*1.58969099521155010221e-10))));
+        const double pc = 4.16666666666666019037e-02 + z*(-1.38888888888741095749e-03 + z*(2.48015872894767294178e-05
+                        + z*(-2.75573143513906633035e-07 + z*(2.08757232129817482790e-09 + z*(-1.13596475577881948265e-11)))));
+        *s = x + x*z*ps;
+        const double hz = 0.5*z, w = 1.0 - hz;
+        *c = w + (((1.0 - w) - hz) + z*z*pc);
+    }
+    else sincos(x, s, c);
+}
+
 // permutation operators B_k q (k = 0,1,2 for principal axes 1,2,3)
 template <int K> RBK_HD d4 quatPerm(d4 q) {
     if (K == 0) return {-q.x,  q.w,  q.z, -q.y};
@@ -84,7 +100,7 @@ template <int K> RBK_HD void uniaxial(double h, double invIk, d4& q, d4& pi) {
     d4 Bq = quatPerm<K>(q);
     double phi = 0.25*dot(pi, Bq)*h*invIk;
     double s, c;
-    sincos(phi, &s, &c);
+    sincosStep(phi, &s, &c);
     d4 Bp = quatPerm<K>(pi);
     q = q*c + Bq*s;
     pi = pi*c + Bp*s;
@@ -348,21 +364,30 @@ RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
     double sx = x[0], sy = y[0], sz = z[0], sr = r[0];
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        double px = 0.0, py = 0.0, pz = 0.0;
+        // Cauchy products, two independent accumulation chains each (ILP for the fp64 pipe)
+        double px = 0.0, py = 0.0, pz = 0.0, px2 = 0.0, py2 = 0.0, pz2 = 0.0;
 #pragma unroll
-        for (int j = 0; j <= k; j++) {
+        for (int j = 0; j <= k; j += 2) {
             px = fma(y[j], z[k - j], px);
             py = fma(z[j], x[k - j], py);
             pz = fma(x[j], y[k - j], pz);
+            if (j + 1 <= k) {
+                px2 = fma(y[j + 1], z[k - j - 1], px2);
+                py2 = fma(z[j + 1], x[k - j - 1], py2);
+                pz2 = fma(x[j + 1], y[k - j - 1], pz2);
+            }
         }
         const double f = 1.0/(k + 1);
-        x[k + 1] = (ca*f)*px;
-        y[k + 1] = (cb*f)*py;
-        z[k + 1] = (cc*f)*pz;
-        double pr = 0.0;
+        x[k + 1] = (ca*f)*(px + px2);
+        y[k + 1] = (cb*f)*(py + py2);
+        z[k + 1] = (cc*f)*(pz + pz2);
+        double pr = 0.0, pr2 = 0.0;
 #pragma unroll
-        for (int j = 1; j <= k + 1; j++) pr = fma(x[j], r[k + 1 - j], pr);
-        r[k + 1] = pr*r[0];
+        for (int j = 1; j <= k + 1; j += 2) {
+            pr = fma(x[j], r[k + 1 - j], pr);
+            if (j + 1 <= k + 1) pr2 = fma(x[j + 1], r[k - j], pr2);
+        }
+        r[k + 1] = (pr + pr2)*r[0];
         sx += x[k + 1]; sy += y[k + 1]; sz += z[k + 1];
         sr = fma(r[k + 1], 1.0/(k + 2), sr);
     }
@@ -372,7 +397,7 @@ RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
     if (!(tailL <= 2.0e-16*L && tailR <= 2.0e-16*fabs(r[0]))) return false;
     const double theta = 0.5*dt*(L*invI.x + (twoT - Lsq*invI.x)*sr);
     double st, ct;
-    sincos(theta, &st, &ct);
+    sincosStep(theta, &st, &ct);
     const d4 z0 = {l0.z, l0.y, L - l0.x, 0.0};
     const d4 za = {sz, sy, L - sx, 0.0};
     const d4 zb = {-sy, sz, 0.0, L - sx};

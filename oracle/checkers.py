@@ -63,6 +63,7 @@ def _lib(kind: str):
         ("part1", [C.c_void_p, C.c_double]),
         ("part2", [C.c_void_p, C.c_double]),
         ("step", [C.c_void_p, C.c_double, C.c_int]),
+        ("set_alternate", [C.c_void_p, C.c_int]),
         ("kinetic", [C.c_void_p, _dp]),
         ("get_bodies", [C.c_void_p, _ip, _ip, _ip] + [_dp] * 10),
         ("get_body_fixed", [C.c_void_p, _dp]),
@@ -166,6 +167,9 @@ class CpuStepper:
 
     def step(self, dt, steps=1):
         self._f("step")(self.h, float(dt), int(steps))
+
+    def set_alternate(self, flag=True):
+        self._f("set_alternate")(self.h, int(flag))
 
     def kinetic(self):
         out = np.zeros(2)

@@ -499,7 +499,7 @@ typedef struct {
     double *d, *delta;                 /* body-frame coordinates and space-frame displacements, 3 per body atom */
     double *freeInvMass, *savedPos;
     double *R, *V, *F;
-    int tether;
+    int tether, alternate;
     double k, E[3], *charge, *x0;
 } sys_t;
 
@@ -836,9 +836,13 @@ void orc_step(void* h, double dt, int steps) {
     for (int i = 0; i < steps; i++) {
         orc_part1(h, dt);
         if (s->tether) orc_compute_forces(h);
+        if (s->alternate)                    /* benchmark workload: fixed forces whose sign flips every step */
+            for (int k = 0; k < 3*s->numAtoms; k++) s->F[k] = -s->F[k];
         orc_part2(h, dt);
     }
 }
+
+void orc_set_alternate(void* h, int flag) { ((sys_t*) h)->alternate = flag != 0; }
 
 /* computeKineticEnergies  RigidBodySystem.cpp:210-220 */
 void orc_kinetic(void* h, double* out) {

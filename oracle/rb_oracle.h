@@ -32,6 +32,7 @@ void orc_update(void* h, int geometry, int velocities);
 void orc_part1(void* h, double dt);
 void orc_part2(void* h, double dt);
 void orc_step(void* h, double dt, int steps);
+void orc_set_alternate(void* h, int flag);     /* flip the sign of F before every Part 2 (benchmark workload) */
 void orc_kinetic(void* h, double* out2);
 void orc_get_bodies(void* h, int* N, int* dof, int* loc, double* mass, double* I, double* invI, double* rcm,
                     double* pcm, double* q, double* pi, double* force, double* torque, double* twoK);

@@ -38,11 +38,11 @@ struct RefHandle {
     vector<int> cleaned;
     int numAtoms;
     // analytic test potential:  U = sum_i 1/2 k |x_i - x0_i|^2 - c_i E.x_i
-    bool tether;
+    bool tether, alternate;
     double k, E[3];
     vector<double> charge;
     vector<Vec3> x0;
-    RefHandle() : context(system), numAtoms(0), tether(false), k(0.0) { E[0] = E[1] = E[2] = 0.0; }
+    RefHandle() : context(system), numAtoms(0), tether(false), alternate(false), k(0.0) { E[0] = E[1] = E[2] = 0.0; }
 };
 
 void toVec(const double* src, vector<Vec3>& dst, int n) {
@@ -174,9 +174,13 @@ void ref_step(void* p, double dt, int steps) {
     for (int s = 0; s < steps; s++) {
         h->bodies.integratePart1(dt, h->context.F, h->context.V, h->context.R);
         if (h->tether) tetherForces(h);
+        if (h->alternate)                       // benchmark workload: fixed forces whose sign flips every step
+            for (int i = 0; i < h->numAtoms; i++) h->context.F[i] = -h->context.F[i];
         h->bodies.integratePart2(dt, h->context.R, h->context.F, h->context.V);
     }
 }
+
+void ref_set_alternate(void* p, int flag) { ((RefHandle*) p)->alternate = flag != 0; }
 
 void ref_kinetic(void* p, double* out) {
     RefHandle* h = (RefHandle*) p;

@@ -92,6 +92,32 @@ def drift_case(name, sysd, modes, steps=10000, every=50):
         s.close()
 
 
+def gravity_case(name, sysd, modes, steps=10000, every=250):
+    """Integrable 10k-step run: fixed forces F_i = m_i g (no torque).  E = -sum F.x + KE."""
+    gvec = np.array([0.3, -0.5, 0.8])
+    sysd = dict(sysd)
+    sysd["F"] = sysd["masses"][:, None] * gvec[None, :]
+    for mode in modes:
+        s = CpuStepper("reference", sysd["bodyIndices"], sysd["masses"], mode)
+        common.init_like_reference(s, sysd)
+        E = []
+        for i in range(steps // every + 1):
+            R, V, _ = s.get_state()
+            ke = s.kinetic()
+            E.append([i * every * DT, -float(np.sum(sysd["F"] * R)), ke[0], ke[1]])
+            if i < steps // every:
+                s.step(DT, every)
+        out = {k: sysd[k] for k in ("bodyIndices", "masses", "R", "V", "F", "charges")}
+        out.update(mode=np.int32(mode), dt=np.float64(DT), every=np.int32(every), series=np.array(E))
+        out["R_end"], out["V_end"] = s.get_state()[:2]
+        path = os.path.join(HERE, f"{name}_mode{mode}.npz")
+        np.savez_compressed(path, **out)
+        e = np.array(E)
+        tot = e[:, 1:].sum(1)
+        print(f"{path}: E0={tot[0]:.6f} max|E-E0|={np.max(np.abs(tot - tot[0])):.3e}")
+        s.close()
+
+
 def special_function_kats():
     import mpmath as mp
     mp.mp.dps = 50
@@ -123,6 +149,7 @@ def main():
     for nm, (sysd, modes) in common.edge_cases().items():
         run_case("edge_" + nm, sysd, modes, [1, 5])
     drift_case("drift_water128", synth.water_box(128, seed=14), [0, 10])
+    gravity_case("gravity_water128", synth.water_box(128, seed=15), [0, 10])
     special_function_kats()
 
 

@@ -12,7 +12,7 @@ import common
 from common import GOLDEN_DIR
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*_mode*.npz"))
-               if not os.path.basename(p).startswith("drift_"))
+               if not os.path.basename(p).startswith(("drift_", "gravity_")))
 
 
 @pytest.fixture(scope="module")

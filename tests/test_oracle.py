@@ -15,7 +15,7 @@ from oracle import checkers
 from oracle.checkers import CpuStepper
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*_mode*.npz"))
-               if not os.path.basename(p).startswith("drift_"))
+               if not os.path.basename(p).startswith(("drift_", "gravity_")))
 
 
 def load(name):
