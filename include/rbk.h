@@ -120,6 +120,10 @@ typedef void (*rbk_force_fn)(const double* R, double* F, int numAtoms, void* use
 int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F,
                      rbk_force_fn forces, void* user, void* stream);
 
+/* rbk_kinetic for callers that hold velocities on the HOST (Reference-platform data): copies V into the
+ * handle's device mirror (only free atoms need it) and runs the same device reduction. */
+int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,9 @@ The arithmetic lives in lib/librbk.so (hand-written CUDA for sm_100a behind the 
 include/rbk.h); this package is the host-side mirror of the reference's interface.  Importing the
 package does not load the library; constructing any system does, and fails loudly if it is missing.
 """
-from ._lib import RBK_LAYOUT_SOA, RBK_LAYOUT_VEC3, RbkError  # noqa: F401
+from ._lib import RBK_LAYOUT_SOA, RBK_LAYOUT_VEC3, OpenMMException, RbkError  # noqa: F401
+from .integrator import Context, HarmonicBondForce, RigidBodyIntegrator, RigidBodySystem, State, System  # noqa: F401
 from .system import DeviceRigidBodySystem  # noqa: F401
 
-__all__ = ["DeviceRigidBodySystem", "RbkError", "RBK_LAYOUT_VEC3", "RBK_LAYOUT_SOA"]
+__all__ = ["DeviceRigidBodySystem", "RbkError", "OpenMMException", "RBK_LAYOUT_VEC3", "RBK_LAYOUT_SOA",
+           "RigidBodyIntegrator", "RigidBodySystem", "System", "Context", "State", "HarmonicBondForce"]

@@ -32,6 +32,7 @@ SIGNATURES = {
     "rbk_part1": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "rbk_part2": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "rbk_kinetic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, _dp, C.c_void_p]),
+    "rbk_kinetic_host": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.c_void_p]),
     "rbk_download_bodies": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_void_p]),
     "rbk_execute_host": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, FORCE_FN, C.c_void_p, C.c_void_p]),
 }
@@ -39,7 +40,11 @@ SIGNATURES = {
 _lib = None
 
 
-class RbkError(RuntimeError):
+class OpenMMException(RuntimeError):
+    """Stand-in for OpenMM::OpenMMException, the exception type of the reference's API."""
+
+
+class RbkError(OpenMMException):
     """Raised for any non-zero return code of the C ABI (the reference throws OpenMMException)."""
 
     def __init__(self, code, message):

@@ -368,6 +368,20 @@ int rbk_kinetic(rbk_system* sys, const double* vel, int layout, long long stride
     return RBK_OK;
 }
 
+int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream) {
+    if (!sys || !V || !out) return fail(RBK_EINVAL, "rbk_kinetic_host: NULL argument");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_kinetic_host: body system not uploaded");
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
+    if (!sys->mVel) {
+        RBK_CUDA(cudaMalloc((void**) &sys->mPos, bytes));
+        RBK_CUDA(cudaMalloc((void**) &sys->mVel, bytes));
+        RBK_CUDA(cudaMalloc((void**) &sys->mForce, bytes));
+    }
+    if (sys->host.numFree > 0) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+    return rbk_kinetic(sys, sys->mVel, RBK_LAYOUT_VEC3, 0, out, stream);
+}
+
 int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, double* pi, double* force,
                         double* torque, void* stream) {
     if (!sys) return fail(RBK_EINVAL, "rbk_download_bodies: NULL system");

@@ -147,6 +147,12 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_kinetic(self.h, _ptr(vel), lay, stride, _d(out), _stream(stream)))
         return out
 
+    def kinetic_host(self, V, stream=None):
+        """Kinetic energies for host-resident velocities [N,3] (numpy or pinned torch CPU tensor)."""
+        out = np.zeros(2)
+        check(self.lib.rbk_kinetic_host(self.h, _ptr(V), _d(out), _stream(stream)))
+        return out
+
     def download_bodies(self, stream=None):
         nb = self.counts()["numBodies"]
         o = {"rcm": np.zeros((nb, 3)), "pcm": np.zeros((nb, 3)), "q": np.zeros((nb, 4)), "pi": np.zeros((nb, 4)),
