@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from openmm_rigidbody_plugin_b200 import synth  # noqa: E402
+from openmm_rigidbody_plugin_b200 import replicas, synth  # noqa: E402
 
 DT = 0.001                      # ps (1 fs, README.md:200 of the reference)
 METRIC = "integrator body-steps/s at 1M rigid waters (mode 0 exact rotation, fixed synthetic forces)"
@@ -216,9 +216,7 @@ def run_b200_arm(args):
     import torch.distributed as dist
     from openmm_rigidbody_plugin_b200 import DeviceRigidBodySystem
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = replicas.rank_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the rigid-body step has no CPU fallback")
     torch.cuda.set_device(local)
@@ -227,7 +225,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     # one independent replica per GPU, distinct seed per replica (BASELINE.json: replicas only)
-    sysd, name = make_workload(args, seed=20240001 + rank)
+    sysd, name = make_workload(args, seed=replicas.replica_seed(20240001, rank))
     n = sysd["masses"].shape[0]
     system = DeviceRigidBodySystem(sysd["bodyIndices"], sysd["masses"], args.mode)
     system.update(sysd["R"], np.zeros((n, 3)), sysd["F"], True, True)
@@ -256,8 +254,7 @@ def run_b200_arm(args):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        replicas.barrier(dist if world > 1 else None)
         torch.cuda.synchronize()
 
     ke_start = system.kinetic(vel)
@@ -273,11 +270,7 @@ def run_b200_arm(args):
         step()
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = replicas.max_over_ranks(e0.elapsed_time(e1), dist if world > 1 else None, dev)
     # ---- per-kernel pass (same workload, same K): events around every launch, for the roofline split
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
     torch.cuda.synchronize()
@@ -329,11 +322,7 @@ def run_b200_arm(args):
         for i in range(k2):                               # one call per step, that step's forces from the host
             system.execute_host(DT, 1, hR, hV, hF[i & 1])
         torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([el], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            el = float(t.item())
+        el = replicas.max_over_ranks(time.perf_counter() - t0, dist if world > 1 else None, dev)
         e2e = {"value": world * nB * k2 / el, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 48 * n,
                "steps": k2, "ms_per_step": 1e3 * el / k2,
                "call": "one rbk_execute_host per step: part1 -> positions D2H -> forces H2D -> part2 -> velocities D2H -> sync, pinned host buffers"}
@@ -354,7 +343,7 @@ def run_b200_arm(args):
                        "layout": args.layout, "dt_ps": DT, "bodies": nB, "body_atoms": nA, "free_atoms": nF,
                        "l2": "no flush needed: the per-step working set (state + atoms, >500 MB at 1M waters) exceeds the 126 MB L2"},
             "ns_per_day": (args.steps / (ms * 1e-3)) * DT * 1e-3 * 86400.0,
-            "clocks": clk, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "e2e": e2e, "gpu_launches": (3 if nA > 8 * nB else 2) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "kinetic_energy_kJmol": {"start": [float(ke_start[0]), float(ke_start[1])], "end": [float(ke[0]), float(ke[1])],
                                      "note": "translational, rotational; the workload stays at its initial ~300 K state"},
         }

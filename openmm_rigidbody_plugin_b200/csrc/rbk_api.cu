@@ -50,8 +50,8 @@ struct rbk_system {
     double* dDxyz = nullptr;
     uint8_t* dLocalBody = nullptr;
     int* dLoc = nullptr;
-    int* dTile = nullptr;
     int4* dTileMeta = nullptr;
+    int4* dBodyTileMeta = nullptr;
     int* dAtomLoc = nullptr;
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
@@ -67,7 +67,7 @@ struct rbk_system {
     std::vector<double> staging;
 
     ~rbk_system() {
-        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTile); cudaFree(dTileMeta);
+        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta);
         cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce);
         if (hKinOut) cudaFreeHost(hKinOut);
@@ -76,7 +76,7 @@ struct rbk_system {
 
 namespace {
 
-// Cut the body list into tiles (<= kBlock bodies, <= kTileAtoms atoms unless one body is larger) and
+// Cut the body list into tiles (<= kBlock bodies, <= kMaxTileAtoms atoms unless one body is larger) and
 // allocate + fill everything that does not change between uploads.
 int allocateDevice(rbk_system* sys, cudaStream_t st) {
     HostModel& h = sys->host;
@@ -87,7 +87,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
         return fail(RBK_ECUDA, "librbk needs a CUDA device (there is no CPU fallback)");
 
     const int nB = h.numBodies, nA = h.numBodyAtoms, nF = h.numFree;
-    std::vector<int> loc((size_t) nB + 1, 0), tile;
+    std::vector<int> loc((size_t) nB + 1, 0);
     std::vector<uint8_t> local(padTo((size_t) std::max(nA, 1) + 4, 16), 0);   // +4: staged in 4-byte granules
     int maxSize = 0;
     for (int b = 0; b < nB; b++) {
@@ -95,25 +95,33 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
         maxSize = std::max(maxSize, h.body[b].N);
     }
     loc[nB] = nB ? h.body[nB-1].loc + h.body[nB-1].N : 0;
-    tile.push_back(0);
-    int inTile = 0, atomsInTile = 0;
-    for (int b = 0; b < nB; b++) {
-        const int n = h.body[b].N;
-        if (inTile > 0 && (inTile == rbk::kBlock || atomsInTile + n > rbk::kTileAtoms)) {
-            tile.push_back(b);
-            inTile = 0;
-            atomsInTile = 0;
+    // atom tiles (define the per-atom body byte) and body tiles
+    auto cut = [&](int atomCap, bool fillLocal) {
+        std::vector<int4> out;
+        int first = 0, inTile = 0, atomsInTile = 0;
+        for (int b = 0; b < nB; b++) {
+            const int n = h.body[b].N;
+            if (inTile > 0 && (inTile == rbk::kBlock || atomsInTile + n > atomCap)) {
+                out.push_back(make_int4(first, inTile, loc[first], atomsInTile));
+                first = b;
+                inTile = 0;
+                atomsInTile = 0;
+            }
+            if (fillLocal) for (int j = 0; j < n; j++) local[(size_t) loc[b] + j] = (uint8_t) inTile;
+            inTile++;
+            atomsInTile += n;
         }
-        for (int j = 0; j < n; j++) local[(size_t) loc[b] + j] = (uint8_t) inTile;
-        inTile++;
-        atomsInTile += n;
-    }
-    if (nB) tile.push_back(nB);
+        if (inTile > 0) out.push_back(make_int4(first, inTile, loc[first], atomsInTile));
+        return out;
+    };
+    std::vector<int4> meta = cut(rbk::kTileAtoms, true), bodyMeta = cut(rbk::kMaxTileAtoms, false);
 
     d.numBodies = nB;
     d.numFree = nF;
     d.numBodyAtoms = nA;
-    d.numTiles = nB ? (int) tile.size() - 1 : 0;
+    d.numTiles = (int) meta.size();
+    d.numBodyTiles = (int) bodyMeta.size();
+    d.splitPart1 = nB > 0 && (long long) nA > (long long) rbk::kSplitAtomsPerBody*nB;
     d.numFreeBlocks = (nF + rbk::kFreePerBlock - 1)/rbk::kFreePerBlock;
     d.rotationMode = h.rotationMode;
     d.maxBodySize = maxSize;
@@ -128,12 +136,12 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(devAlloc(sys->dDxyz, d.atomStride*3));
     RBK_CUDA(devAlloc(sys->dLocalBody, local.size()));
     RBK_CUDA(devAlloc(sys->dLoc, loc.size()));
-    RBK_CUDA(devAlloc(sys->dTile, tile.size()));
-    std::vector<int4> meta((size_t) std::max(d.numTiles, 1));
-    for (int t = 0; t < d.numTiles; t++)
-        meta[t] = make_int4(tile[t], tile[t+1] - tile[t], loc[tile[t]], loc[tile[t+1]] - loc[tile[t]]);
+    if (meta.empty()) meta.push_back(make_int4(0, 0, 0, 0));
+    if (bodyMeta.empty()) bodyMeta.push_back(make_int4(0, 0, 0, 0));
     RBK_CUDA(devAlloc(sys->dTileMeta, meta.size()));
+    RBK_CUDA(devAlloc(sys->dBodyTileMeta, bodyMeta.size()));
     RBK_CUDA(cudaMemcpyAsync(sys->dTileMeta, meta.data(), meta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaMemcpyAsync(sys->dBodyTileMeta, bodyMeta.data(), bodyMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
     RBK_CUDA(devAlloc(sys->dFreeInvMass, (size_t) std::max(nF, 1)));
     RBK_CUDA(devAlloc(sys->dSavedPos, d.freeStride*3));
@@ -145,7 +153,6 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(cudaMemsetAsync(sys->dSavedPos, 0, d.freeStride*3*sizeof(double), st));
     RBK_CUDA(cudaMemcpyAsync(sys->dLocalBody, local.data(), local.size(), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaMemcpyAsync(sys->dLoc, loc.data(), loc.size()*sizeof(int), cudaMemcpyHostToDevice, st));
-    RBK_CUDA(cudaMemcpyAsync(sys->dTile, tile.data(), tile.size()*sizeof(int), cudaMemcpyHostToDevice, st));
     if (nF) RBK_CUDA(cudaMemcpyAsync(sys->dFreeInvMass, h.freeInvMass.data(), (size_t) nF*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));       // the host vectors above die at scope exit
 
@@ -153,8 +160,8 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.dxyz = sys->dDxyz;
     d.localBody = sys->dLocalBody;
     d.loc = sys->dLoc;
-    d.tileBody = sys->dTile;
     d.tileMeta = sys->dTileMeta;
+    d.bodyTileMeta = sys->dBodyTileMeta;
     d.atomLoc = nullptr;
     d.freeInvMass = sys->dFreeInvMass;
     d.savedPos = sys->dSavedPos;

@@ -5,7 +5,7 @@
 //                r[3] p[3] q[4] pi[4] F[3] tau[3] invm I[3] invI[3]          (27 planes)
 //   body atoms : dxyz = 3 planes of atomStride doubles (body-frame coordinates, body-major order),
 //                localBody = 1 byte per body atom (index of its body inside its tile)
-//   maps       : loc[nB+1] prefix offsets, tileBody[nTiles+1], atomLoc[numActualAtoms] (or NULL = identity)
+//   maps       : loc[nB+1] prefix offsets, tile descriptors int4[nTiles], atomLoc[numActualAtoms] (or NULL = identity)
 //   free atoms : freeInvMass[nF], savedPos = 3 planes of freeStride doubles
 #pragma once
 #include <cstddef>
@@ -19,19 +19,25 @@ enum Plane : int {
 };
 
 constexpr int kBlock = 128;            // threads per CTA = max bodies per tile
-constexpr int kTileAtoms = 768;        // soft cap of body atoms per tile = staged d capacity (a single larger body gets its own tile)
+// Two tilings of the body list.  "Atom tiles" (<=128 bodies, <=kTileAtoms atoms, a larger single body
+// alone) drive every thread-per-atom phase: many CTAs, coordinates staged in shared memory.  "Body tiles"
+// (<=128 bodies, <=kMaxTileAtoms atoms) drive the stand-alone rotation kernel used when bodies are large,
+// so that its thread-per-body phase runs full warps.  For small bodies (water) the two coincide.
+constexpr int kTileAtoms = 768;
+constexpr int kMaxTileAtoms = 8192;
+constexpr int kSplitAtomsPerBody = 8;  // mean body size above which part 1 runs as rotation kernel + atom kernel
 constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
 
 struct DeviceSystem {
-    int numBodies, numFree, numBodyAtoms, numTiles, numFreeBlocks;
-    int rotationMode, maxBodySize, numSMs;
+    int numBodies, numFree, numBodyAtoms, numTiles, numBodyTiles, numFreeBlocks;
+    int rotationMode, maxBodySize, numSMs, splitPart1;
     size_t bodyStride, atomStride, freeStride;
     double* state;
     const double* dxyz;
     const uint8_t* localBody;
     const int* loc;
-    const int* tileBody;
-    const int4* tileMeta;        // per tile: first body, #bodies, first body-atom, #atoms
+    const int4* tileMeta;        // per atom tile: first body, #bodies, first body-atom, #atoms
+    const int4* bodyTileMeta;    // per body tile, same fields
     const int* atomLoc;
     const double* freeInvMass;
     double* savedPos;
@@ -47,6 +53,7 @@ cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
 // partial: scratch of 2*kKineticBlocks doubles; counter: zero-initialised unsigned; out: 2 doubles (device)
 constexpr int kKineticBlocks = 592;    // 148 SMs x 4
+int part1LaunchesPerStep(const DeviceSystem& S);   // 1 (fused) or 2 (rotation kernel + atom kernel)
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out, cudaStream_t st);
 
 } // namespace rbk

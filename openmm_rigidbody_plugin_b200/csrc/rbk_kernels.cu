@@ -15,6 +15,8 @@
 #include "rbk_device.hpp"
 #include "rbk_step.cuh"
 
+#include <cstddef>
+
 namespace rbk {
 namespace {
 
@@ -49,12 +51,18 @@ __device__ __forceinline__ long long atomSlot(const DeviceSystem& S, int pluginI
 // ------------------------------------------------------------------------------------------------
 // Part 1: half kick, drift, rotation, position reconstruction (+ free atoms: half kick, drift)
 //
-// Persistent CTAs (grid = SMs x resident CTAs) walk the tile list.  The 24 body-state planes of the
+// Persistent CTAs (grid = SMs x resident CTAs) walk a tile list.  The 24 body-state planes of the
 // NEXT tile are brought into shared memory with cp.async (LDGSTS) while the current tile's rotation
-// update runs (double buffer); the tile's body-frame coordinates are requested at the start of the
-// tile and consumed in its atom phase.  The long fp64 phase therefore never waits on HBM.
+// update runs (double buffer, descriptors two tiles ahead); no value loaded from HBM is ever held in a
+// register across the long fp64 phase.
+//   FUSED  (small bodies, e.g. water): walks the ATOM tiles; the tile's body-frame coordinates are
+//          requested at the start of the tile and consumed in its thread-per-atom phase, so rotation
+//          update and atom scatter are one kernel and r, q never go back through HBM.
+//   !FUSED (mean body size > kSplitAtomsPerBody): walks the BODY tiles (full warps in the rotation
+//          phase) and leaves the positions to atomPositionKernel, which runs with full occupancy;
+//          re-reading r, q costs 56 B per body, amortised over the body's many atoms.
 // ------------------------------------------------------------------------------------------------
-// Resident CTAs per SM.  Exact mode: the order-16 series keeps ~70 doubles live, 246 registers without
+// Resident CTAs per SM.  Exact mode: the order-16 series keeps ~70 doubles live, 236 registers without
 // spills -> 2 CTAs (3 CTAs at 168 registers spill and measured slower).  NO-SQUISH needs ~100 -> 3 CTAs
 // (then shared memory, 66 KB per CTA, is the limit).
 #ifndef RBK_P1_MINBLOCKS_EXACT
@@ -67,9 +75,9 @@ constexpr int kP1Planes = 24;                       // r3 p3 q4 pi4 F3 tau3 invm
 
 struct Part1Smem {
     double body[2][kP1Planes][kBlock];
-    double d[3][kTileAtoms];
+    int4 meta[3];                                   // ring: descriptors of the current, next and next-but-one tile
+    double d[3][kTileAtoms];                        // FUSED only (the !FUSED kernel allocates up to here)
     unsigned char localBody[kTileAtoms + 16];
-    int4 meta[3];                                   // ring: tile descriptors of the current, next and next-but-one tile
 };
 
 __device__ __forceinline__ void cpAsync8(void* smem, const void* gmem) {
@@ -90,17 +98,17 @@ template <int N> __device__ __forceinline__ void cpWait() { asm volatile("cp.asy
 // smem plane k of a stage <-> global state plane (the I planes 21..23 are not needed on the device path)
 __device__ __forceinline__ int globalPlane(int k) { return k < 21 ? k : k + 3; }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT) part1Kernel(const DeviceSystem S, const double dt, const AtomView pos,
-                                                                       const AtomView vel, const AtomView force) {
+template <bool EXACT, bool FUSED>
+__global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT)
+part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     Part1Smem& sm = *reinterpret_cast<Part1Smem*>(smemRaw);
     const int tid = threadIdx.x;
     const int G = gridDim.x;
     const size_t ld = S.bodyStride, as = S.atomStride;
+    const int4* __restrict__ tiles = FUSED ? S.tileMeta : S.bodyTileMeta;
+    const int numTiles = FUSED ? S.numTiles : S.numBodyTiles;
 
-    // Everything a tile needs is requested with cp.async one tile ahead (descriptor: two tiles ahead),
-    // so no value loaded from HBM is ever held in a register across the long rotation phase.
     auto requestBody = [&](int4 m, int stage) {
         if (tid < m.y) {
             const double* g = S.state + (size_t) (m.x + tid);
@@ -122,75 +130,78 @@ __global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P
     };
 
     const int tile0 = blockIdx.x;
-    if (tile0 >= S.numTiles) goto freeAtoms;
-    if (tid == 0) {
-        sm.meta[0] = S.tileMeta[tile0];
-        if (tile0 + G < S.numTiles) sm.meta[1] = S.tileMeta[tile0 + G];
-    }
-    __syncthreads();
-    requestBody(sm.meta[0], 0);
-    cpCommit();
-    for (int tile = tile0, it = 0; tile < S.numTiles; tile += G, it++) {
-        const int stage = it & 1;
-        const int4 m = sm.meta[it % 3];
-        requestAtoms(m);
-        cpCommit();
-        cpWait<1>();                                           // body state of this tile (+ descriptor of the next) landed
+    if (tile0 < numTiles) {
+        if (tid == 0) {
+            sm.meta[0] = tiles[tile0];
+            if (tile0 + G < numTiles) sm.meta[1] = tiles[tile0 + G];
+        }
         __syncthreads();
-        if (tile + G < S.numTiles) {
-            requestBody(sm.meta[(it + 1) % 3], stage ^ 1);
-            if (tid == 0 && tile + 2*G < S.numTiles) cpAsync16(&sm.meta[(it + 2) % 3], S.tileMeta + tile + 2*G);
-        }
+        requestBody(sm.meta[0], 0);
         cpCommit();
-
-        double (*B)[kBlock] = sm.body[stage];
-        if (tid < m.y) {                                       // ---- thread per body
-            d3 r = {B[0][tid], B[1][tid], B[2][tid]};
-            d3 p = {B[3][tid], B[4][tid], B[5][tid]};
-            d4 q = {B[6][tid], B[7][tid], B[8][tid], B[9][tid]};
-            d4 pi = {B[10][tid], B[11][tid], B[12][tid], B[13][tid]};
-            const d3 F = {B[14][tid], B[15][tid], B[16][tid]};
-            const d3 tau = {B[17][tid], B[18][tid], B[19][tid]};
-            const double invm = B[20][tid];
-            const d3 invI = {B[21][tid], B[22][tid], B[23][tid]};
-            bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
-            double* s = S.state + (size_t) (m.x + tid);
-            storePlane3(s + PL_R*ld, ld, r);
-            storePlane3(s + PL_P*ld, ld, p);
-            storePlane4(s + PL_Q*ld, ld, q);
-            storePlane4(s + PL_PI*ld, ld, pi);
-            B[0][tid] = r.x; B[1][tid] = r.y; B[2][tid] = r.z;         // hand r, q to the atom phase
-            B[6][tid] = q.w; B[7][tid] = q.x; B[8][tid] = q.y; B[9][tid] = q.z;
-        }
-        cpWait<1>();                                           // this tile's coordinates have landed
-        __syncthreads();
-
-        if (m.w <= kTileAtoms) {                               // ---- thread per atom
-            const int shift = m.z & 3;
-            for (int j = tid; j < m.w; j += kBlock) {
-                const int k = sm.localBody[j + shift];
-                const d3 d = {sm.d[0][j], sm.d[1][j], sm.d[2][j]};
-                const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
-                const d3 r = {B[0][k], B[1][k], B[2][k]};
-                storeAtom(pos, atomSlot(S, S.numFree + m.z + j), atomPosition(r, q, d));
+        for (int tile = tile0, it = 0; tile < numTiles; tile += G, it++) {
+            const int stage = it & 1;
+            const int4 m = sm.meta[it % 3];
+            if (FUSED) requestAtoms(m);
+            cpCommit();
+            cpWait<1>();                                       // body state of this tile (+ descriptor of the next) landed
+            __syncthreads();
+            if (tile + G < numTiles) {
+                requestBody(sm.meta[(it + 1) % 3], stage ^ 1);
+                if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tiles + tile + 2*G);
             }
-        }
-        else {                                                 // one body larger than the staging buffer
-            for (int a = m.z + tid; a < m.z + m.w; a += kBlock) {
-                const int k = S.localBody[a];
-                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-                const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
-                const d3 r = {B[0][k], B[1][k], B[2][k]};
-                storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+            cpCommit();
+
+            double (*B)[kBlock] = sm.body[stage];
+            if (tid < m.y) {                                   // ---- thread per body
+                d3 r = {B[0][tid], B[1][tid], B[2][tid]};
+                d3 p = {B[3][tid], B[4][tid], B[5][tid]};
+                d4 q = {B[6][tid], B[7][tid], B[8][tid], B[9][tid]};
+                d4 pi = {B[10][tid], B[11][tid], B[12][tid], B[13][tid]};
+                const d3 F = {B[14][tid], B[15][tid], B[16][tid]};
+                const d3 tau = {B[17][tid], B[18][tid], B[19][tid]};
+                const double invm = B[20][tid];
+                const d3 invI = {B[21][tid], B[22][tid], B[23][tid]};
+                bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
+                double* s = S.state + (size_t) (m.x + tid);
+                storePlane3(s + PL_R*ld, ld, r);
+                storePlane3(s + PL_P*ld, ld, p);
+                storePlane4(s + PL_Q*ld, ld, q);
+                storePlane4(s + PL_PI*ld, ld, pi);
+                if (FUSED) {                                   // hand r, q to the atom phase
+                    B[0][tid] = r.x; B[1][tid] = r.y; B[2][tid] = r.z;
+                    B[6][tid] = q.w; B[7][tid] = q.x; B[8][tid] = q.y; B[9][tid] = q.z;
+                }
             }
+            if (FUSED) {
+                cpWait<1>();                                   // this tile's coordinates have landed
+                __syncthreads();
+                if (m.w <= kTileAtoms) {                       // ---- thread per atom
+                    const int shift = m.z & 3;
+                    for (int j = tid; j < m.w; j += kBlock) {
+                        const int k = sm.localBody[j + shift];
+                        const d3 d = {sm.d[0][j], sm.d[1][j], sm.d[2][j]};
+                        const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
+                        const d3 r = {B[0][k], B[1][k], B[2][k]};
+                        storeAtom(pos, atomSlot(S, S.numFree + m.z + j), atomPosition(r, q, d));
+                    }
+                }
+                else {                                         // one body larger than the staging buffer
+                    for (int a = m.z + tid; a < m.z + m.w; a += kBlock) {
+                        const int k = S.localBody[a];
+                        const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+                        const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
+                        const d3 r = {B[0][k], B[1][k], B[2][k]};
+                        storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+                    }
+                }
+            }
+            __syncthreads();                                   // buffers are reused by the next tile
         }
-        __syncthreads();                                       // buffers are reused by the next tile
+        cpWait<0>();
     }
-    cpWait<0>();
 
-freeAtoms:
     // ---- free atoms: velocity-Verlet half kick + drift, grid-stride over chunks
-    for (int c = blockIdx.x; c < S.numFreeBlocks; c += gridDim.x) {
+    for (int c = blockIdx.x; c < S.numFreeBlocks; c += G) {
         const int base = c*kFreePerBlock + tid;
 #pragma unroll
         for (int j = 0; j < kFreePerBlock/kBlock; j++) {
@@ -207,10 +218,38 @@ freeAtoms:
     }
 }
 
+// Positions of the body atoms from the updated (r, q): one CTA per atom tile, thread per atom.
+// Second half of part 1 for large-body systems (see part1Kernel, !FUSED).
+__global__ void __launch_bounds__(kBlock) atomPositionKernel(const DeviceSystem S, const AtomView pos) {
+    __shared__ double sB[7][kBlock];
+    const int tid = threadIdx.x;
+    const int4 m = S.tileMeta[blockIdx.x];
+    const size_t ld = S.bodyStride, as = S.atomStride;
+    if (tid < m.y) {
+        const double* s = S.state + (size_t) (m.x + tid);
+        const d3 r = loadPlane3(s + PL_R*ld, ld);
+        const d4 q = loadPlane4(s + PL_Q*ld, ld);
+        sB[0][tid] = r.x; sB[1][tid] = r.y; sB[2][tid] = r.z;
+        sB[3][tid] = q.w; sB[4][tid] = q.x; sB[5][tid] = q.y; sB[6][tid] = q.z;
+    }
+    __syncthreads();
+    for (int a = m.z + tid; a < m.z + m.w; a += kBlock) {
+        const int k = S.localBody[a];
+        const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+        const d3 r = {sB[0][k], sB[1][k], sB[2][k]};
+        const d4 q = {sB[3][k], sB[4][k], sB[5][k], sB[6][k]};
+        storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// Part 2: force/torque segmented reduction, second half kick, velocity reconstruction
+// Part 2: force/torque segmented reduction, second half kick, velocity reconstruction.
+// One CTA per atom tile.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) part2Kernel(const DeviceSystem S, const double dt, const AtomView pos,
+#ifndef RBK_P2_MINBLOCKS
+#define RBK_P2_MINBLOCKS 9
+#endif
+__global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const DeviceSystem S, const double dt, const AtomView pos,
                                                      const AtomView vel, const AtomView force) {
     __shared__ double sQ[4][kBlock];
     __shared__ double sAcc[6][kBlock];        // (F, tau) per body, later (v_cm, omega_space)
@@ -219,16 +258,16 @@ __global__ void __launch_bounds__(kBlock) part2Kernel(const DeviceSystem S, cons
     __shared__ int sLoc[kBlock + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if ((int) blockIdx.x < S.numTiles) {
-        const int b0 = S.tileBody[blockIdx.x], b1 = S.tileBody[blockIdx.x + 1];
-        const int nb = b1 - b0;
+        const int4 m = S.tileMeta[blockIdx.x];
+        const int nb = m.y;
         const size_t ld = S.bodyStride;
-        double* s = S.state + (size_t) (b0 + tid);
+        double* s = S.state + (size_t) (m.x + tid);
         if (tid < nb) {                                        // ---- A: thread per body, stage q
             const d4 q = loadPlane4(s + PL_Q*ld, ld);
+            sLoc[tid] = S.loc[m.x + tid];
             sQ[0][tid] = q.w; sQ[1][tid] = q.x; sQ[2][tid] = q.y; sQ[3][tid] = q.z;
         }
-        if (tid < nb) sLoc[tid] = S.loc[b0 + tid];
-        if (tid == 0) sLoc[nb] = S.loc[b1];
+        if (tid == 0) sLoc[nb] = m.z + m.w;
 #pragma unroll
         for (int k = 0; k < 6; k++) sAcc[k][tid] = 0.0;
         if (tid < kWarps*6) sHead[tid/6][tid%6] = 0.0;
@@ -236,9 +275,9 @@ __global__ void __launch_bounds__(kBlock) part2Kernel(const DeviceSystem S, cons
 
         // ---- B: thread per atom.  Each warp walks a contiguous range of the tile's atoms in steps of
         // 32, so that partial sums of one body are always added in the same order (deterministic).
-        const int a0 = sLoc[0], a1 = sLoc[nb];
+        const int a0 = m.z, a1 = m.z + m.w;
         const size_t as = S.atomStride;
-        const int per = ((a1 - a0 + kBlock - 1)/kBlock)*32;
+        const int per = ((m.w + kBlock - 1)/kBlock)*32;
         const int wBeg = a0 + warp*per;
         const int wEnd = min(wBeg + per, a1);
         int firstKey = -1;
@@ -398,30 +437,35 @@ __global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem 
     }
 }
 
-int gridFor(const DeviceSystem& S) { return S.numTiles + S.numFreeBlocks; }
+template <bool EXACT, bool FUSED>
+cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    const size_t smem = FUSED ? sizeof(Part1Smem) : offsetof(Part1Smem, d);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(part1Kernel<EXACT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    // persistent CTAs: one wave that fills every SM
+    const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
+    const int work = tiles > 0 ? tiles : S.numFreeBlocks;
+    const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
+    part1Kernel<EXACT, FUSED><<<work < resident ? work : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
+    if (!FUSED && S.numTiles > 0) atomPositionKernel<<<S.numTiles, kBlock, 0, st>>>(S, pos);
+    return cudaGetLastError();
+}
 
 } // namespace
 
 cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(part1Kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Part1Smem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(part1Kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Part1Smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    // persistent CTAs: one wave that fills every SM
-    const int work = S.numTiles > 0 ? S.numTiles : S.numFreeBlocks;
-    const int resident = S.numSMs*(S.rotationMode == 0 ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
-    const int grid = work < resident ? work : resident;
-    if (S.rotationMode == 0) part1Kernel<true><<<grid, kBlock, sizeof(Part1Smem), st>>>(S, dt, pos, vel, force);
-    else part1Kernel<false><<<grid, kBlock, sizeof(Part1Smem), st>>>(S, dt, pos, vel, force);
-    return cudaGetLastError();
+    const bool exact = S.rotationMode == 0, fused = !S.splitPart1;
+    if (exact) return fused ? launchPart1Variant<true, true>(S, dt, pos, vel, force, st) : launchPart1Variant<true, false>(S, dt, pos, vel, force, st);
+    return fused ? launchPart1Variant<false, true>(S, dt, pos, vel, force, st) : launchPart1Variant<false, false>(S, dt, pos, vel, force, st);
 }
 
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    const int grid = gridFor(S);
+    const int grid = S.numTiles + S.numFreeBlocks;
     if (grid == 0) return cudaSuccess;
     part2Kernel<<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
@@ -432,5 +476,7 @@ cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, 
     kineticKernel<<<kKineticBlocks, kKinThreads, 0, st>>>(S, vel, partial, counter, out);
     return cudaGetLastError();
 }
+
+int part1LaunchesPerStep(const DeviceSystem& S) { return (S.splitPart1 && S.numTiles > 0) ? 2 : 1; }
 
 } // namespace rbk
