@@ -72,11 +72,17 @@ RBK_HD d3 quatCt(d4 q, d4 y) {
 // body frame -> space frame: A^T(q) v = C^T(q) B(q) v
 RBK_HD d3 bodyToSpace(d4 q, d3 v) { return quatCt(q, quatB(q, v)); }
 
-// sin and cos for the small angles of a single time step: the classic minimax kernels on [-pi/4, pi/4]
-// (error < 1 ulp) without range reduction; anything larger takes the library routine.
+// sin and cos for the small angles of a single time step, without range reduction:
+//   |x| <= 1/32 : truncated Maclaurin series (remainders x^9/9! and x^10/10! are < 2e-18 relative),
+//   |x| <= pi/4 : the classic minimax kernels (error < 1 ulp),
+//   otherwise   : the library routine.
 RBK_HD void sincosStep(double x, double* s, double* c) {
-    if (fabs(x) <= 0.78539816339744830962) {
-        const double z = x*x;
+    const double z = x*x;
+    if (z <= 9.765625e-4) {
+        *s = x + x*z*(-1.0/6.0 + z*(1.0/120.0 + z*(-1.0/5040.0)));
+        *c = 1.0 + z*(-0.5 + z*(1.0/24.0 + z*(-1.0/720.0 + z*(1.0/40320.0))));
+    }
+    else if (z <= 0.6168502750680849) {
         const double ps = -1.66666666666666324348e-01 + z*(8.33333333332248946124e-03 + z*(-1.98412698298579493134e-04
                         + z*(2.75573137070700676789e-06 + z*(-2.50507602534068634195e-08 + z*1.58969099521155010221e-10))));
         const double pc = 4.16666666666666019037e-02 + z*(-1.38888888888741095749e-03 + z*(2.48015872894767294178e-05
@@ -95,27 +101,31 @@ template <int K> RBK_HD d4 quatPerm(d4 q) {
     return {-q.z,  q.y, -q.x,  q.w};
 }
 
-// One uniaxial free rotation about principal axis K for time h.
-template <int K> RBK_HD void uniaxial(double h, double invIk, d4& q, d4& pi) {
-    d4 Bq = quatPerm<K>(q);
-    double phi = 0.25*dot(pi, Bq)*h*invIk;
+// One uniaxial free rotation about principal axis K; quarterHinvI = h/(4 I_K).
+template <int K> RBK_HD void uniaxialScaled(double quarterHinvI, d4& q, d4& pi) {
+    const d4 Bq = quatPerm<K>(q);
+    const double phi = dot(pi, Bq)*quarterHinvI;
     double s, c;
     sincosStep(phi, &s, &c);
-    d4 Bp = quatPerm<K>(pi);
+    const d4 Bp = quatPerm<K>(pi);
     q = q*c + Bq*s;
     pi = pi*c + Bp*s;
 }
+template <int K> RBK_HD void uniaxial(double h, double invIk, d4& q, d4& pi) { uniaxialScaled<K>(0.25*h*invIk, q, pi); }
 
 // NO-SQUISH: n sub-steps of R3(h/2) R2(h/2) R1(h) R2(h/2) R3(h/2); axis 3 skipped for linear bodies.
+// Consecutive half rotations about axis 3 of neighbouring sub-steps are flows of the same one-axis
+// Hamiltonian and are applied as one rotation over h (identical map, 4n+1 instead of 5n rotations).
 RBK_HD void noSquish(double dt, int n, d3 invI, d4& q, d4& pi) {
-    const double h = dt/n, hh = 0.5*h;
+    const double h = dt/n;
+    const double k1 = 0.25*h*invI.x, k2 = 0.125*h*invI.y, k3 = 0.25*h*invI.z;
     const bool axis3 = invI.z != 0.0;            // dof == 6 (linear bodies carry invI.z = 0)
+    if (axis3) uniaxialScaled<2>(0.5*k3, q, pi);
     for (int i = 0; i < n; i++) {
-        if (axis3) uniaxial<2>(hh, invI.z, q, pi);
-        uniaxial<1>(hh, invI.y, q, pi);
-        uniaxial<0>(h, invI.x, q, pi);
-        uniaxial<1>(hh, invI.y, q, pi);
-        if (axis3) uniaxial<2>(hh, invI.z, q, pi);
+        uniaxialScaled<1>(k2, q, pi);
+        uniaxialScaled<0>(k1, q, pi);
+        uniaxialScaled<1>(k2, q, pi);
+        if (axis3) uniaxialScaled<2>(i == n - 1 ? 0.5*k3 : k3, q, pi);
     }
 }
 
@@ -362,37 +372,50 @@ RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
     const double ca = dt*(invI.z - invI.y), cb = dt*(invI.x - invI.z), cc = dt*(invI.y - invI.x);
     r[0] = 1.0/(L - x[0]);
     double sx = x[0], sy = y[0], sz = z[0], sr = r[0];
+    // Order k+1 from orders 0..k.  Each Cauchy product is summed so that the terms containing the
+    // NEWEST coefficients (index k) come last: everything else of order k+1 only needs orders < k and
+    // overlaps with the tail of order k, which keeps the fp64 pipe fed from a single warp.
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        // Cauchy products, two independent accumulation chains each (ILP for the fp64 pipe)
-        double px = 0.0, py = 0.0, pz = 0.0, px2 = 0.0, py2 = 0.0, pz2 = 0.0;
+        double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
 #pragma unroll
-        for (int j = 0; j <= k; j += 2) {
-            px = fma(y[j], z[k - j], px);
-            py = fma(z[j], x[k - j], py);
-            pz = fma(x[j], y[k - j], pz);
-            if (j + 1 <= k) {
-                px2 = fma(y[j + 1], z[k - j - 1], px2);
-                py2 = fma(z[j + 1], x[k - j - 1], py2);
-                pz2 = fma(x[j + 1], y[k - j - 1], pz2);
+        for (int j = 1; j <= k - 1; j += 2) {
+            ax = fma(y[j], z[k - j], ax);
+            ay = fma(z[j], x[k - j], ay);
+            az = fma(x[j], y[k - j], az);
+            if (j + 1 <= k - 1) {
+                bx = fma(y[j + 1], z[k - j - 1], bx);
+                by = fma(z[j + 1], x[k - j - 1], by);
+                bz = fma(x[j + 1], y[k - j - 1], bz);
             }
         }
-        const double f = 1.0/(k + 1);
-        x[k + 1] = (ca*f)*(px + px2);
-        y[k + 1] = (cb*f)*(py + py2);
-        z[k + 1] = (cc*f)*(pz + pz2);
-        double pr = 0.0, pr2 = 0.0;
-#pragma unroll
-        for (int j = 1; j <= k + 1; j += 2) {
-            pr = fma(x[j], r[k + 1 - j], pr);
-            if (j + 1 <= k + 1) pr2 = fma(x[j + 1], r[k - j], pr2);
+        double ex, ey, ez;
+        if (k == 0) { ex = y[0]*z[0]; ey = z[0]*x[0]; ez = x[0]*y[0]; }
+        else {
+            ex = fma(y[0], z[k], y[k]*z[0]);
+            ey = fma(z[0], x[k], z[k]*x[0]);
+            ez = fma(x[0], y[k], x[k]*y[0]);
         }
-        r[k + 1] = (pr + pr2)*r[0];
+        const double f = 1.0/(k + 1);
+        x[k + 1] = (ca*f)*((ax + bx) + ex);
+        y[k + 1] = (cb*f)*((ay + by) + ey);
+        z[k + 1] = (cc*f)*((az + bz) + ez);
         sx += x[k + 1]; sy += y[k + 1]; sz += z[k + 1];
+        // reciprocal series: r[k+1] = r0 * sum_{j=1..k+1} x[j] r[k+1-j]; the term with the newest r (j = 1) and
+        // the one with the newest x (j = k+1) come last
+        double ar = 0.0, br = 0.0;
+#pragma unroll
+        for (int j = 2; j <= k; j += 2) {
+            ar = fma(x[j], r[k + 1 - j], ar);
+            if (j + 1 <= k) br = fma(x[j + 1], r[k - j], br);
+        }
+        double er = x[k + 1]*r[0];
+        if (k >= 1) er = fma(x[1], r[k], er);
+        r[k + 1] = ((ar + br) + er)*r[0];
         sr = fma(r[k + 1], 1.0/(k + 2), sr);
     }
-    // truncation check on the last two orders of every series (relative to L, resp. r[0])
     const double tailL = fabs(x[K]) + fabs(y[K]) + fabs(z[K]) + fabs(x[K - 1]) + fabs(y[K - 1]) + fabs(z[K - 1]);
+    // truncation check on the last two orders of every series (relative to L, resp. r[0])
     const double tailR = fabs(r[K]) + fabs(r[K - 1]);
     if (!(tailL <= 2.0e-16*L && tailR <= 2.0e-16*fabs(r[0]))) return false;
     const double theta = 0.5*dt*(L*invI.x + (twoT - Lsq*invI.x)*sr);
@@ -409,13 +432,17 @@ RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
     return true;
 }
 
-constexpr int kSeriesOrder = 16;
+#ifndef RBK_SERIES_ORDER
+#define RBK_SERIES_ORDER 14
+#endif
+constexpr int kSeriesOrder = RBK_SERIES_ORDER;
 
-// Mode 0 entry point used by the step.  Order-16 series over dt; if its truncation check fails
-// (fast rotor / long step) four quarter steps - the composition of exact flows is exact and the tail
-// shrinks by 4^16 - and only then the elliptic-integral route, which needs I = 1/invI.
+// Mode 0 entry point used by the step.  One series step over dt; if its truncation check fails (fast
+// rotor / long step) the step is redone as 2, then 4 exact sub-steps - the composition of exact flows is
+// exact and every halving shrinks the tail by 2^order - and only then by the elliptic-integral route,
+// which needs I = 1/invI.
 RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
-    for (int n = 1; n <= 4; n <<= 2) {
+    for (int n = 1; n <= 4; n <<= 1) {
         d4 q1 = q, p1 = pi;
         const double h = dt/n;
         bool ok = true;
