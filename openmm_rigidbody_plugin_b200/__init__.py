@@ -7,6 +7,10 @@ package does not load the library; constructing any system does, and fails loudl
 from ._lib import RBK_LAYOUT_SOA, RBK_LAYOUT_VEC3, OpenMMException, RbkError  # noqa: F401
 from .integrator import Context, HarmonicBondForce, RigidBodyIntegrator, RigidBodySystem, State, System  # noqa: F401
 from .system import DeviceRigidBodySystem  # noqa: F401
+from . import serialization  # noqa: F401
+from .forcefield import ForceField  # noqa: F401
+from .statedatareporter import StateDataReporter  # noqa: F401
 
 __all__ = ["DeviceRigidBodySystem", "RbkError", "OpenMMException", "RBK_LAYOUT_VEC3", "RBK_LAYOUT_SOA",
-           "RigidBodyIntegrator", "RigidBodySystem", "System", "Context", "State", "HarmonicBondForce"]
+           "RigidBodyIntegrator", "RigidBodySystem", "System", "Context", "State", "HarmonicBondForce",
+           "ForceField", "StateDataReporter", "serialization"]

@@ -1,0 +1,33 @@
+#ifndef OPENMM_INTEGRATOR_H_
+#define OPENMM_INTEGRATOR_H_
+// shim, see Vec3.h
+#include "State.h"
+#include <string>
+#include <vector>
+namespace OpenMM {
+class Context;
+class ContextImpl;
+class Integrator {
+public:
+    Integrator() : context(NULL), owner(NULL), stepSize(0.0), constraintTol(1e-5) {}
+    virtual ~Integrator() {}
+    virtual double getStepSize() const { return stepSize; }
+    virtual void setStepSize(double size) { stepSize = size; }
+    virtual double getConstraintTolerance() const { return constraintTol; }
+    virtual void setConstraintTolerance(double tol) { constraintTol = tol; }
+    virtual void step(int steps) = 0;
+protected:
+    friend class Context;
+    friend class ContextImpl;
+    ContextImpl* context;
+    Context* owner;
+    virtual void initialize(ContextImpl& context) = 0;
+    virtual void cleanup() {}
+    virtual std::vector<std::string> getKernelNames() = 0;
+    virtual void stateChanged(State::DataType changed) {}
+    virtual double computeKineticEnergy() = 0;
+private:
+    double stepSize, constraintTol;
+};
+}
+#endif

@@ -1,0 +1,166 @@
+// Integration tests of the C++ glue on the GPU, in the style of the reference's tests/TestRigidBodyIntegrator.h:
+// testSingleBond is the reference's own test (two free atoms on a harmonic bond against the analytic solution);
+// the other tests exercise what that file leaves commented out or never covered: actual rigid bodies.
+#include "B200RigidBodyKernelFactory.h"
+#include "RigidBodyIntegrator.h"
+#include "openmm/Context.h"
+#include "openmm/HarmonicBondForce.h"
+#include "openmm/OpenMMException.h"
+#include "openmm/reference/ReferencePlatform.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace RigidBodyPlugin;
+using namespace OpenMM;
+using namespace std;
+
+#define ASSERT(cond) do { if (!(cond)) throw runtime_error(string("assertion failed: ") + #cond + " (line " + to_string(__LINE__) + ")"); } while (0)
+#define ASSERT_TOL(expected, found, tol) do { double e_ = (expected), f_ = (found); \
+    if (!(fabs(e_ - f_) <= (tol)*max(1.0, fabs(e_)))) throw runtime_error("expected " + to_string(e_) + " found " + to_string(f_) + " (line " + to_string(__LINE__) + ")"); } while (0)
+#define ASSERT_VEC(expected, found, tol) do { Vec3 e_ = (expected), f_ = (found); \
+    for (int c_ = 0; c_ < 3; c_++) if (!(fabs(e_[c_] - f_[c_]) <= (tol))) throw runtime_error("vector mismatch (line " + to_string(__LINE__) + ")"); } while (0)
+
+static void testSingleBond(Platform& platform) {
+    System system;
+    system.addParticle(2.0);
+    system.addParticle(2.0);
+    vector<int> bodyIndices(2, 0);
+    RigidBodyIntegrator integrator(0.01, bodyIndices);
+    HarmonicBondForce* bond = new HarmonicBondForce();
+    bond->addBond(0, 1, 1.5, 1);
+    system.addForce(bond);
+    Context context(system, integrator, platform);
+    vector<Vec3> positions(2);
+    positions[0] = Vec3(-1, 0, 0);
+    positions[1] = Vec3(1, 0, 0);
+    context.setPositions(positions);
+    const double freq = 1.0;
+    State state = context.getState(State::Energy);
+    const double initialEnergy = state.getKineticEnergy() + state.getPotentialEnergy();
+    for (int i = 0; i < 1000; ++i) {
+        state = context.getState(State::Positions | State::Velocities | State::Energy);
+        double time = state.getTime();
+        double dist = 1.5 + 0.5*cos(freq*time);
+        ASSERT_VEC(Vec3(-0.5*dist, 0, 0), state.getPositions()[0], 0.02);
+        ASSERT_VEC(Vec3(0.5*dist, 0, 0), state.getPositions()[1], 0.02);
+        double speed = -0.5*freq*sin(freq*time);
+        ASSERT_VEC(Vec3(-0.5*speed, 0, 0), state.getVelocities()[0], 0.02);
+        ASSERT_VEC(Vec3(0.5*speed, 0, 0), state.getVelocities()[1], 0.02);
+        ASSERT_TOL(initialEnergy, state.getKineticEnergy() + state.getPotentialEnergy(), 0.01);
+        integrator.step(1);
+    }
+    ASSERT_TOL(10.0, context.getState(0).getTime(), 1e-5);
+}
+
+// 64 rigid waters coupled by harmonic bonds between neighbouring oxygens: bodies stay rigid, total energy is
+// conserved to the integrator's accuracy, DOF and the kinetic-energy split are reported like the reference's API.
+static void testRigidWaters(Platform& platform, int mode) {
+    const int nMol = 64;
+    const double rOH = 0.09572, half = 0.5*104.52*M_PI/180.0;
+    System system;
+    vector<int> bodyIndices;
+    vector<Vec3> positions, velocities;
+    unsigned seed = 12345u;
+    auto rnd = [&]() { seed = seed*1664525u + 1013904223u; return (seed >> 8)/16777216.0 - 0.5; };
+    for (int m = 0; m < nMol; m++) {
+        Vec3 c(0.35*(m % 4), 0.35*((m/4) % 4), 0.35*(m/16));
+        system.addParticle(15.99943); system.addParticle(1.007947); system.addParticle(1.007947);
+        positions.push_back(c);
+        positions.push_back(c + Vec3(rOH*sin(half), 0, rOH*cos(half)));
+        positions.push_back(c + Vec3(-rOH*sin(half), 0, rOH*cos(half)));
+        for (int k = 0; k < 3; k++) { bodyIndices.push_back(m + 1); velocities.push_back(Vec3(rnd(), rnd(), rnd())); }
+    }
+    HarmonicBondForce* bonds = new HarmonicBondForce();
+    for (int m = 0; m + 1 < nMol; m++) bonds->addBond(3*m, 3*(m + 1), 0.33, 2000.0);
+    for (int m = 0; m + 4 < nMol; m++) bonds->addBond(3*m + 1, 3*(m + 4) + 2, 0.36, 500.0);
+    system.addForce(bonds);
+    RigidBodyIntegrator integrator(0.001, bodyIndices);
+    integrator.setRotationMode(mode);
+    Context context(system, integrator, platform);
+    context.setPositions(positions);
+    context.setVelocities(velocities);
+    ASSERT(integrator.getRigidBodySystem().getNumBodies() == nMol);
+    ASSERT(integrator.getRigidBodySystem().getNumFree() == 0);
+    ASSERT(integrator.getRigidBodySystem().getNumDOF() == 6*nMol);
+    State s0 = context.getState(State::Energy);
+    const double e0 = s0.getKineticEnergy() + s0.getPotentialEnergy();
+    for (int block = 0; block < 10; block++) {
+        integrator.step(100);
+        State s = context.getState(State::Positions | State::Velocities | State::Energy);
+        ASSERT_TOL(e0, s.getKineticEnergy() + s.getPotentialEnergy(), 2e-3);
+        vector<double> ke = integrator.getKineticEnergies();
+        ASSERT_TOL(s.getKineticEnergy(), ke[0] + ke[1], 1e-12);
+        ASSERT_TOL(ke[0] + ke[1], integrator.getRigidBodySystem().getKineticEnergy(), 1e-12);
+        for (int m = 0; m < nMol; m++) {                       // every molecule is still a rigid TIP3P water
+            Vec3 a = s.getPositions()[3*m + 1] - s.getPositions()[3*m], b = s.getPositions()[3*m + 2] - s.getPositions()[3*m];
+            ASSERT_TOL(rOH, sqrt(a.dot(a)), 1e-11);
+            ASSERT_TOL(rOH, sqrt(b.dot(b)), 1e-11);
+            ASSERT_TOL(cos(2*half), a.dot(b)/(rOH*rOH), 1e-10);
+            Vec3 dv = s.getVelocities()[3*m + 1] - s.getVelocities()[3*m];
+            ASSERT(fabs(dv.dot(a)) < 1e-10);                   // no velocity along a rigid bond
+        }
+    }
+    ASSERT_TOL(1.0, context.getState(0).getTime(), 1e-9);
+    vector<double> refined = integrator.getRefinedKineticEnergies();
+    vector<double> plain = integrator.getKineticEnergies();
+    ASSERT(refined[0] == plain[0] && refined[1] == plain[1]);
+    ASSERT(integrator.getPotentialEnergyRefinement() == 0.0);
+}
+
+static void testErrors(Platform& platform) {
+    System system;
+    for (int i = 0; i < 4; i++) system.addParticle(12.0);
+    {
+        vector<int> wrong(3, 0);
+        RigidBodyIntegrator integrator(0.001, wrong);
+        bool thrown = false;
+        try { Context context(system, integrator, platform); } catch (const OpenMMException& e) {
+            thrown = string(e.what()).find("Number of body indices differs") != string::npos;
+        }
+        ASSERT(thrown);
+    }
+    vector<int> idx = {1, 1, 1, 0};
+    RigidBodyIntegrator integrator(0.001, idx);
+    bool thrown = false;
+    try { integrator.setRotationMode(-2); } catch (const OpenMMException& e) { thrown = string(e.what()) == "Rotation mode cannot be negative"; }
+    ASSERT(thrown);
+    thrown = false;
+    try { integrator.step(1); } catch (const OpenMMException& e) { thrown = string(e.what()).find("not bound to a context") != string::npos; }
+    ASSERT(thrown);
+    Context context(system, integrator, platform);
+    thrown = false;
+    try { integrator.setRotationMode(2); } catch (const OpenMMException& e) { thrown = string(e.what()).find("already bound to a context") != string::npos; }
+    ASSERT(thrown);
+    System constrained;
+    for (int i = 0; i < 4; i++) constrained.addParticle(12.0);
+    constrained.addConstraint(0, 3, 0.1);
+    RigidBodyIntegrator integrator2(0.001, idx);
+    thrown = false;
+    try { Context c2(constrained, integrator2, platform); } catch (const OpenMMException& e) {
+        thrown = string(e.what()) == "Constraints involving rigid-body atoms are not allowed";
+    }
+    ASSERT(thrown);
+}
+
+int main() {
+    try {
+        ReferencePlatform* platform = new ReferencePlatform();
+        Platform::registerPlatform(platform);
+        registerRigidBodyB200KernelFactories();
+        testErrors(*platform);
+        testSingleBond(*platform);
+        testRigidWaters(*platform, 0);
+        testRigidWaters(*platform, 3);
+    }
+    catch (const exception& e) {
+        cout << "exception: " << e.what() << endl;
+        return 1;
+    }
+    cout << "Done" << endl;
+    return 0;
+}
