@@ -120,6 +120,23 @@ typedef void (*rbk_force_fn)(const double* R, double* F, int numAtoms, void* use
 int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F,
                      rbk_force_fn forces, void* user, void* stream);
 
+/* ---- OpenMM-CUDA boundary formats ------------------------------------------------------------
+ * The device arrays OpenMM's CUDA platform hands to an integrator kernel (what the reference's CUDA kernels
+ * read and write, platforms/cuda/src/kernels/rigidbodyintegrator.cu:30-64,270-279 and
+ * platforms/cuda/src/CudaRigidBodyKernels.cpp:389-403): posq = real4 (xyz + charge), in mixed precision with a
+ * second float4 array posqCorrection holding the low-order part; velm = mixed4 (xyz + inverse mass);
+ * force = long long[3*paddedNumAtoms], one plane per component, fixed point with scale 2^32.  The kernels read
+ * and write these formats directly (no conversion pass); .w components are never modified.  Atom order is
+ * OpenMM's reordered order: pass the mapping with rbk_set_atom_location after every reorder. */
+#define RBK_OPENMM_SINGLE 0   /* posq float4,            velm float4  */
+#define RBK_OPENMM_MIXED  1   /* posq float4 + correction, velm double4 */
+#define RBK_OPENMM_DOUBLE 2   /* posq double4,           velm double4 */
+int rbk_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
+                     int paddedNumAtoms, int precision, void* stream);
+int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
+                     int paddedNumAtoms, int precision, void* stream);
+int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double* out, void* stream);
+
 /* rbk_kinetic for callers that hold velocities on the HOST (Reference-platform data): copies V into the
  * handle's device mirror (only free atoms need it) and runs the same device reduction. */
 int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream);

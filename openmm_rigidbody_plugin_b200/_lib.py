@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("RBK_LIB", os.path.join(_HERE, "lib", "librbk.so"))   
 
 RBK_LAYOUT_VEC3 = 0
 RBK_LAYOUT_SOA = 1
+RBK_OPENMM_SINGLE, RBK_OPENMM_MIXED, RBK_OPENMM_DOUBLE = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -32,6 +33,9 @@ SIGNATURES = {
     "rbk_part1": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "rbk_part2": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "rbk_kinetic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, _dp, C.c_void_p]),
+    "rbk_part1_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rbk_part2_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rbk_kinetic_openmm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_void_p]),
     "rbk_kinetic_host": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.c_void_p]),
     "rbk_download_bodies": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_void_p]),
     "rbk_execute_host": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, FORCE_FN, C.c_void_p, C.c_void_p]),

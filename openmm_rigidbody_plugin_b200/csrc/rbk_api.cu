@@ -190,6 +190,8 @@ int setLocation(rbk_system* sys, const int* location, cudaStream_t st) {
 
 int viewOf(const void* p, int layout, long long stride, AtomView& v) {
     v.p = (double*) p;
+    v.fmt = rbk::FMT_F64;
+    v.aux = nullptr;
     if (layout == RBK_LAYOUT_VEC3) { v.sa = 3; v.sc = 1; }
     else if (layout == RBK_LAYOUT_SOA) {
         if (stride <= 0) return fail(RBK_EINVAL, "RBK_LAYOUT_SOA needs a positive plane stride");
@@ -375,6 +377,57 @@ int rbk_kinetic(rbk_system* sys, const double* vel, int layout, long long stride
     return RBK_OK;
 }
 
+namespace {
+int openmmViews(void* posq, void* posqCorrection, void* velm, const long long* force, int paddedNumAtoms, int precision,
+                AtomView& p, AtomView& v, AtomView& f) {
+    if (paddedNumAtoms <= 0) return fail(RBK_EINVAL, "OpenMM layout: paddedNumAtoms must be positive");
+    p = AtomView{(double*) posq, 0, 0, 0, nullptr};
+    v = AtomView{(double*) velm, 0, 0, 0, nullptr};
+    f = AtomView{(double*) force, 1, (long long) paddedNumAtoms, rbk::FMT_FORCE_FIXED, nullptr};
+    if (precision == RBK_OPENMM_SINGLE) { p.fmt = rbk::FMT_REAL4_F32; v.fmt = rbk::FMT_REAL4_F32; }
+    else if (precision == RBK_OPENMM_MIXED) {
+        if (!posqCorrection) return fail(RBK_EINVAL, "OpenMM mixed precision needs posqCorrection");
+        p.fmt = rbk::FMT_POSQ_MIXED; p.aux = posqCorrection; v.fmt = rbk::FMT_REAL4_F64;
+    }
+    else if (precision == RBK_OPENMM_DOUBLE) { p.fmt = rbk::FMT_REAL4_F64; v.fmt = rbk::FMT_REAL4_F64; }
+    else return fail(RBK_EINVAL, "unknown OpenMM precision");
+    return RBK_OK;
+}
+} // namespace
+
+int rbk_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
+                     int paddedNumAtoms, int precision, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_part1_openmm: NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part1_openmm: body system not uploaded");
+    AtomView p, v, f;
+    if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
+    RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
+                     int paddedNumAtoms, int precision, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_part2_openmm: NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2_openmm: body system not uploaded");
+    AtomView p, v, f;
+    if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
+    RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double* out, void* stream) {
+    if (!sys || !out) return fail(RBK_EINVAL, "rbk_kinetic_openmm: NULL argument");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_kinetic_openmm: body system not uploaded");
+    cudaStream_t st = (cudaStream_t) stream;
+    AtomView v{(double*) velm, 0, 0, precision == RBK_OPENMM_SINGLE ? rbk::FMT_REAL4_F32 : rbk::FMT_REAL4_F64, nullptr};
+    RBK_CUDA(rbk::launchKinetic(sys->dev, v, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
+    RBK_CUDA(cudaMemcpyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    out[0] = sys->hKinOut[0];
+    out[1] = sys->hKinOut[1];
+    return RBK_OK;
+}
+
 int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream) {
     if (!sys || !V || !out) return fail(RBK_EINVAL, "rbk_kinetic_host: NULL argument");
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_kinetic_host: body system not uploaded");
@@ -439,7 +492,7 @@ int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V
         RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
         sys->mirrorsLoaded = true;
     }
-    const AtomView p{sys->mPos, 3, 1}, v{sys->mVel, 3, 1}, f{sys->mForce, 3, 1};
+    const AtomView p{sys->mPos, 3, 1, rbk::FMT_F64, nullptr}, v{sys->mVel, 3, 1, rbk::FMT_F64, nullptr}, f{sys->mForce, 3, 1, rbk::FMT_F64, nullptr};
     for (int i = 0; i < steps; i++) {
         RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, f, st));
         RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));

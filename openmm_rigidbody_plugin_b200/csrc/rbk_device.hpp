@@ -43,10 +43,18 @@ struct DeviceSystem {
     double* savedPos;
 };
 
-// Caller-owned atom arrays: element (atom i, component c) lives at p[i*sa + c*sc].
+// Caller-owned atom arrays.  fmt selects how atom i's three components are stored:
+//   FMT_F64       double, component c at p[i*sa + c*sc]           (RBK_LAYOUT_VEC3: sa=3, sc=1; RBK_LAYOUT_SOA: sa=1, sc=stride)
+//   FMT_POSQ_MIXED  OpenMM-CUDA mixed precision positions: float4 posq[i] + float4 posqCorrection[i] (aux); .w untouched
+//   FMT_REAL4_F64 double4 per atom (OpenMM posq in double precision, velm in mixed/double); .w untouched
+//   FMT_REAL4_F32 float4 per atom (OpenMM single precision posq / velm); .w untouched
+//   FMT_FORCE_FIXED OpenMM-CUDA forces: long long planes x[sc] y[sc] z[sc], fixed point with scale 2^32 (read only)
+enum AtomFormat : int { FMT_F64 = 0, FMT_POSQ_MIXED = 1, FMT_REAL4_F64 = 2, FMT_REAL4_F32 = 3, FMT_FORCE_FIXED = 4 };
 struct AtomView {
     double* p;
     long long sa, sc;
+    int fmt;
+    void* aux;
 };
 
 cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);

@@ -36,12 +36,60 @@ __device__ __forceinline__ void storePlane4(double* base, size_t stride, d4 v) {
     base[0] = v.w; base[stride] = v.x; base[2*stride] = v.y; base[3*stride] = v.z;
 }
 __device__ __forceinline__ d3 loadAtom(const AtomView& A, long long i) {
-    const double* p = A.p + i*A.sa;
-    return {p[0], p[A.sc], p[2*A.sc]};
+    if (A.fmt == FMT_F64) {                                    // the fp64 layouts of the integrator-only path
+        const double* p = A.p + i*A.sa;
+        return {p[0], p[A.sc], p[2*A.sc]};
+    }
+    if (A.fmt == FMT_POSQ_MIXED) {                             // OpenMM-CUDA boundary formats (uniform branch)
+        const float4 hi = reinterpret_cast<const float4*>(A.p)[i], lo = reinterpret_cast<const float4*>(A.aux)[i];
+        return {(double) hi.x + (double) lo.x, (double) hi.y + (double) lo.y, (double) hi.z + (double) lo.z};
+    }
+    if (A.fmt == FMT_REAL4_F64) {
+        const double2* p = reinterpret_cast<const double2*>(A.p) + 2*i;
+        const double2 xy = p[0];
+        return {xy.x, xy.y, p[1].x};
+    }
+    if (A.fmt == FMT_REAL4_F32) {
+        const float4 v = reinterpret_cast<const float4*>(A.p)[i];
+        return {(double) v.x, (double) v.y, (double) v.z};
+    }
+    const long long* f = reinterpret_cast<const long long*>(A.p) + i;      // FMT_FORCE_FIXED
+    const double scale = 1.0/4294967296.0;
+    return {scale*(double) f[0], scale*(double) f[A.sc], scale*(double) f[2*A.sc]};
 }
 __device__ __forceinline__ void storeAtom(const AtomView& A, long long i, d3 v) {
-    double* p = A.p + i*A.sa;
-    p[0] = v.x; p[A.sc] = v.y; p[2*A.sc] = v.z;
+    if (A.fmt == FMT_F64) {
+        double* p = A.p + i*A.sa;
+        p[0] = v.x; p[A.sc] = v.y; p[2*A.sc] = v.z;
+    }
+    else if (A.fmt == FMT_POSQ_MIXED) {                        // value = (float) hi + (float) lo, charge (.w) untouched
+        float* hi = reinterpret_cast<float*>(A.p) + 4*i;
+        float* lo = reinterpret_cast<float*>(A.aux) + 4*i;
+        const float hx = (float) v.x, hy = (float) v.y, hz = (float) v.z;
+        hi[0] = hx; hi[1] = hy; hi[2] = hz;
+        lo[0] = (float) (v.x - (double) hx); lo[1] = (float) (v.y - (double) hy); lo[2] = (float) (v.z - (double) hz);
+    }
+    else if (A.fmt == FMT_REAL4_F64) {                         // .w (charge / inverse mass) untouched
+        double* p = A.p + 4*i;
+        *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
+        p[2] = v.z;
+    }
+    else if (A.fmt == FMT_REAL4_F32) {
+        float* p = reinterpret_cast<float*>(A.p) + 4*i;
+        p[0] = (float) v.x; p[1] = (float) v.y; p[2] = (float) v.z;
+    }
+}
+// The value a later loadAtom will return for v once it has been stored in A's format (identity for fp64).
+// Free atoms keep it as savedPos, so that (x - savedPos)/dt in part 2 is exactly zero without constraints,
+// whatever precision the caller's position array has.
+__device__ __forceinline__ d3 asStored(const AtomView& A, d3 v) {
+    if (A.fmt == FMT_POSQ_MIXED) {
+        const float hx = (float) v.x, hy = (float) v.y, hz = (float) v.z;
+        return {(double) hx + (double) (float) (v.x - (double) hx), (double) hy + (double) (float) (v.y - (double) hy),
+                (double) hz + (double) (float) (v.z - (double) hz)};
+    }
+    if (A.fmt == FMT_REAL4_F32) return {(double) (float) v.x, (double) (float) v.y, (double) (float) v.z};
+    return v;
 }
 // plugin-order atom slot -> index in the caller's arrays
 __device__ __forceinline__ long long atomSlot(const DeviceSystem& S, int pluginIndex) {
@@ -212,7 +260,7 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
                 freePart1(dt, loadAtom(force, gi), S.freeInvMass[k], x, v);
                 storeAtom(vel, gi, v);
                 storeAtom(pos, gi, x);
-                storePlane3(S.savedPos + k, S.freeStride, x);
+                storePlane3(S.savedPos + k, S.freeStride, asStored(pos, x));
             }
         }
     }

@@ -147,6 +147,20 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_kinetic(self.h, _ptr(vel), lay, stride, _d(out), _stream(stream)))
         return out
 
+    # ---- OpenMM-CUDA boundary formats (posq real4 [+ correction], velm mixed4, int64 fixed-point force planes)
+    def part1_openmm(self, dt, posq, posqCorrection, velm, force, paddedNumAtoms, precision, stream=None):
+        check(self.lib.rbk_part1_openmm(self.h, float(dt), _ptr(posq), _ptr(posqCorrection), _ptr(velm), _ptr(force),
+                                        int(paddedNumAtoms), int(precision), _stream(stream)))
+
+    def part2_openmm(self, dt, posq, posqCorrection, velm, force, paddedNumAtoms, precision, stream=None):
+        check(self.lib.rbk_part2_openmm(self.h, float(dt), _ptr(posq), _ptr(posqCorrection), _ptr(velm), _ptr(force),
+                                        int(paddedNumAtoms), int(precision), _stream(stream)))
+
+    def kinetic_openmm(self, velm, precision, stream=None):
+        out = np.zeros(2)
+        check(self.lib.rbk_kinetic_openmm(self.h, _ptr(velm), int(precision), _d(out), _stream(stream)))
+        return out
+
     def kinetic_host(self, V, stream=None):
         """Kinetic energies for host-resident velocities [N,3] (numpy or pinned torch CPU tensor)."""
         out = np.zeros(2)
