@@ -78,6 +78,15 @@ int rbk_get_body_fixed(const rbk_system* sys, double* d);  /* [numBodyAtoms][3] 
  * copy the whole host body model to the device in SoA form. */
 int rbk_upload(rbk_system* sys, void* stream);
 
+/* rbk_update + rbk_upload without leaving the device: RigidBodySystem::update (RigidBodySystem.cpp:120-142) evaluated by
+ * one thread per body directly on the caller's DEVICE arrays, writing the body state and body-frame coordinates in
+ * place (no host rebuild, no upload).  Same rounding as the host model except for libm's acos/cos (agreement ~1e-15).
+ * The dynamics build SETS p = sum m v (the reference accumulates into its stale host copy when velocities are set
+ * twice).  Afterwards the host copy of the bodies is stale: rbk_get_host_bodies fails, use rbk_download_bodies.
+ * If the caller's atoms are reordered, call rbk_upload once (or this function) and rbk_set_atom_location first. */
+int rbk_update_device(rbk_system* sys, const double* pos, const double* vel, const double* force, int layout,
+                      long long stride, int geometry, int velocities, void* stream);
+
 /* Replace the plugin-order -> caller-order atom map (CUDA platform's atomLocation,
  * CudaRigidBodyKernels.cpp:277-284 and ReorderListener :69-113).  location[i] is the index in the
  * caller's pos/vel/force arrays of plugin atom i (i indexes rbk_get_atom_index order).
@@ -136,6 +145,8 @@ int rbk_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
 int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
                      int paddedNumAtoms, int precision, void* stream);
 int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double* out, void* stream);
+int rbk_update_device_openmm(rbk_system* sys, void* posq, void* posqCorrection, void* velm, const long long* force,
+                             int paddedNumAtoms, int precision, int geometry, int velocities, void* stream);
 
 /* rbk_kinetic for callers that hold velocities on the HOST (Reference-platform data): copies V into the
  * handle's device mirror (only free atoms need it) and runs the same device reduction. */

@@ -29,6 +29,8 @@ SIGNATURES = {
     "rbk_get_host_bodies": (C.c_int, [C.c_void_p, _ip, _ip, _ip] + [_dp] * 10),
     "rbk_get_body_fixed": (C.c_int, [C.c_void_p, _dp]),
     "rbk_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rbk_update_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "rbk_update_device_openmm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rbk_set_atom_location": (C.c_int, [C.c_void_p, _ip, C.c_void_p]),
     "rbk_part1": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "rbk_part2": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),

@@ -55,6 +55,9 @@ struct rbk_system {
     int* dAtomLoc = nullptr;
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
+    double* dAtomMass = nullptr;     // body atoms, plugin order (GPU-side body build)
+    int* dDofSum = nullptr;
+    bool hostStale = false;          // device build used: the host copy of the bodies is not current
     double* dKinPartial = nullptr;
     unsigned* dKinCounter = nullptr;
     double* dKinOut = nullptr;
@@ -68,7 +71,7 @@ struct rbk_system {
 
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta);
-        cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dKinPartial);
+        cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce);
         if (hKinOut) cudaFreeHost(hKinOut);
     }
@@ -145,6 +148,12 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
     RBK_CUDA(devAlloc(sys->dFreeInvMass, (size_t) std::max(nF, 1)));
     RBK_CUDA(devAlloc(sys->dSavedPos, d.freeStride*3));
+    std::vector<double> atomMass((size_t) std::max(nA, 1), 0.0);
+    for (int a = 0; a < nA; a++) atomMass[a] = h.mass[h.atomIndex[(size_t) nF + a]];
+    RBK_CUDA(devAlloc(sys->dAtomMass, atomMass.size()));
+    RBK_CUDA(devAlloc(sys->dDofSum, 1));
+    RBK_CUDA(cudaMemcpyAsync(sys->dAtomMass, atomMass.data(), atomMass.size()*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaMemsetAsync(sys->dState, 0, d.bodyStride*rbk::NPLANES*sizeof(double), st));
     RBK_CUDA(devAlloc(sys->dKinPartial, (size_t) 2*rbk::kKineticBlocks));
     RBK_CUDA(devAlloc(sys->dKinCounter, 1));
     RBK_CUDA(devAlloc(sys->dKinOut, 2));
@@ -259,12 +268,14 @@ int rbk_update(rbk_system* sys, const double* R, const double* V, const double* 
     if (velocities && !geometry && sys->host.numBodies > 0 && sys->host.body[0].mass == 0.0)
         return fail(RBK_ESTATE, "rbk_update: velocities before any geometry build");
     sys->host.update(R, V, F, geometry != 0, velocities != 0);
+    sys->hostStale = false;
     return RBK_OK;
 }
 
 int rbk_get_host_bodies(const rbk_system* sys, int* N, int* dof, int* loc, double* mass, double* I, double* invI,
                         double* rcm, double* pcm, double* q, double* pi, double* force, double* torque, double* twoK) {
     if (!sys) return fail(RBK_EINVAL, "rbk_get_host_bodies: NULL system");
+    if (sys->hostStale) return fail(RBK_ESTATE, "rbk_get_host_bodies: bodies were built on the device (rbk_update_device); use rbk_download_bodies");
     const HostModel& h = sys->host;
     for (int b = 0; b < h.numBodies; b++) {
         const HostBody& B = h.body[b];
@@ -335,6 +346,39 @@ int rbk_upload(rbk_system* sys, void* stream) {
     sys->uploaded = true;
     sys->mirrorsLoaded = false;
     return RBK_OK;
+}
+
+namespace {
+int updateDevice(rbk_system* sys, AtomView p, AtomView v, AtomView f, int geometry, int velocities, cudaStream_t st) {
+    if (!sys->allocated) {
+        int rc = allocateDevice(sys, st);
+        if (rc != RBK_OK) return rc;
+        rc = setLocation(sys, nullptr, st);
+        if (rc != RBK_OK) return rc;
+    }
+    if (velocities && !geometry && !sys->uploaded) return fail(RBK_ESTATE, "rbk_update_device: velocities before any geometry build");
+    RBK_CUDA(rbk::launchBuild(sys->dev, sys->dAtomMass, p, v, f, sys->dDxyz, geometry != 0, velocities != 0, sys->dDofSum, st));
+    if (geometry) {
+        int dofSum = 0;
+        RBK_CUDA(cudaMemcpyAsync(&dofSum, sys->dDofSum, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RBK_CUDA(cudaStreamSynchronize(st));
+        sys->host.numDOF = sys->host.numFree - sys->host.numConstraints + dofSum;      // RigidBodySystem.cpp:130-134
+    }
+    sys->uploaded = true;
+    sys->hostStale = true;
+    sys->mirrorsLoaded = false;
+    return RBK_OK;
+}
+} // namespace
+
+int rbk_update_device(rbk_system* sys, const double* pos, const double* vel, const double* force, int layout,
+                      long long stride, int geometry, int velocities, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_update_device: NULL system");
+    if (geometry && (!pos || !force)) return fail(RBK_EINVAL, "rbk_update_device: geometry needs positions and forces");
+    if (velocities && !vel) return fail(RBK_EINVAL, "rbk_update_device: velocities needed");
+    AtomView p, v, f;
+    if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
+    return updateDevice(sys, p, v, f, geometry, velocities, (cudaStream_t) stream);
 }
 
 int rbk_set_atom_location(rbk_system* sys, const int* location, void* stream) {
@@ -413,6 +457,14 @@ int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
     if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
     RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, (cudaStream_t) stream));
     return RBK_OK;
+}
+
+int rbk_update_device_openmm(rbk_system* sys, void* posq, void* posqCorrection, void* velm, const long long* force,
+                             int paddedNumAtoms, int precision, int geometry, int velocities, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_update_device_openmm: NULL system");
+    AtomView p, v, f;
+    if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
+    return updateDevice(sys, p, v, f, geometry, velocities, (cudaStream_t) stream);
 }
 
 int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double* out, void* stream) {

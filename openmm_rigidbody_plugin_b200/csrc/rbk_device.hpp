@@ -61,6 +61,9 @@ cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
 // partial: scratch of 2*kKineticBlocks doubles; counter: zero-initialised unsigned; out: 2 doubles (device)
 constexpr int kKineticBlocks = 592;    // 148 SMs x 4
+// GPU-side body build (rbk_build.cu): geometry and/or dynamics of every body from the caller's atom arrays.
+cudaError_t launchBuild(const DeviceSystem& S, const double* atomMass, AtomView pos, AtomView vel, AtomView force,
+                        double* dxyz, bool geometry, bool velocities, int* dofSum, cudaStream_t st);
 int part1LaunchesPerStep(const DeviceSystem& S);   // 1 (fused) or 2 (rotation kernel + atom kernel)
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out, cudaStream_t st);
 

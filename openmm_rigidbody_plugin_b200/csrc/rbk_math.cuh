@@ -18,7 +18,7 @@
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #define RBK_HD __host__ __device__ __forceinline__
-#define RBK_HD_NOINLINE __host__ __device__ __noinline__
+#define RBK_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define RBK_HD inline
 #define RBK_HD_NOINLINE inline

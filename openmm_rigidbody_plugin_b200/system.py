@@ -129,6 +129,18 @@ class DeviceRigidBodySystem:
     def upload(self, stream=None):
         check(self.lib.rbk_upload(self.h, _stream(stream)))
 
+    def update_device(self, pos=None, vel=None, force=None, geometry=True, velocities=True, layout=None, stream=None):
+        """GPU-side body build from device arrays (rbk_update_device): no host rebuild, no upload."""
+        ref = pos if pos is not None else vel
+        lay, stride = _layout(ref, layout)
+        check(self.lib.rbk_update_device(self.h, _ptr(pos), _ptr(vel), _ptr(force), lay, stride, int(geometry), int(velocities),
+                                         _stream(stream)))
+
+    def update_device_openmm(self, posq, posqCorrection, velm, force, paddedNumAtoms, precision, geometry=True,
+                             velocities=True, stream=None):
+        check(self.lib.rbk_update_device_openmm(self.h, _ptr(posq), _ptr(posqCorrection), _ptr(velm), _ptr(force),
+                                                int(paddedNumAtoms), int(precision), int(geometry), int(velocities), _stream(stream)))
+
     def set_atom_location(self, location=None, stream=None):
         loc = None if location is None else np.ascontiguousarray(location, dtype=np.int32)
         check(self.lib.rbk_set_atom_location(self.h, _i(loc), _stream(stream)))
