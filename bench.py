@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--workload", default="water", choices=["water", "mixed"])
     ap.add_argument("--layout", default="vec3", choices=["vec3", "soa"])
+    ap.add_argument("--no-fuse", action="store_true", help="step with separate part1/part2 launches only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -244,30 +245,44 @@ def run_b200_arm(args):
     # after 100 steps), alternating ones keep the system at its 300 K state for any number of steps.
     forces = (dev_array(sysd["F"]), dev_array(-sysd["F"]))
     stream = torch.cuda.current_stream()
-    counter = [0]
+    cur = [0]                 # index of the force buffer of the most recent force "evaluation"
 
     def step():
-        counter[0] += 1
-        force = forces[counter[0] & 1]
-        system.part1(DT, pos, vel, force)
-        system.part2(DT, pos, vel, force)
+        # Part 1 kicks with the forces of the previous evaluation, Part 2 with the new ones - the order in which
+        # the reference's execute() sees them (ReferenceRigidBodyKernels.cpp:97-102)
+        system.part1(DT, pos, vel, forces[cur[0]])
+        cur[0] ^= 1
+        system.part2(DT, pos, vel, forces[cur[0]])
 
     def barrier():
         torch.cuda.synchronize()
         replicas.barrier(dist if world > 1 else None)
         torch.cuda.synchronize()
 
+    def run_steps(k):
+        """k integrator steps the way RigidBodyIntegrator::step(k) runs on this library: part1, then (k-1) times
+        [new forces, part2+part1 in one pass (rbk_part2_part1)], then new forces, part2.  --no-fuse: k x [part1, part2]."""
+        if args.no_fuse:
+            for _ in range(k):
+                step()
+            return 2 * k
+        system.part1(DT, pos, vel, forces[cur[0]])
+        for _ in range(k - 1):
+            cur[0] ^= 1
+            system.part2_part1(DT, pos, vel, forces[cur[0]])
+        cur[0] ^= 1
+        system.part2(DT, pos, vel, forces[cur[0]])
+        return k + 1
+
     ke_start = system.kinetic(vel)
     clocks = ClockSampler(local)
     clocks.start()
-    for _ in range(max(args.warmup, 3)):
-        step()
+    run_steps(max(args.warmup, 3))
     # ---- timed region: exactly K steps, CUDA events on the launching stream, barrier + sync both sides
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
+    launches = run_steps(args.steps)
     e1.record(stream)
     barrier()
     ms = replicas.max_over_ranks(e0.elapsed_time(e1), dist if world > 1 else None, dev)
@@ -275,16 +290,29 @@ def run_b200_arm(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
     torch.cuda.synchronize()
     for i in range(args.steps):
-        counter[0] += 1
-        force = forces[counter[0] & 1]
         ev[3*i].record(stream)
-        system.part1(DT, pos, vel, force)
+        system.part1(DT, pos, vel, forces[cur[0]])
         ev[3*i+1].record(stream)
-        system.part2(DT, pos, vel, force)
+        cur[0] ^= 1
+        system.part2(DT, pos, vel, forces[cur[0]])
         ev[3*i+2].record(stream)
     torch.cuda.synchronize()
     t1 = float(np.mean([ev[3*i].elapsed_time(ev[3*i+1]) for i in range(args.steps)]))
     t2 = float(np.mean([ev[3*i+1].elapsed_time(ev[3*i+2]) for i in range(args.steps)]))
+    fused_ok = (not args.no_fuse) and nB > 0 and nA <= 8 * nB
+    tf = None
+    if fused_ok:          # event-time the one-pass kernel (part 2 of step k + part 1 of step k+1 = one step of work)
+        fe = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        system.part1(DT, pos, vel, forces[cur[0]])
+        for i in range(args.steps):
+            fe[i].record(stream)
+            cur[0] ^= 1
+            system.part2_part1(DT, pos, vel, forces[cur[0]])
+        fe[args.steps].record(stream)
+        cur[0] ^= 1
+        system.part2(DT, pos, vel, forces[cur[0]])
+        torch.cuda.synchronize()
+        tf = float(np.mean([fe[i].elapsed_time(fe[i+1]) for i in range(args.steps)]))
     clk = clocks.stop()
     ke = system.kinetic(vel)
     if not np.isfinite(ke).all():
@@ -295,6 +323,8 @@ def run_b200_arm(args):
     bytes2 = P2_BODY * nB + P2_ATOM * nA + FREE_P2 * nF
     peak, peak_src = measured_peak()
     dom = ("part1", bytes1, t1) if t1 >= t2 else ("part2", bytes2, t2)
+    if tf is not None:
+        dom = ("part2Part1", bytes1 + bytes2, tf)
     ach = dom[1] / (dom[2] * 1e-3) / 1e9
     step_ach = (bytes1 + bytes2) / ((ms / args.steps) * 1e-3) / 1e9
     roofline = {
@@ -304,8 +334,17 @@ def run_b200_arm(args):
         "kernels": {"part1": {"ms": t1, "bytes": bytes1, "GBps": bytes1 / (t1 * 1e-3) / 1e9},
                     "part2": {"ms": t2, "bytes": bytes2, "GBps": bytes2 / (t2 * 1e-3) / 1e9}},
         "step": {"achieved": step_ach, "frac": step_ach / peak, "bytes": bytes1 + bytes2,
-                 "note": "whole step (both kernels) from the 2-event timed region"},
+                 "note": "whole step from the 2-event timed region (all launches, incl. the opening part1 / closing part2)"},
     }
+    if tf is not None:
+        roofline["kernels"]["part2Part1"] = {"ms": tf, "bytes": bytes1 + bytes2, "GBps": (bytes1 + bytes2) / (tf * 1e-3) / 1e9}
+        # what the one-pass kernel itself has to move: state read once (r p q pi 1/m 1/I), written once (r p q pi F tau);
+        # per atom: force + coordinates + body byte in, velocity + position out
+        fused_bytes = (144 + 160) * nB + (49 + 48) * nA + 288 * nF
+        roofline["one_pass_compulsory_bytes"] = fused_bytes
+        roofline["note"] = ("achieved/frac use SURVEY.md's algorithmic bytes of the two-kernel formulation (560+128n per body-step); the "
+                            "one-pass kernel moves fewer compulsory bytes (state resident across the step boundary), so frac can exceed "
+                            "what a two-kernel step could reach; frac_of_one_pass_bytes = " + f"{fused_bytes / (tf * 1e-3) / 1e9 / peak:.3f}")
 
     # ---- e2e: host-buffer call, pinned host R/V/F, copies inside the timed region
     e2e = None
@@ -343,7 +382,7 @@ def run_b200_arm(args):
                        "layout": args.layout, "dt_ps": DT, "bodies": nB, "body_atoms": nA, "free_atoms": nF,
                        "l2": "no flush needed: the per-step working set (state + atoms, >500 MB at 1M waters) exceeds the 126 MB L2"},
             "ns_per_day": (args.steps / (ms * 1e-3)) * DT * 1e-3 * 86400.0,
-            "clocks": clk, "e2e": e2e, "gpu_launches": (3 if nA > 8 * nB else 2) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches * (2 if (nA > 8 * nB and not args.no_fuse) else 1) if not args.no_fuse else (3 if nA > 8 * nB else 2) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "kinetic_energy_kJmol": {"start": [float(ke_start[0]), float(ke_start[1])], "end": [float(ke[0]), float(ke[1])],
                                      "note": "translational, rotational; the workload stays at its initial ~300 K state"},
         }

@@ -106,6 +106,17 @@ int rbk_part1(rbk_system* sys, double dt, double* pos, double* vel, const double
 int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const double* force,
               int layout, long long stride, void* stream);
 
+/* rbk_part2 of step k immediately followed by rbk_part1 of step k+1, as ONE pass over the data - legal because nothing
+ * happens between the two in RigidBodyIntegrator::step (openmmapi/src/RigidBodyIntegrator.cpp:96-101: execute, execute,
+ * ...; the force evaluation sits between Part 1 and Part 2 of the SAME step).  step(n) becomes
+ *     part1, forces, [part2_part1, forces] x (n-1), part2.
+ * Bit-identical to calling rbk_part2 then rbk_part1 with the same arguments; the body state makes one round trip
+ * through HBM instead of two and the body-frame coordinates are read once.  On return `vel` holds the velocities at the
+ * end of step k and `pos` the positions after Part 1 of step k+1 (exactly the state the reference is in when it
+ * evaluates forces). */
+int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force,
+                    int layout, long long stride, void* stream);
+
 /* RigidBodySystem::computeKineticEnergies (RigidBodySystem.cpp:210-220) =
  * IntegrateRigidBodyStepKernel::getKineticEnergies (RigidBodyKernels.h:86): out[0] = translational,
  * out[1] = rotational kinetic energy.  Synchronises `stream` once to return the two doubles. */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "rbk_set_atom_location": (C.c_int, [C.c_void_p, _ip, C.c_void_p]),
     "rbk_part1": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "rbk_part2": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+    "rbk_part2_part1": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "rbk_kinetic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, _dp, C.c_void_p]),
     "rbk_part1_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rbk_part2_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

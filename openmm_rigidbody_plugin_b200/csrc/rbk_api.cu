@@ -125,6 +125,8 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.numTiles = (int) meta.size();
     d.numBodyTiles = (int) bodyMeta.size();
     d.splitPart1 = nB > 0 && (long long) nA > (long long) rbk::kSplitAtomsPerBody*nB;
+    d.fusable = !d.splitPart1;
+    for (const int4& t : meta) if (t.w > rbk::kTileAtoms) d.fusable = 0;
     d.numFreeBlocks = (nF + rbk::kFreePerBlock - 1)/rbk::kFreePerBlock;
     d.rotationMode = h.rotationMode;
     d.maxBodySize = maxSize;
@@ -404,6 +406,16 @@ int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const 
     AtomView p, v, f;
     if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
     RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force, int layout,
+                    long long stride, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_part2_part1: NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2_part1: body system not uploaded");
+    AtomView p, v, f;
+    if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
+    RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, (cudaStream_t) stream));
     return RBK_OK;
 }
 

@@ -23,7 +23,7 @@ constexpr int kBlock = 128;            // threads per CTA = max bodies per tile
 // alone) drive every thread-per-atom phase: many CTAs, coordinates staged in shared memory.  "Body tiles"
 // (<=128 bodies, <=kMaxTileAtoms atoms) drive the stand-alone rotation kernel used when bodies are large,
 // so that its thread-per-body phase runs full warps.  For small bodies (water) the two coincide.
-constexpr int kTileAtoms = 768;
+constexpr int kTileAtoms = 512;
 constexpr int kMaxTileAtoms = 8192;
 constexpr int kSplitAtomsPerBody = 8;  // mean body size above which part 1 runs as rotation kernel + atom kernel
 constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
@@ -31,6 +31,7 @@ constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
 struct DeviceSystem {
     int numBodies, numFree, numBodyAtoms, numTiles, numBodyTiles, numFreeBlocks;
     int rotationMode, maxBodySize, numSMs, splitPart1;
+    int fusable;                 // every atom tile fits the shared-memory staging of the step-fused kernel
     size_t bodyStride, atomStride, freeStride;
     double* state;
     const double* dxyz;
@@ -59,6 +60,8 @@ struct AtomView {
 
 cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
+// part 2 of one step immediately followed by part 1 of the next (identical results, one pass over the data)
+cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
 // partial: scratch of 2*kKineticBlocks doubles; counter: zero-initialised unsigned; out: 2 doubles (device)
 constexpr int kKineticBlocks = 592;    // 148 SMs x 4
 // GPU-side body build (rbk_build.cu): geometry and/or dynamics of every body from the caller's atom arrays.

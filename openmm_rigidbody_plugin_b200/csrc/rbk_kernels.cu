@@ -16,6 +16,7 @@
 #include "rbk_step.cuh"
 
 #include <cstddef>
+#include <cstdlib>
 
 namespace rbk {
 namespace {
@@ -425,6 +426,217 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
 }
 
 // ------------------------------------------------------------------------------------------------
+// Step-fused kernel: Part 2 of step k + Part 1 of step k+1 in one pass (small-body systems).
+//
+// Nothing happens between the two halves in RigidBodyIntegrator::step, so a tile's bodies can take the
+// second half kick, the next first half kick, the drift and the rotation back to back while their state
+// sits in shared memory / registers: per body-step the state makes ONE round trip through HBM (read
+// r p q pi 1/m 1/I, write r p q pi F tau) instead of two, F and tau are never re-read and the body-frame
+// coordinates are read once.  Same persistent cp.async pipeline as part1Kernel, now also prefetching the
+// tile's atom forces and coordinates; same deterministic warp-shuffle segmented reduction as part2Kernel,
+// reading its operands from shared memory.  Results are bit-identical to part2Kernel + part1Kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFPlanes = 18;                        // r3 p3 q4 pi4 invm invI3
+
+struct FusedStage {
+    double body[kFPlanes][kBlock];
+    double f[3][kTileAtoms];                        // atom forces, later the arms delta = A^T(q) d
+    double d[3][kTileAtoms];
+    int loc[kBlock + 4];
+    unsigned char localBody[kTileAtoms + 16];
+};
+struct FusedSmem {
+    FusedStage stage[2];
+    double acc[6][kBlock];
+    double head[kWarps][6];
+    int headKey[kWarps];
+    int4 meta[3];
+};
+
+// stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
+__device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k == 14 ? (int) PL_INVM : (int) PL_INVI + (k - 15)); }
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kBlock, 2)
+part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smemRaw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const size_t ld = S.bodyStride, as = S.atomStride;
+    const int numTiles = S.numTiles;
+
+    auto request = [&](int4 m, int st) {
+        FusedStage& T = sm.stage[st];
+        if (tid < m.y) {
+            const double* g = S.state + (size_t) (m.x + tid);
+#pragma unroll
+            for (int k = 0; k < kFPlanes; k++) cpAsync8(&T.body[k][tid], g + fusedGlobalPlane(k)*ld);
+            cpAsync4(&T.loc[tid], S.loc + m.x + tid);
+        }
+        for (int j = tid; j < m.w; j += kBlock) {
+            const double* g = S.dxyz + (size_t) (m.z + j);
+            cpAsync8(&T.d[0][j], g);
+            cpAsync8(&T.d[1][j], g + as);
+            cpAsync8(&T.d[2][j], g + 2*as);
+            const double* fp = force.p + atomSlot(S, S.numFree + m.z + j)*force.sa;
+            cpAsync8(&T.f[0][j], fp);
+            cpAsync8(&T.f[1][j], fp + force.sc);
+            cpAsync8(&T.f[2][j], fp + 2*force.sc);
+        }
+        const int first = m.z & ~3;
+        for (int w = tid; 4*w < m.z + m.w - first; w += kBlock)
+            cpAsync4(&T.localBody[4*w], S.localBody + first + 4*w);
+    };
+
+    const int tile0 = blockIdx.x;
+    if (tile0 < numTiles) {
+        if (tid == 0) {
+            sm.meta[0] = S.tileMeta[tile0];
+            if (tile0 + G < numTiles) sm.meta[1] = S.tileMeta[tile0 + G];
+        }
+        __syncthreads();
+        request(sm.meta[0], 0);
+        cpCommit();
+        for (int tile = tile0, it = 0; tile < numTiles; tile += G, it++) {
+            const int4 m = sm.meta[it % 3];
+            FusedStage& T = sm.stage[it & 1];
+#pragma unroll
+            for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
+            if (tid < kWarps*6) sm.head[tid/6][tid%6] = 0.0;
+            cpWait<0>();                                       // this tile (+ the next tile's descriptor) landed
+            __syncthreads();
+            if (tile + G < numTiles) {
+                request(sm.meta[(it + 1) % 3], (it & 1) ^ 1);
+                if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], S.tileMeta + tile + 2*G);
+            }
+            cpCommit();
+
+            // ---- B: thread per atom, forces and torques -> per-body sums (see part2Kernel)
+            const int shift = m.z & 3;
+            const int per = ((m.w + kBlock - 1)/kBlock)*32;
+            const int wBeg = warp*per, wEnd = min(wBeg + per, m.w);        // tile-local atom indices
+            int firstKey = -1;
+            if (wBeg < wEnd) {
+                const int k0 = T.localBody[wBeg + shift];
+                if (T.loc[k0] - m.z < wBeg) firstKey = k0;
+            }
+            if (lane == 0) sm.headKey[warp] = firstKey;
+            for (int base = wBeg; base < wEnd; base += 32) {
+                const int j = base + lane;
+                const bool valid = j < wEnd;
+                int key = 0x7fffffff;
+                double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                if (valid) {
+                    key = T.localBody[j + shift];
+                    const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
+                    const d3 f = {T.f[0][j], T.f[1][j], T.f[2][j]};
+                    const d4 q = {T.body[6][key], T.body[7][key], T.body[8][key], T.body[9][key]};
+                    const d3 delta = bodyToSpace(q, d);
+                    T.f[0][j] = delta.x; T.f[1][j] = delta.y; T.f[2][j] = delta.z;     // kept for the velocities
+                    const d3 t = cross(delta, f);
+                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = t.x; v[4] = t.y; v[5] = t.z;
+                }
+                for (int off = 1; off < 32 && off < S.maxBodySize; off <<= 1) {
+                    const int kp = __shfl_up_sync(kFull, key, off);
+                    const bool take = lane >= off && kp == key;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const double t = __shfl_up_sync(kFull, v[k], off);
+                        if (take) v[k] += t;
+                    }
+                }
+                const int kn = __shfl_down_sync(kFull, key, 1);
+                if (valid && (lane == 31 || kn != key)) {
+                    if (key == firstKey) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) sm.head[warp][k] += v[k];
+                    }
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) sm.acc[k][key] += v[k];
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+
+            // ---- C: thread per body: second kick of this step, then first kick + drift + rotation of the next
+            double (*B)[kBlock] = T.body;
+            if (tid < m.y) {
+                double sum[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) sum[k] = sm.acc[k][tid];
+#pragma unroll
+                for (int w = 1; w < kWarps; w++)
+                    if (sm.headKey[w] == tid) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) sum[k] += sm.head[w][k];
+                    }
+                const d3 F = {sum[0], sum[1], sum[2]}, tau = {sum[3], sum[4], sum[5]};
+                d3 r = {B[0][tid], B[1][tid], B[2][tid]};
+                d3 p = {B[3][tid], B[4][tid], B[5][tid]};
+                d4 q = {B[6][tid], B[7][tid], B[8][tid], B[9][tid]};
+                d4 pi = {B[10][tid], B[11][tid], B[12][tid], B[13][tid]};
+                const double invm = B[14][tid];
+                const d3 invI = {B[15][tid], B[16][tid], B[17][tid]};
+                d3 vcm, om;
+                bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
+                sm.acc[0][tid] = vcm.x; sm.acc[1][tid] = vcm.y; sm.acc[2][tid] = vcm.z;
+                sm.acc[3][tid] = om.x; sm.acc[4][tid] = om.y; sm.acc[5][tid] = om.z;
+                bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
+                double* s = S.state + (size_t) (m.x + tid);
+                storePlane3(s + PL_R*ld, ld, r);
+                storePlane3(s + PL_P*ld, ld, p);
+                storePlane4(s + PL_Q*ld, ld, q);
+                storePlane4(s + PL_PI*ld, ld, pi);
+                storePlane3(s + PL_F*ld, ld, F);
+                storePlane3(s + PL_TAU*ld, ld, tau);
+                B[0][tid] = r.x; B[1][tid] = r.y; B[2][tid] = r.z;
+                B[6][tid] = q.w; B[7][tid] = q.x; B[8][tid] = q.y; B[9][tid] = q.z;
+            }
+            __syncthreads();
+
+            // ---- D: thread per atom: velocities at the end of this step, positions of the next
+            for (int j = tid; j < m.w; j += kBlock) {
+                const int k = T.localBody[j + shift];
+                const d3 delta = {T.f[0][j], T.f[1][j], T.f[2][j]};
+                const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
+                const d3 om = {sm.acc[3][k], sm.acc[4][k], sm.acc[5][k]};
+                const long long slot = atomSlot(S, S.numFree + m.z + j);
+                storeAtom(vel, slot, atomVelocity(vcm, om, delta));
+                const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
+                const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
+                const d3 r = {B[0][k], B[1][k], B[2][k]};
+                storeAtom(pos, slot, atomPosition(r, q, d));
+            }
+            __syncthreads();
+        }
+        cpWait<0>();
+    }
+
+    // ---- free atoms: second half kick of this step, first half kick + drift of the next
+    for (int c = blockIdx.x; c < S.numFreeBlocks; c += G) {
+        const int base = c*kFreePerBlock + tid;
+#pragma unroll
+        for (int jj = 0; jj < kFreePerBlock/kBlock; jj++) {
+            const int k = base + jj*kBlock;
+            if (k < S.numFree) {
+                const long long gi = atomSlot(S, k);
+                const d3 f = loadAtom(force, gi);
+                const double invm = S.freeInvMass[k];
+                d3 x = loadAtom(pos, gi), v = loadAtom(vel, gi);
+                freePart2(dt, f, invm, x, loadPlane3(S.savedPos + k, S.freeStride), v);
+                freePart1(dt, f, invm, x, v);
+                storeAtom(vel, gi, v);
+                storeAtom(pos, gi, x);
+                storePlane3(S.savedPos + k, S.freeStride, asStored(pos, x));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Kinetic energies: fixed-shape two-level tree (warp shuffles -> shared -> last CTA), no atomics
 // on the data path, so the two doubles are bit-reproducible from run to run.
 // ------------------------------------------------------------------------------------------------
@@ -497,7 +709,9 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     // persistent CTAs: one wave that fills every SM
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
     const int work = tiles > 0 ? tiles : S.numFreeBlocks;
-    const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
+    int perSM = EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT;
+    if (const char* e = getenv("RBK_DEBUG_CTAS_PER_SM")) perSM = atoi(e) > 0 ? atoi(e) : perSM;     // profiling experiments only
+    const int resident = S.numSMs*perSM;
     part1Kernel<EXACT, FUSED><<<work < resident ? work : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
     if (!FUSED && S.numTiles > 0) atomPositionKernel<<<S.numTiles, kBlock, 0, st>>>(S, pos);
     return cudaGetLastError();
@@ -517,6 +731,30 @@ cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView
     if (grid == 0) return cudaSuccess;
     part2Kernel<<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
+}
+
+template <bool EXACT>
+cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int work = S.numTiles > 0 ? S.numTiles : S.numFreeBlocks;
+    const int resident = S.numSMs*2;
+    part2Part1Kernel<EXACT><<<work < resident ? work : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
+    return cudaGetLastError();
+}
+
+cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
+    // the one-pass kernel stages fp64 forces with cp.async; other formats / large bodies take the two kernels
+    if (!S.fusable || force.fmt != FMT_F64) {
+        cudaError_t e = launchPart2(S, dt, pos, vel, force, st);
+        return e != cudaSuccess ? e : launchPart1(S, dt, pos, vel, force, st);
+    }
+    return S.rotationMode == 0 ? launchFused<true>(S, dt, pos, vel, force, st) : launchFused<false>(S, dt, pos, vel, force, st);
 }
 
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out,

@@ -449,8 +449,10 @@ RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
         for (int i = 0; i < n && ok; i++) ok = exactRotationSeries<kSeriesOrder>(h, invI, q1, p1);
         if (ok) { q = q1; pi = p1; return; }
     }
+#ifndef RBK_EXPERIMENT_NO_ELLIPTIC
     const d3 I = {1.0/invI.x, 1.0/invI.y, 1.0/invI.z};
     exactRotationElliptic(dt, I, invI, q, pi);
+#endif
 }
 
 } // namespace rbk

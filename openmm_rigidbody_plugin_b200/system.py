@@ -153,6 +153,11 @@ class DeviceRigidBodySystem:
         lay, stride = _layout(pos, layout)
         check(self.lib.rbk_part2(self.h, float(dt), _ptr(pos), _ptr(vel), _ptr(force), lay, stride, _stream(stream)))
 
+    def part2_part1(self, dt, pos, vel, force, layout=None, stream=None):
+        """Part 2 of this step fused with Part 1 of the next one (rbk_part2_part1)."""
+        lay, stride = _layout(pos, layout)
+        check(self.lib.rbk_part2_part1(self.h, float(dt), _ptr(pos), _ptr(vel), _ptr(force), lay, stride, _stream(stream)))
+
     def kinetic(self, vel, layout=None, stream=None):
         lay, stride = _layout(vel, layout)
         out = np.zeros(2)

@@ -188,6 +188,17 @@ class GpuStepper:
         self.sys.part2(dt, self.dR, self.dV, self.dF)
 
     def step(self, dt, steps=1):
+        if getattr(self, "fused", False) and steps > 0:
+            # part1, forces, [part2+part1 fused, forces] x (steps-1), part2  (rbk_part2_part1)
+            self.sys.part1(dt, self.dR, self.dV, self.dF)
+            for _ in range(steps - 1):
+                if self.tether is not None:
+                    self.compute_forces()
+                self.sys.part2_part1(dt, self.dR, self.dV, self.dF)
+            if self.tether is not None:
+                self.compute_forces()
+            self.sys.part2(dt, self.dR, self.dV, self.dF)
+            return
         for _ in range(steps):
             self.sys.part1(dt, self.dR, self.dV, self.dF)
             if self.tether is not None:
