@@ -364,7 +364,7 @@ def run_b200_arm(args):
         el = replicas.max_over_ranks(time.perf_counter() - t0, dist if world > 1 else None, dev)
         e2e = {"value": world * nB * k2 / el, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 48 * n,
                "steps": k2, "ms_per_step": 1e3 * el / k2,
-               "call": "one rbk_execute_host per step: part1 -> positions D2H -> forces H2D -> part2 -> velocities D2H -> sync, pinned host buffers"}
+               "call": "one rbk_execute_host per step with that step's forces in pinned host memory: forces H2D (copy stream) under part1 + positions D2H, part2, velocities D2H, sync"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

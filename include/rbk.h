@@ -136,7 +136,8 @@ typedef void (*rbk_force_fn)(const double* R, double* F, int numAtoms, void* use
  * with HOST buffers, `steps` times: Part 1 on the device, positions copied to R, forces obtained
  * from `forces` (NULL = keep F as is) and copied to the device, Part 2, velocities copied to V.
  * R,V,F: host arrays in RBK_LAYOUT_VEC3 (pinned memory makes the copies asynchronous); on the first
- * call R,V,F are uploaded in full.  Uses device mirrors owned by the handle. */
+ * call R,V,F are uploaded in full.  Uses device mirrors owned by the handle.  With forces == NULL the
+ * upload of F (known before the call) runs on a copy stream underneath Part 1 and the download of R. */
 int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F,
                      rbk_force_fn forces, void* user, void* stream);
 

@@ -66,13 +66,19 @@ struct rbk_system {
     double* mPos = nullptr;
     double* mVel = nullptr;
     double* mForce = nullptr;
+    double* mForce2 = nullptr;       // second force mirror: new forces land here while part 1 still reads the old ones
+    cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
+    cudaEvent_t evStart = nullptr, evForces = nullptr, evPart1 = nullptr, evPositions = nullptr;
     bool mirrorsLoaded = false;
     std::vector<double> staging;
 
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta);
         cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
-        cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce);
+        cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
+        if (h2dStream) cudaStreamDestroy(h2dStream);
+        if (d2hStream) cudaStreamDestroy(d2hStream);
+        for (cudaEvent_t e : {evStart, evForces, evPart1, evPositions}) if (e) cudaEventDestroy(e);
         if (hKinOut) cudaFreeHost(hKinOut);
     }
 };
@@ -550,23 +556,48 @@ int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V
         RBK_CUDA(cudaMalloc((void**) &sys->mVel, bytes));
         RBK_CUDA(cudaMalloc((void**) &sys->mForce, bytes));
     }
+    if (!sys->mForce2) {
+        RBK_CUDA(cudaMalloc((void**) &sys->mForce2, bytes));
+        RBK_CUDA(cudaStreamCreateWithFlags(&sys->h2dStream, cudaStreamNonBlocking));
+        RBK_CUDA(cudaStreamCreateWithFlags(&sys->d2hStream, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&sys->evStart, &sys->evForces, &sys->evPart1, &sys->evPositions})
+            RBK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
     if (!sys->mirrorsLoaded) {
         RBK_CUDA(cudaMemcpyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
         RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
         RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
         sys->mirrorsLoaded = true;
     }
-    const AtomView p{sys->mPos, 3, 1, rbk::FMT_F64, nullptr}, v{sys->mVel, 3, 1, rbk::FMT_F64, nullptr}, f{sys->mForce, 3, 1, rbk::FMT_F64, nullptr};
+    const AtomView p{sys->mPos, 3, 1, rbk::FMT_F64, nullptr}, v{sys->mVel, 3, 1, rbk::FMT_F64, nullptr};
     for (int i = 0; i < steps; i++) {
-        RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, f, st));
-        RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
+        const AtomView fOld{sys->mForce, 3, 1, rbk::FMT_F64, nullptr}, fNew{sys->mForce2, 3, 1, rbk::FMT_F64, nullptr};
         if (forces) {
+            // forces depend on the new positions: Part 1 -> positions to the host -> callback -> forces to the device
+            RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, fOld, st));
+            RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
             RBK_CUDA(cudaStreamSynchronize(st));
             forces(R, F, sys->host.numAtoms, user);
+            RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, st));
         }
-        RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
-        RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, st));
+        else {
+            // F is this step's input, known up front: its upload (H2D engine) runs under Part 1 and under the download
+            // of the positions (D2H engine); Part 2 waits for the forces only
+            RBK_CUDA(cudaEventRecord(sys->evStart, st));
+            RBK_CUDA(cudaStreamWaitEvent(sys->h2dStream, sys->evStart, 0));
+            RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, sys->h2dStream));
+            RBK_CUDA(cudaEventRecord(sys->evForces, sys->h2dStream));
+            RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, fOld, st));
+            RBK_CUDA(cudaEventRecord(sys->evPart1, st));
+            RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
+            RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
+            RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
+            RBK_CUDA(cudaStreamWaitEvent(st, sys->evForces, 0));
+        }
+        RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, fNew, st));
         RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
+        if (!forces) RBK_CUDA(cudaStreamWaitEvent(st, sys->evPositions, 0));     // R is complete when `st` is
+        std::swap(sys->mForce, sys->mForce2);
     }
     RBK_CUDA(cudaStreamSynchronize(st));
     return RBK_OK;
