@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -123,7 +124,11 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
         if (inTile > 0) out.push_back(make_int4(first, inTile, loc[first], atomsInTile));
         return out;
     };
-    std::vector<int4> meta = cut(rbk::kTileAtoms, true), bodyMeta = cut(rbk::kMaxTileAtoms, false);
+    // large bodies: smaller atom tiles keep a tile's coordinates L1-resident between the two atom phases of part 2
+    const bool large = nB > 0 && (long long) nA > (long long) rbk::kSplitAtomsPerBody*nB;
+    int atomCap = large ? rbk::kLargeBodyTileAtoms : rbk::kTileAtoms;
+    if (const char* e = getenv("RBK_DEBUG_TILE_ATOMS")) atomCap = atoi(e) > 0 ? atoi(e) : atomCap;     // profiling experiments only
+    std::vector<int4> meta = cut(atomCap, true), bodyMeta = cut(rbk::kMaxTileAtoms, false);
 
     d.numBodies = nB;
     d.numFree = nF;

@@ -24,6 +24,7 @@ constexpr int kBlock = 128;            // threads per CTA = max bodies per tile
 // (<=128 bodies, <=kMaxTileAtoms atoms) drive the stand-alone rotation kernel used when bodies are large,
 // so that its thread-per-body phase runs full warps.  For small bodies (water) the two coincide.
 constexpr int kTileAtoms = 512;
+constexpr int kLargeBodyTileAtoms = 768;   // atom-tile cap when bodies are large (see rbk_api.cu)
 constexpr int kMaxTileAtoms = 8192;
 constexpr int kSplitAtomsPerBody = 8;  // mean body size above which part 1 runs as rotation kernel + atom kernel
 constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)

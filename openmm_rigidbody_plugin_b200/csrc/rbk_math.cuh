@@ -101,32 +101,50 @@ template <int K> RBK_HD d4 quatPerm(d4 q) {
     return {-q.z,  q.y, -q.x,  q.w};
 }
 
+// sin/cos by truncated Maclaurin series, valid (remainder < 2e-18 relative) for |x| <= 1/32; no branches.
+RBK_HD void sincosTiny(double x, double* s, double* c) {
+    const double z = x*x;
+    *s = x + x*z*(-1.0/6.0 + z*(1.0/120.0 + z*(-1.0/5040.0)));
+    *c = 1.0 + z*(-0.5 + z*(1.0/24.0 + z*(-1.0/720.0 + z*(1.0/40320.0))));
+}
+
 // One uniaxial free rotation about principal axis K; quarterHinvI = h/(4 I_K).
-template <int K> RBK_HD void uniaxialScaled(double quarterHinvI, d4& q, d4& pi) {
+template <int K, bool TINY> RBK_HD void uniaxialScaled(double quarterHinvI, d4& q, d4& pi) {
     const d4 Bq = quatPerm<K>(q);
     const double phi = dot(pi, Bq)*quarterHinvI;
     double s, c;
-    sincosStep(phi, &s, &c);
+    if (TINY) sincosTiny(phi, &s, &c);
+    else sincosStep(phi, &s, &c);
     const d4 Bp = quatPerm<K>(pi);
     q = q*c + Bq*s;
     pi = pi*c + Bp*s;
 }
-template <int K> RBK_HD void uniaxial(double h, double invIk, d4& q, d4& pi) { uniaxialScaled<K>(0.25*h*invIk, q, pi); }
+template <int K> RBK_HD void uniaxial(double h, double invIk, d4& q, d4& pi) { uniaxialScaled<K, false>(0.25*h*invIk, q, pi); }
 
 // NO-SQUISH: n sub-steps of R3(h/2) R2(h/2) R1(h) R2(h/2) R3(h/2); axis 3 skipped for linear bodies.
 // Consecutive half rotations about axis 3 of neighbouring sub-steps are flows of the same one-axis
 // Hamiltonian and are applied as one rotation over h (identical map, 4n+1 instead of 5n rotations).
+template <bool TINY> RBK_HD void noSquishLoop(int n, double k1, double k2, double k3, bool axis3, d4& q, d4& pi) {
+    if (axis3) uniaxialScaled<2, TINY>(0.5*k3, q, pi);
+    for (int i = 0; i < n; i++) {
+        uniaxialScaled<1, TINY>(k2, q, pi);
+        uniaxialScaled<0, TINY>(k1, q, pi);
+        uniaxialScaled<1, TINY>(k2, q, pi);
+        if (axis3) uniaxialScaled<2, TINY>(i == n - 1 ? 0.5*k3 : k3, q, pi);
+    }
+}
+
 RBK_HD void noSquish(double dt, int n, d3 invI, d4& q, d4& pi) {
     const double h = dt/n;
     const double k1 = 0.25*h*invI.x, k2 = 0.125*h*invI.y, k3 = 0.25*h*invI.z;
     const bool axis3 = invI.z != 0.0;            // dof == 6 (linear bodies carry invI.z = 0)
-    if (axis3) uniaxialScaled<2>(0.5*k3, q, pi);
-    for (int i = 0; i < n; i++) {
-        uniaxialScaled<1>(k2, q, pi);
-        uniaxialScaled<0>(k1, q, pi);
-        uniaxialScaled<1>(k2, q, pi);
-        if (axis3) uniaxialScaled<2>(i == n - 1 ? 0.5*k3 : k3, q, pi);
-    }
+    // Every rotation angle is (pi . B_k q) k with |B_k q| = |q| and both norms invariant under the rotations
+    // (they act orthogonally on q and on pi), so |angle| <= |pi| |q| max(k) throughout: one test per body
+    // selects the branch-free small-angle sin/cos for all 4n+1 rotations.
+    const double kmax = fmax(fabs(k1), fmax(fabs(k2), fabs(k3)));
+    const double bound2 = dot(pi, pi)*dot(q, q)*kmax*kmax;
+    if (bound2 <= 9.5e-4) noSquishLoop<true>(n, k1, k2, k3, axis3, q, pi);
+    else noSquishLoop<false>(n, k1, k2, k3, axis3, q, pi);
 }
 
 // ---------------------------------------------------------------------------------------------
