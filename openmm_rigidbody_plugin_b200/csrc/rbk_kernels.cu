@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
 // reading its operands from shared memory.  Results are bit-identical to part2Kernel + part1Kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFPlanes = 18;                        // r3 p3 q4 pi4 invm invI3
+constexpr int kSmallBody = 8;                       // bodies up to this size are reduced by their own thread
 
 struct FusedStage {
     double body[kFPlanes][kBlock];
@@ -456,7 +457,7 @@ struct FusedSmem {
 // stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
 __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k == 14 ? (int) PL_INVM : (int) PL_INVI + (k - 15)); }
 
-template <bool EXACT>
+template <bool EXACT, bool SMALL>
 __global__ void __launch_bounds__(kBlock, 2)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -501,9 +502,11 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         for (int tile = tile0, it = 0; tile < numTiles; tile += G, it++) {
             const int4 m = sm.meta[it % 3];
             FusedStage& T = sm.stage[it & 1];
+            if (!SMALL) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
-            if (tid < kWarps*6) sm.head[tid/6][tid%6] = 0.0;
+                for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
+                if (tid < kWarps*6) sm.head[tid/6][tid%6] = 0.0;
+            }
             cpWait<0>();                                       // this tile (+ the next tile's descriptor) landed
             __syncthreads();
             if (tile + G < numTiles) {
@@ -512,71 +515,91 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             }
             cpCommit();
 
-            // ---- B: thread per atom, forces and torques -> per-body sums (see part2Kernel)
+            // ---- B: forces and torques -> per-body sums.
+            // SMALL (every body has <= kSmallBody atoms, e.g. water): each body's thread sums its own atoms straight
+            // from the staged forces/coordinates in phase C - sequential order, no shuffles, no extra barrier.
+            // Otherwise: thread per atom + warp-shuffle segmented scan, exactly as in part2Kernel.
             const int shift = m.z & 3;
-            const int per = ((m.w + kBlock - 1)/kBlock)*32;
-            const int wBeg = warp*per, wEnd = min(wBeg + per, m.w);        // tile-local atom indices
-            int firstKey = -1;
-            if (wBeg < wEnd) {
-                const int k0 = T.localBody[wBeg + shift];
-                if (T.loc[k0] - m.z < wBeg) firstKey = k0;
-            }
-            if (lane == 0) sm.headKey[warp] = firstKey;
-            for (int base = wBeg; base < wEnd; base += 32) {
-                const int j = base + lane;
-                const bool valid = j < wEnd;
-                int key = 0x7fffffff;
-                double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                if (valid) {
-                    key = T.localBody[j + shift];
-                    const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
-                    const d3 f = {T.f[0][j], T.f[1][j], T.f[2][j]};
-                    const d4 q = {T.body[6][key], T.body[7][key], T.body[8][key], T.body[9][key]};
-                    const d3 delta = bodyToSpace(q, d);
-                    T.f[0][j] = delta.x; T.f[1][j] = delta.y; T.f[2][j] = delta.z;     // kept for the velocities
-                    const d3 t = cross(delta, f);
-                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = t.x; v[4] = t.y; v[5] = t.z;
+            if (!SMALL) {
+                const int per = ((m.w + kBlock - 1)/kBlock)*32;
+                const int wBeg = warp*per, wEnd = min(wBeg + per, m.w);        // tile-local atom indices
+                int firstKey = -1;
+                if (wBeg < wEnd) {
+                    const int k0 = T.localBody[wBeg + shift];
+                    if (T.loc[k0] - m.z < wBeg) firstKey = k0;
                 }
-                for (int off = 1; off < 32 && off < S.maxBodySize; off <<= 1) {
-                    const int kp = __shfl_up_sync(kFull, key, off);
-                    const bool take = lane >= off && kp == key;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        const double t = __shfl_up_sync(kFull, v[k], off);
-                        if (take) v[k] += t;
+                if (lane == 0) sm.headKey[warp] = firstKey;
+                for (int base = wBeg; base < wEnd; base += 32) {
+                    const int j = base + lane;
+                    const bool valid = j < wEnd;
+                    int key = 0x7fffffff;
+                    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    if (valid) {
+                        key = T.localBody[j + shift];
+                        const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
+                        const d3 f = {T.f[0][j], T.f[1][j], T.f[2][j]};
+                        const d4 q = {T.body[6][key], T.body[7][key], T.body[8][key], T.body[9][key]};
+                        const d3 delta = bodyToSpace(q, d);
+                        T.f[0][j] = delta.x; T.f[1][j] = delta.y; T.f[2][j] = delta.z;     // kept for the velocities
+                        const d3 t = cross(delta, f);
+                        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = t.x; v[4] = t.y; v[5] = t.z;
                     }
+                    for (int off = 1; off < 32 && off < S.maxBodySize; off <<= 1) {
+                        const int kp = __shfl_up_sync(kFull, key, off);
+                        const bool take = lane >= off && kp == key;
+    #pragma unroll
+                        for (int k = 0; k < 6; k++) {
+                            const double t = __shfl_up_sync(kFull, v[k], off);
+                            if (take) v[k] += t;
+                        }
+                    }
+                    const int kn = __shfl_down_sync(kFull, key, 1);
+                    if (valid && (lane == 31 || kn != key)) {
+                        if (key == firstKey) {
+    #pragma unroll
+                            for (int k = 0; k < 6; k++) sm.head[warp][k] += v[k];
+                        }
+                        else {
+    #pragma unroll
+                            for (int k = 0; k < 6; k++) sm.acc[k][key] += v[k];
+                        }
+                    }
+                    __syncwarp();
                 }
-                const int kn = __shfl_down_sync(kFull, key, 1);
-                if (valid && (lane == 31 || kn != key)) {
-                    if (key == firstKey) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) sm.head[warp][k] += v[k];
-                    }
-                    else {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) sm.acc[k][key] += v[k];
-                    }
-                }
-                __syncwarp();
-            }
-            __syncthreads();
+                __syncthreads();
 
+            }
             // ---- C: thread per body: second kick of this step, then first kick + drift + rotation of the next
             double (*B)[kBlock] = T.body;
             if (tid < m.y) {
-                double sum[6];
-#pragma unroll
-                for (int k = 0; k < 6; k++) sum[k] = sm.acc[k][tid];
-#pragma unroll
-                for (int w = 1; w < kWarps; w++)
-                    if (sm.headKey[w] == tid) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) sum[k] += sm.head[w][k];
-                    }
-                const d3 F = {sum[0], sum[1], sum[2]}, tau = {sum[3], sum[4], sum[5]};
                 d3 r = {B[0][tid], B[1][tid], B[2][tid]};
                 d3 p = {B[3][tid], B[4][tid], B[5][tid]};
                 d4 q = {B[6][tid], B[7][tid], B[8][tid], B[9][tid]};
+                d3 F = {0.0, 0.0, 0.0}, tau = {0.0, 0.0, 0.0};
+                if (SMALL) {
+                    const int j0 = T.loc[tid] - m.z, j1 = (tid + 1 < m.y ? T.loc[tid + 1] - m.z : m.w);
+                    for (int j = j0; j < j1; j++) {
+                        const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
+                        const d3 f = {T.f[0][j], T.f[1][j], T.f[2][j]};
+                        const d3 delta = bodyToSpace(q, d);
+                        T.f[0][j] = delta.x; T.f[1][j] = delta.y; T.f[2][j] = delta.z;     // kept for the velocities
+                        F = F + f;
+                        tau = tau + cross(delta, f);
+                    }
+                }
+                else {
+                    double sum[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) sum[k] = sm.acc[k][tid];
+#pragma unroll
+                    for (int w = 1; w < kWarps; w++)
+                        if (sm.headKey[w] == tid) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) sum[k] += sm.head[w][k];
+                        }
+                    F = {sum[0], sum[1], sum[2]};
+                    tau = {sum[3], sum[4], sum[5]};
+                }
                 d4 pi = {B[10][tid], B[11][tid], B[12][tid], B[13][tid]};
                 const double invm = B[14][tid];
                 const d3 invI = {B[15][tid], B[16][tid], B[17][tid]};
@@ -733,17 +756,17 @@ cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView
     return cudaGetLastError();
 }
 
-template <bool EXACT>
+template <bool EXACT, bool SMALL>
 cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(FusedSmem));
+        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int work = S.numTiles > 0 ? S.numTiles : S.numFreeBlocks;
     const int resident = S.numSMs*2;
-    part2Part1Kernel<EXACT><<<work < resident ? work : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
+    part2Part1Kernel<EXACT, SMALL><<<work < resident ? work : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 
@@ -754,7 +777,9 @@ cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, Ato
         cudaError_t e = launchPart2(S, dt, pos, vel, force, st);
         return e != cudaSuccess ? e : launchPart1(S, dt, pos, vel, force, st);
     }
-    return S.rotationMode == 0 ? launchFused<true>(S, dt, pos, vel, force, st) : launchFused<false>(S, dt, pos, vel, force, st);
+    const bool small = S.maxBodySize <= kSmallBody;
+    if (S.rotationMode == 0) return small ? launchFused<true, true>(S, dt, pos, vel, force, st) : launchFused<true, false>(S, dt, pos, vel, force, st);
+    return small ? launchFused<false, true>(S, dt, pos, vel, force, st) : launchFused<false, false>(S, dt, pos, vel, force, st);
 }
 
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out,

@@ -1,5 +1,8 @@
-"""The step-fused kernel (rbk_part2_part1 = Part 2 of step k + Part 1 of step k+1 in one pass) must be bit-identical
-to the two separate kernels, for every system shape (it falls back to the two kernels for large bodies)."""
+"""The step-fused kernel (rbk_part2_part1 = Part 2 of step k + Part 1 of step k+1 in one pass) against the two separate
+kernels, for every system shape.  Where it uses the same segmented scan (bodies larger than 8 atoms somewhere in the
+system) or falls back to the two kernels (large mean body size) the results are bit-identical; for small bodies it sums
+each body's forces sequentially in the body's own thread (the reference's summation order), which differs from the
+scan's tree order by rounding only."""
 import numpy as np
 import pytest
 
@@ -19,12 +22,14 @@ def run(sysd, mode, fused, layout, shuffle, tether, steps):
 
 
 @pytest.mark.parametrize("mode", [0, 3])
-@pytest.mark.parametrize("case", ["water", "small_mixed", "large_mixed", "free_only"])
+@pytest.mark.parametrize("case", ["water", "small_mixed", "medium_mixed", "large_mixed", "free_only"])
 def test_fused_is_bit_identical(case, mode):
     if case == "water":
         sysd, layout, shuffle = common.synth.water_box(3000, seed=91), "vec3", False
     elif case == "small_mixed":      # bodies of 3..7 atoms + interleaved free atoms, reordered, SoA layout
         sysd, layout, shuffle = common.synth.mixed_system(2500, 3000, seed=92, max_atoms=7), "soa", True
+    elif case == "medium_mixed":     # mean body size <= 8 but some bodies > 8 atoms: fused kernel with the segmented scan
+        sysd, layout, shuffle = common.synth.mixed_system(2500, 1000, seed=95, max_atoms=12), "vec3", True
     elif case == "large_mixed":      # mean body size > 8: the fused entry point takes the two-kernel route
         sysd, layout, shuffle = common.synth.mixed_system(400, 500, seed=93, max_atoms=60), "vec3", True
     else:
@@ -36,6 +41,13 @@ def test_fused_is_bit_identical(case, mode):
     for tether in (False, True):
         a = run(sysd, mode, False, layout, shuffle, tether, 6)
         b = run(sysd, mode, True, layout, shuffle, tether, 6)
+        if case in ("water", "small_mixed"):          # sequential per-body sums vs tree order: rounding-level differences
+            assert common.rel_inf(b[0], a[0]) <= 1e-12 and common.rel_inf(b[1], a[1]) <= 1e-11
+            assert common.rel_inf(b[2], a[2]) <= 1e-13
+            for k in ("rcm", "pcm", "pi", "force", "torque"):
+                assert common.rel_inf(b[3][k], a[3][k]) <= 1e-11, k
+            assert common.quat_rel(b[3]["q"], a[3]["q"]) <= 1e-11
+            continue
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         for k in ("rcm", "pcm", "q", "pi", "force", "torque"):
             assert np.array_equal(a[3][k], b[3][k]), k
