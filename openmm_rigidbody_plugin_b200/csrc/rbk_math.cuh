@@ -457,12 +457,11 @@ RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
 #endif
 constexpr int kSeriesOrder = RBK_SERIES_ORDER;
 
-// Mode 0 entry point used by the step.  One series step over dt; if its truncation check fails (fast
-// rotor / long step) the step is redone as 2, then 4 exact sub-steps - the composition of exact flows is
-// exact and every halving shrinks the tail by 2^order - and only then by the elliptic-integral route,
-// which needs I = 1/invI.
-RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
-    for (int n = 1; n <= 4; n <<= 1) {
+// Slow path of mode 0 (rare; kept out of line so that the fast path stays straight-line code): the step is
+// redone as 2, then 4 exact sub-steps - the composition of exact flows is exact and every halving shrinks the
+// series tail by 2^order - and only then by the elliptic-integral route, which needs I = 1/invI.
+RBK_HD_NOINLINE void exactRotationRetry(double dt, d3 invI, d4& q, d4& pi) {
+    for (int n = 2; n <= 4; n <<= 1) {
         d4 q1 = q, p1 = pi;
         const double h = dt/n;
         bool ok = true;
@@ -473,6 +472,12 @@ RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
     const d3 I = {1.0/invI.x, 1.0/invI.y, 1.0/invI.z};
     exactRotationElliptic(dt, I, invI, q, pi);
 #endif
+}
+
+// Mode 0 entry point used by the step: one series step over dt; if its truncation check fails (fast rotor /
+// long step) the retry path above.
+RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
+    if (!exactRotationSeries<kSeriesOrder>(dt, invI, q, pi)) exactRotationRetry(dt, invI, q, pi);
 }
 
 } // namespace rbk

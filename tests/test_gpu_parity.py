@@ -73,12 +73,15 @@ def test_golden_from_true_reference(name, layout, shuffle):
     s.close()
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("mode", [0, 1, 10])
 @pytest.mark.parametrize("layout", ["vec3", "soa"])
-def test_water_vs_oracle(mode, layout):
+def test_water_vs_oracle(mode, layout, fused):
+    """fused=True steps with rbk_part2_part1 (one pass per step) instead of separate part1/part2 launches."""
     sysd = common.synth.water_box(20000, seed=100 + mode)
     o = CpuStepper("oracle", sysd["bodyIndices"], sysd["masses"], mode)
     s = GpuStepper(sysd["bodyIndices"], sysd["masses"], mode, layout=layout)
+    s.fused = fused
     for st in (o, s):
         common.init_like_reference(st, sysd)
         st.step(0.001, 3)
