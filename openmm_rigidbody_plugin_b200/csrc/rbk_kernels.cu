@@ -36,12 +36,11 @@ __device__ __forceinline__ void storePlane3(double* base, size_t stride, d3 v) {
 __device__ __forceinline__ void storePlane4(double* base, size_t stride, d4 v) {
     base[0] = v.w; base[stride] = v.x; base[2*stride] = v.y; base[3*stride] = v.z;
 }
-__device__ __forceinline__ d3 loadAtom(const AtomView& A, long long i) {
-    if (A.fmt == FMT_F64) {                                    // the fp64 layouts of the integrator-only path
-        const double* p = A.p + i*A.sa;
-        return {p[0], p[A.sc], p[2*A.sc]};
-    }
-    if (A.fmt == FMT_POSQ_MIXED) {                             // OpenMM-CUDA boundary formats (uniform branch)
+// OpenMM-CUDA boundary formats.  Kernels are instantiated twice: NATIVE (all three atom arrays fp64 - the
+// integrator-only path, no conversion code at all) and generic (format switch per access).  With a single
+// instantiation ptxas speculates the float conversions of the other formats into the fp64 path.
+__device__ __forceinline__ d3 loadAtomFormat(const AtomView& A, long long i) {
+    if (A.fmt == FMT_POSQ_MIXED) {
         const float4 hi = reinterpret_cast<const float4*>(A.p)[i], lo = reinterpret_cast<const float4*>(A.aux)[i];
         return {(double) hi.x + (double) lo.x, (double) hi.y + (double) lo.y, (double) hi.z + (double) lo.z};
     }
@@ -58,12 +57,8 @@ __device__ __forceinline__ d3 loadAtom(const AtomView& A, long long i) {
     const double scale = 1.0/4294967296.0;
     return {scale*(double) f[0], scale*(double) f[A.sc], scale*(double) f[2*A.sc]};
 }
-__device__ __forceinline__ void storeAtom(const AtomView& A, long long i, d3 v) {
-    if (A.fmt == FMT_F64) {
-        double* p = A.p + i*A.sa;
-        p[0] = v.x; p[A.sc] = v.y; p[2*A.sc] = v.z;
-    }
-    else if (A.fmt == FMT_POSQ_MIXED) {                        // value = (float) hi + (float) lo, charge (.w) untouched
+__device__ __forceinline__ void storeAtomFormat(const AtomView& A, long long i, d3 v) {
+    if (A.fmt == FMT_POSQ_MIXED) {                             // value = (float) hi + (float) lo, charge (.w) untouched
         float* hi = reinterpret_cast<float*>(A.p) + 4*i;
         float* lo = reinterpret_cast<float*>(A.aux) + 4*i;
         const float hx = (float) v.x, hy = (float) v.y, hz = (float) v.z;
@@ -80,10 +75,25 @@ __device__ __forceinline__ void storeAtom(const AtomView& A, long long i, d3 v) 
         p[0] = (float) v.x; p[1] = (float) v.y; p[2] = (float) v.z;
     }
 }
+template <bool NATIVE> __device__ __forceinline__ d3 loadAtom(const AtomView& A, long long i) {
+    if (NATIVE || A.fmt == FMT_F64) {
+        const double* p = A.p + i*A.sa;
+        return {p[0], p[A.sc], p[2*A.sc]};
+    }
+    return loadAtomFormat(A, i);
+}
+template <bool NATIVE> __device__ __forceinline__ void storeAtom(const AtomView& A, long long i, d3 v) {
+    if (NATIVE || A.fmt == FMT_F64) {
+        double* p = A.p + i*A.sa;
+        p[0] = v.x; p[A.sc] = v.y; p[2*A.sc] = v.z;
+    }
+    else storeAtomFormat(A, i, v);
+}
 // The value a later loadAtom will return for v once it has been stored in A's format (identity for fp64).
 // Free atoms keep it as savedPos, so that (x - savedPos)/dt in part 2 is exactly zero without constraints,
 // whatever precision the caller's position array has.
-__device__ __forceinline__ d3 asStored(const AtomView& A, d3 v) {
+template <bool NATIVE> __device__ __forceinline__ d3 asStored(const AtomView& A, d3 v) {
+    if (NATIVE) return v;
     if (A.fmt == FMT_POSQ_MIXED) {
         const float hx = (float) v.x, hy = (float) v.y, hz = (float) v.z;
         return {(double) hx + (double) (float) (v.x - (double) hx), (double) hy + (double) (float) (v.y - (double) hy),
@@ -147,7 +157,7 @@ template <int N> __device__ __forceinline__ void cpWait() { asm volatile("cp.asy
 // smem plane k of a stage <-> global state plane (the I planes 21..23 are not needed on the device path)
 __device__ __forceinline__ int globalPlane(int k) { return k < 21 ? k : k + 3; }
 
-template <bool EXACT, bool FUSED>
+template <bool EXACT, bool FUSED, bool NATIVE>
 __global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT)
 part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -231,7 +241,7 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
                         const d3 d = {sm.d[0][j], sm.d[1][j], sm.d[2][j]};
                         const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
                         const d3 r = {B[0][k], B[1][k], B[2][k]};
-                        storeAtom(pos, atomSlot(S, S.numFree + m.z + j), atomPosition(r, q, d));
+                        storeAtom<NATIVE>(pos, atomSlot(S, S.numFree + m.z + j), atomPosition(r, q, d));
                     }
                 }
                 else {                                         // one body larger than the staging buffer
@@ -240,7 +250,7 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
                         const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
                         const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
                         const d3 r = {B[0][k], B[1][k], B[2][k]};
-                        storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+                        storeAtom<NATIVE>(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
                     }
                 }
             }
@@ -257,11 +267,11 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
             const int k = base + j*kBlock;
             if (k < S.numFree) {
                 const long long gi = atomSlot(S, k);
-                d3 x = loadAtom(pos, gi), v = loadAtom(vel, gi);
-                freePart1(dt, loadAtom(force, gi), S.freeInvMass[k], x, v);
-                storeAtom(vel, gi, v);
-                storeAtom(pos, gi, x);
-                storePlane3(S.savedPos + k, S.freeStride, asStored(pos, x));
+                d3 x = loadAtom<NATIVE>(pos, gi), v = loadAtom<NATIVE>(vel, gi);
+                freePart1(dt, loadAtom<NATIVE>(force, gi), S.freeInvMass[k], x, v);
+                storeAtom<NATIVE>(vel, gi, v);
+                storeAtom<NATIVE>(pos, gi, x);
+                storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x));
             }
         }
     }
@@ -269,6 +279,7 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
 
 // Positions of the body atoms from the updated (r, q): one CTA per atom tile, thread per atom.
 // Second half of part 1 for large-body systems (see part1Kernel, !FUSED).
+template <bool NATIVE>
 __global__ void __launch_bounds__(kBlock) atomPositionKernel(const DeviceSystem S, const AtomView pos) {
     __shared__ double sB[7][kBlock];
     const int tid = threadIdx.x;
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(kBlock) atomPositionKernel(const DeviceSystem 
         const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
         const d3 r = {sB[0][k], sB[1][k], sB[2][k]};
         const d4 q = {sB[3][k], sB[4][k], sB[5][k], sB[6][k]};
-        storeAtom(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+        storeAtom<NATIVE>(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
     }
 }
 
@@ -298,6 +309,7 @@ __global__ void __launch_bounds__(kBlock) atomPositionKernel(const DeviceSystem 
 #ifndef RBK_P2_MINBLOCKS
 #define RBK_P2_MINBLOCKS 9
 #endif
+template <bool NATIVE>
 __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const DeviceSystem S, const double dt, const AtomView pos,
                                                      const AtomView vel, const AtomView force) {
     __shared__ double sQ[4][kBlock];
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
             if (valid) {
                 key = S.localBody[a];
                 const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-                const d3 f = loadAtom(force, atomSlot(S, S.numFree + a));
+                const d3 f = loadAtom<NATIVE>(force, atomSlot(S, S.numFree + a));
                 const d4 q = {sQ[0][key], sQ[1][key], sQ[2][key], sQ[3][key]};
                 const d3 t = cross(bodyToSpace(q, d), f);
                 v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = t.x; v[4] = t.y; v[5] = t.z;
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
             const d4 q = {sQ[0][lb], sQ[1][lb], sQ[2][lb], sQ[3][lb]};
             const d3 vcm = {sAcc[0][lb], sAcc[1][lb], sAcc[2][lb]};
             const d3 om = {sAcc[3][lb], sAcc[4][lb], sAcc[5][lb]};
-            storeAtom(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
+            storeAtom<NATIVE>(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
         }
     }
     else {                                                     // ---- free atoms
@@ -416,10 +428,10 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
             const int k = base + j*kBlock;
             if (k < S.numFree) {
                 const long long gi = atomSlot(S, k);
-                d3 v = loadAtom(vel, gi);
-                freePart2(dt, loadAtom(force, gi), S.freeInvMass[k], loadAtom(pos, gi),
+                d3 v = loadAtom<NATIVE>(vel, gi);
+                freePart2(dt, loadAtom<NATIVE>(force, gi), S.freeInvMass[k], loadAtom<NATIVE>(pos, gi),
                           loadPlane3(S.savedPos + k, S.freeStride), v);
-                storeAtom(vel, gi, v);
+                storeAtom<NATIVE>(vel, gi, v);
             }
         }
     }
@@ -457,7 +469,7 @@ struct FusedSmem {
 // stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
 __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k == 14 ? (int) PL_INVM : (int) PL_INVI + (k - 15)); }
 
-template <bool EXACT, bool SMALL>
+template <bool EXACT, bool SMALL, bool NATIVE>
 __global__ void __launch_bounds__(kBlock, 2)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -627,11 +639,11 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
                 const d3 om = {sm.acc[3][k], sm.acc[4][k], sm.acc[5][k]};
                 const long long slot = atomSlot(S, S.numFree + m.z + j);
-                storeAtom(vel, slot, atomVelocity(vcm, om, delta));
+                storeAtom<NATIVE>(vel, slot, atomVelocity(vcm, om, delta));
                 const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
                 const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
                 const d3 r = {B[0][k], B[1][k], B[2][k]};
-                storeAtom(pos, slot, atomPosition(r, q, d));
+                storeAtom<NATIVE>(pos, slot, atomPosition(r, q, d));
             }
             __syncthreads();
         }
@@ -646,14 +658,14 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             const int k = base + jj*kBlock;
             if (k < S.numFree) {
                 const long long gi = atomSlot(S, k);
-                const d3 f = loadAtom(force, gi);
+                const d3 f = loadAtom<NATIVE>(force, gi);
                 const double invm = S.freeInvMass[k];
-                d3 x = loadAtom(pos, gi), v = loadAtom(vel, gi);
+                d3 x = loadAtom<NATIVE>(pos, gi), v = loadAtom<NATIVE>(vel, gi);
                 freePart2(dt, f, invm, x, loadPlane3(S.savedPos + k, S.freeStride), v);
                 freePart1(dt, f, invm, x, v);
-                storeAtom(vel, gi, v);
-                storeAtom(pos, gi, x);
-                storePlane3(S.savedPos + k, S.freeStride, asStored(pos, x));
+                storeAtom<NATIVE>(vel, gi, v);
+                storeAtom<NATIVE>(pos, gi, x);
+                storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x));
             }
         }
     }
@@ -679,6 +691,7 @@ __device__ __forceinline__ void blockSum2(double& a, double& b, double (*scratch
     for (int w = 0; w < kKinThreads/32; w++) { a += scratch[w][0]; b += scratch[w][1]; }
 }
 
+template <bool NATIVE>
 __global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem S, const AtomView vel, double* partial,
                                                             unsigned* counter, double* out) {
     __shared__ double scratch[kKinThreads/32][2];
@@ -695,7 +708,7 @@ __global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem 
         kr += r2;
     }
     for (int k = g; k < S.numFree; k += T)
-        kt += freeKinetic(loadAtom(vel, atomSlot(S, k)), S.freeInvMass[k]);
+        kt += freeKinetic(loadAtom<NATIVE>(vel, atomSlot(S, k)), S.freeInvMass[k]);
     blockSum2(kt, kr, scratch);
     if (threadIdx.x == 0) {
         partial[2*blockIdx.x] = kt;
@@ -720,12 +733,12 @@ __global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem 
     }
 }
 
-template <bool EXACT, bool FUSED>
+template <bool EXACT, bool FUSED, bool NATIVE>
 cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     const size_t smem = FUSED ? sizeof(Part1Smem) : offsetof(Part1Smem, d);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(part1Kernel<EXACT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaError_t e = cudaFuncSetAttribute(part1Kernel<EXACT, FUSED, NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -735,24 +748,8 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     int perSM = EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT;
     if (const char* e = getenv("RBK_DEBUG_CTAS_PER_SM")) perSM = atoi(e) > 0 ? atoi(e) : perSM;     // profiling experiments only
     const int resident = S.numSMs*perSM;
-    part1Kernel<EXACT, FUSED><<<work < resident ? work : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
-    if (!FUSED && S.numTiles > 0) atomPositionKernel<<<S.numTiles, kBlock, 0, st>>>(S, pos);
-    return cudaGetLastError();
-}
-
-} // namespace
-
-cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
-    const bool exact = S.rotationMode == 0, fused = !S.splitPart1;
-    if (exact) return fused ? launchPart1Variant<true, true>(S, dt, pos, vel, force, st) : launchPart1Variant<true, false>(S, dt, pos, vel, force, st);
-    return fused ? launchPart1Variant<false, true>(S, dt, pos, vel, force, st) : launchPart1Variant<false, false>(S, dt, pos, vel, force, st);
-}
-
-cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    const int grid = S.numTiles + S.numFreeBlocks;
-    if (grid == 0) return cudaSuccess;
-    part2Kernel<<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    part1Kernel<EXACT, FUSED, NATIVE><<<work < resident ? work : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
+    if (!FUSED && S.numTiles > 0) atomPositionKernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, pos);
     return cudaGetLastError();
 }
 
@@ -760,20 +757,46 @@ template <bool EXACT, bool SMALL>
 cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(FusedSmem));
+        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int work = S.numTiles > 0 ? S.numTiles : S.numFreeBlocks;
     const int resident = S.numSMs*2;
-    part2Part1Kernel<EXACT, SMALL><<<work < resident ? work : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
+    part2Part1Kernel<EXACT, SMALL, true><<<work < resident ? work : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
+    return cudaGetLastError();
+}
+
+bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
+    return a.fmt == FMT_F64 && b.fmt == FMT_F64 && c.fmt == FMT_F64;
+}
+
+template <bool NATIVE>
+cudaError_t launchPart1Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    const bool exact = S.rotationMode == 0, fused = !S.splitPart1;
+    if (exact) return fused ? launchPart1Variant<true, true, NATIVE>(S, dt, pos, vel, force, st) : launchPart1Variant<true, false, NATIVE>(S, dt, pos, vel, force, st);
+    return fused ? launchPart1Variant<false, true, NATIVE>(S, dt, pos, vel, force, st) : launchPart1Variant<false, false, NATIVE>(S, dt, pos, vel, force, st);
+}
+
+} // namespace
+
+cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
+    return nativeIO(pos, vel, force) ? launchPart1Formats<true>(S, dt, pos, vel, force, st) : launchPart1Formats<false>(S, dt, pos, vel, force, st);
+}
+
+cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    const int grid = S.numTiles + S.numFreeBlocks;
+    if (grid == 0) return cudaSuccess;
+    if (nativeIO(pos, vel, force)) part2Kernel<true><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    else part2Kernel<false><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 
 cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
     // the one-pass kernel stages fp64 forces with cp.async; other formats / large bodies take the two kernels
-    if (!S.fusable || force.fmt != FMT_F64) {
+    if (!S.fusable || !nativeIO(pos, vel, force)) {
         cudaError_t e = launchPart2(S, dt, pos, vel, force, st);
         return e != cudaSuccess ? e : launchPart1(S, dt, pos, vel, force, st);
     }
@@ -784,7 +807,8 @@ cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, Ato
 
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out,
                           cudaStream_t st) {
-    kineticKernel<<<kKineticBlocks, kKinThreads, 0, st>>>(S, vel, partial, counter, out);
+    if (vel.fmt == FMT_F64) kineticKernel<true><<<kKineticBlocks, kKinThreads, 0, st>>>(S, vel, partial, counter, out);
+    else kineticKernel<false><<<kKineticBlocks, kKinThreads, 0, st>>>(S, vel, partial, counter, out);
     return cudaGetLastError();
 }
 
