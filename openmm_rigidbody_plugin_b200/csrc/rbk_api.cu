@@ -6,7 +6,6 @@
 
 #include <algorithm>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -126,8 +125,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     };
     // large bodies: smaller atom tiles keep a tile's coordinates L1-resident between the two atom phases of part 2
     const bool large = nB > 0 && (long long) nA > (long long) rbk::kSplitAtomsPerBody*nB;
-    int atomCap = large ? rbk::kLargeBodyTileAtoms : rbk::kTileAtoms;
-    if (const char* e = getenv("RBK_DEBUG_TILE_ATOMS")) atomCap = atoi(e) > 0 ? atoi(e) : atomCap;     // profiling experiments only
+    const int atomCap = large ? rbk::kLargeBodyTileAtoms : rbk::kTileAtoms;
     std::vector<int4> meta = cut(atomCap, true), bodyMeta = cut(rbk::kMaxTileAtoms, false);
 
     d.numBodies = nB;
@@ -202,8 +200,7 @@ int setLocation(rbk_system* sys, const int* location, cudaStream_t st) {
         return RBK_OK;
     }
     for (int i = 0; i < n; i++)
-        if (src[i] < 0 || (location == nullptr && src[i] >= h.numAtoms))
-            return fail(RBK_EINVAL, "rbk_set_atom_location: negative or out-of-range location");
+        if (src[i] < 0) return fail(RBK_EINVAL, "rbk_set_atom_location: negative location");
     RBK_CUDA(cudaMemcpyAsync(sys->dAtomLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     sys->dev.atomLoc = sys->dAtomLoc;

@@ -16,7 +16,6 @@
 #include "rbk_step.cuh"
 
 #include <cstddef>
-#include <cstdlib>
 
 namespace rbk {
 namespace {
@@ -745,9 +744,7 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     // persistent CTAs: one wave that fills every SM
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
     const int work = tiles > 0 ? tiles : S.numFreeBlocks;
-    int perSM = EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT;
-    if (const char* e = getenv("RBK_DEBUG_CTAS_PER_SM")) perSM = atoi(e) > 0 ? atoi(e) : perSM;     // profiling experiments only
-    const int resident = S.numSMs*perSM;
+    const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
     part1Kernel<EXACT, FUSED, NATIVE><<<work < resident ? work : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
     if (!FUSED && S.numTiles > 0) atomPositionKernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, pos);
     return cudaGetLastError();
