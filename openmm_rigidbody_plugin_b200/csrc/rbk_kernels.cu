@@ -258,22 +258,6 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
         cpWait<0>();
     }
 
-    // ---- free atoms: velocity-Verlet half kick + drift, grid-stride over chunks
-    for (int c = blockIdx.x; c < S.numFreeBlocks; c += G) {
-        const int base = c*kFreePerBlock + tid;
-#pragma unroll
-        for (int j = 0; j < kFreePerBlock/kBlock; j++) {
-            const int k = base + j*kBlock;
-            if (k < S.numFree) {
-                const long long gi = atomSlot(S, k);
-                d3 x = loadAtom<NATIVE>(pos, gi), v = loadAtom<NATIVE>(vel, gi);
-                freePart1(dt, loadAtom<NATIVE>(force, gi), S.freeInvMass[k], x, v);
-                storeAtom<NATIVE>(vel, gi, v);
-                storeAtom<NATIVE>(pos, gi, x);
-                storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x));
-            }
-        }
-    }
 }
 
 // Positions of the body atoms from the updated (r, q): one CTA per atom tile, thread per atom.
@@ -418,20 +402,6 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
             const d3 vcm = {sAcc[0][lb], sAcc[1][lb], sAcc[2][lb]};
             const d3 om = {sAcc[3][lb], sAcc[4][lb], sAcc[5][lb]};
             storeAtom<NATIVE>(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
-        }
-    }
-    else {                                                     // ---- free atoms
-        const int base = ((int) blockIdx.x - S.numTiles)*kFreePerBlock + tid;
-#pragma unroll
-        for (int j = 0; j < kFreePerBlock/kBlock; j++) {
-            const int k = base + j*kBlock;
-            if (k < S.numFree) {
-                const long long gi = atomSlot(S, k);
-                d3 v = loadAtom<NATIVE>(vel, gi);
-                freePart2(dt, loadAtom<NATIVE>(force, gi), S.freeInvMass[k], loadAtom<NATIVE>(pos, gi),
-                          loadPlane3(S.savedPos + k, S.freeStride), v);
-                storeAtom<NATIVE>(vel, gi, v);
-            }
         }
     }
 }
@@ -649,25 +619,34 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         cpWait<0>();
     }
 
-    // ---- free atoms: second half kick of this step, first half kick + drift of the next
-    for (int c = blockIdx.x; c < S.numFreeBlocks; c += G) {
-        const int base = c*kFreePerBlock + tid;
-#pragma unroll
-        for (int jj = 0; jj < kFreePerBlock/kBlock; jj++) {
-            const int k = base + jj*kBlock;
-            if (k < S.numFree) {
-                const long long gi = atomSlot(S, k);
-                const d3 f = loadAtom<NATIVE>(force, gi);
-                const double invm = S.freeInvMass[k];
-                d3 x = loadAtom<NATIVE>(pos, gi), v = loadAtom<NATIVE>(vel, gi);
-                freePart2(dt, f, invm, x, loadPlane3(S.savedPos + k, S.freeStride), v);
-                freePart1(dt, f, invm, x, v);
-                storeAtom<NATIVE>(vel, gi, v);
-                storeAtom<NATIVE>(pos, gi, x);
-                storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x));
-            }
-        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Free atoms: velocity Verlet, one thread per atom, its own launch so that it runs at full occupancy next to
+// the persistent body kernels.  PHASE 1 = part 1 (half kick + drift), 2 = part 2 (half kick + constraint
+// displacement), 3 = part 2 of this step followed by part 1 of the next.
+// ------------------------------------------------------------------------------------------------
+template <int PHASE, bool NATIVE>
+__global__ void __launch_bounds__(256) freeAtomsKernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel,
+                                                       const AtomView force) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= S.numFree) return;
+    const long long gi = atomSlot(S, k);
+    const d3 f = loadAtom<NATIVE>(force, gi);
+    const double invm = S.freeInvMass[k];
+    d3 x = loadAtom<NATIVE>(pos, gi), v = loadAtom<NATIVE>(vel, gi);
+    if (PHASE & 2) freePart2(dt, f, invm, x, loadPlane3(S.savedPos + k, S.freeStride), v);
+    if (PHASE & 1) {
+        freePart1(dt, f, invm, x, v);
+        storeAtom<NATIVE>(pos, gi, x);
+        storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x));
     }
+    storeAtom<NATIVE>(vel, gi, v);
+}
+
+template <int PHASE, bool NATIVE>
+void launchFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    if (S.numFree > 0) freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -742,10 +721,10 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
         configured = true;
     }
     // persistent CTAs: one wave that fills every SM
+    launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
-    const int work = tiles > 0 ? tiles : S.numFreeBlocks;
     const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
-    part1Kernel<EXACT, FUSED, NATIVE><<<work < resident ? work : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
+    if (tiles > 0) part1Kernel<EXACT, FUSED, NATIVE><<<tiles < resident ? tiles : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
     if (!FUSED && S.numTiles > 0) atomPositionKernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, pos);
     return cudaGetLastError();
 }
@@ -758,9 +737,10 @@ cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int work = S.numTiles > 0 ? S.numTiles : S.numFreeBlocks;
+    launchFree<3, true>(S, dt, pos, vel, force, st);
     const int resident = S.numSMs*2;
-    part2Part1Kernel<EXACT, SMALL, true><<<work < resident ? work : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
+    if (S.numTiles > 0)
+        part2Part1Kernel<EXACT, SMALL, true><<<S.numTiles < resident ? S.numTiles : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 
@@ -783,10 +763,15 @@ cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView
 }
 
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    const int grid = S.numTiles + S.numFreeBlocks;
-    if (grid == 0) return cudaSuccess;
-    if (nativeIO(pos, vel, force)) part2Kernel<true><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
-    else part2Kernel<false><<<grid, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
+    if (nativeIO(pos, vel, force)) {
+        launchFree<2, true>(S, dt, pos, vel, force, st);
+        if (S.numTiles > 0) part2Kernel<true><<<S.numTiles, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    }
+    else {
+        launchFree<2, false>(S, dt, pos, vel, force, st);
+        if (S.numTiles > 0) part2Kernel<false><<<S.numTiles, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    }
     return cudaGetLastError();
 }
 
