@@ -201,15 +201,18 @@ std::string HostModel::initialize(int nAtoms, const int* labels, const double* m
     isVirtual.assign(nAtoms, 0);
     if (virt) for (int i = 0; i < nAtoms; i++) isVirtual[i] = virt[i] ? 1 : 0;
 
-    // compact labels: distinct positive values -> 1..nB in ascending order of the value
+    // compact labels: distinct positive values -> 1..nB in ascending order of the value (sort + binary search, so
+    // that sparse labels such as residue serial numbers in the billions cost O(N log N), not O(max label) memory)
     int top = *std::max_element(labels, labels + nAtoms);
     if (top < 0) return "bodyIndices has no non-negative entry";
-    std::vector<int> rank((size_t) top + 1, 0);
-    for (int i = 0; i < nAtoms; i++) if (labels[i] > 0) rank[labels[i]] = 1;
-    numBodies = 0;
-    for (int v = 1; v <= top; v++) if (rank[v]) rank[v] = ++numBodies;
+    std::vector<int> distinct;
+    for (int i = 0; i < nAtoms; i++) if (labels[i] > 0) distinct.push_back(labels[i]);
+    std::sort(distinct.begin(), distinct.end());
+    distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+    numBodies = (int) distinct.size();
     bodyIndex.resize(nAtoms);
-    for (int i = 0; i < nAtoms; i++) bodyIndex[i] = labels[i] > 0 ? rank[labels[i]] : 0;
+    for (int i = 0; i < nAtoms; i++)
+        bodyIndex[i] = labels[i] > 0 ? (int) (std::lower_bound(distinct.begin(), distinct.end(), labels[i]) - distinct.begin()) + 1 : 0;
 
     numActualAtoms = nAtoms;
     for (int i = 0; i < nAtoms; i++) if (isVirtual[i]) numActualAtoms--;

@@ -21,6 +21,7 @@ namespace rbk {
 namespace {
 
 constexpr int kWarps = kBlock/32;
+constexpr int kMaxDevices = 64;
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ d3 loadPlane3(const double* base, size_t stride) {
@@ -714,11 +715,13 @@ __global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem 
 template <bool EXACT, bool FUSED, bool NATIVE>
 cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     const size_t smem = FUSED ? sizeof(Part1Smem) : offsetof(Part1Smem, d);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};                  // the attribute is per device
+    int device = 0;
+    cudaGetDevice(&device);
+    if (device < 0 || device >= kMaxDevices || !configured[device]) {
         cudaError_t e = cudaFuncSetAttribute(part1Kernel<EXACT, FUSED, NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
     // persistent CTAs: one wave that fills every SM
     launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
@@ -731,11 +734,13 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
 
 template <bool EXACT, bool SMALL>
 cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    if (device < 0 || device >= kMaxDevices || !configured[device]) {
         cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
     launchFree<3, true>(S, dt, pos, vel, force, st);
     const int resident = S.numSMs*2;
