@@ -423,18 +423,45 @@ constexpr int kSmallBody = 8;                       // bodies up to this size ar
 
 struct FusedStage {
     double body[kFPlanes][kBlock];
-    double f[3][kTileAtoms];                        // atom forces, later the arms delta = A^T(q) d
+    double f[3*kTileAtoms];                         // atom forces as xyzxyz..., later the arms delta = A^T(q) d
     double d[3][kTileAtoms];
     int loc[kBlock + 4];
-    unsigned char localBody[kTileAtoms + 16];
+    unsigned char localBody[kTileAtoms + 32];
 };
 struct FusedSmem {
     FusedStage stage[2];
+    unsigned long long bar[2];                      // one mbarrier per stage (bulk-copy completion)
     double acc[6][kBlock];
     double head[kWarps][6];
     int headKey[kWarps];
     int4 meta[3];
 };
+
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier completion: one elected thread moves a whole plane
+// segment with one instruction instead of every thread issuing an 8-byte cp.async per element.
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulkCopy(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smemAddr(smem)), "l"(gmem), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
 __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k == 14 ? (int) PL_INVM : (int) PL_INVI + (k - 15)); }
@@ -449,8 +476,32 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     const size_t ld = S.bodyStride, as = S.atomStride;
     const int numTiles = S.numTiles;
 
+    // A tile can arrive by bulk copies when every segment is 16-byte aligned and a multiple of 16 bytes long and the
+    // tile's forces are one contiguous Vec3 range (water tiles always are); otherwise per-thread cp.async.
+    const bool contiguousForces = S.atomLoc == nullptr && force.sa == 3 && force.sc == 1 && (reinterpret_cast<size_t>(force.p) & 15) == 0;
+    auto bulkOK = [&](int4 m) {
+        return contiguousForces && (m.x & 3) == 0 && (m.y & 3) == 0 && (m.z & 1) == 0 && (m.w & 1) == 0 &&
+               ((S.numFree + m.z) & 1) == 0;
+    };
     auto request = [&](int4 m, int st) {
         FusedStage& T = sm.stage[st];
+        const int lbFirst = m.z & ~15;                         // 16-byte granules of the byte array
+        const unsigned lbBytes = (unsigned) (((m.z + m.w - lbFirst) + 15) & ~15);
+        if (bulkOK(m)) {
+            if (tid == 0) {
+                fenceProxyAsync();                             // earlier generic-proxy writes to this stage are ordered first
+                mbarExpectTx(&sm.bar[st], (unsigned) (kFPlanes*8*m.y + 4*m.y + 48*m.w) + lbBytes);
+                const double* g = S.state + (size_t) m.x;
+#pragma unroll
+                for (int k = 0; k < kFPlanes; k++) bulkCopy(&T.body[k][0], g + fusedGlobalPlane(k)*ld, 8u*m.y, &sm.bar[st]);
+                bulkCopy(&T.loc[0], S.loc + m.x, 4u*m.y, &sm.bar[st]);
+#pragma unroll
+                for (int c = 0; c < 3; c++) bulkCopy(&T.d[c][0], S.dxyz + (size_t) m.z + c*as, 8u*m.w, &sm.bar[st]);
+                bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
+                bulkCopy(&T.localBody[0], S.localBody + lbFirst, lbBytes, &sm.bar[st]);
+            }
+            return;
+        }
         if (tid < m.y) {
             const double* g = S.state + (size_t) (m.x + tid);
 #pragma unroll
@@ -463,13 +514,18 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             cpAsync8(&T.d[1][j], g + as);
             cpAsync8(&T.d[2][j], g + 2*as);
             const double* fp = force.p + atomSlot(S, S.numFree + m.z + j)*force.sa;
-            cpAsync8(&T.f[0][j], fp);
-            cpAsync8(&T.f[1][j], fp + force.sc);
-            cpAsync8(&T.f[2][j], fp + 2*force.sc);
+            cpAsync8(&T.f[3*j], fp);
+            cpAsync8(&T.f[3*j + 1], fp + force.sc);
+            cpAsync8(&T.f[3*j + 2], fp + 2*force.sc);
         }
-        const int first = m.z & ~3;
-        for (int w = tid; 4*w < m.z + m.w - first; w += kBlock)
-            cpAsync4(&T.localBody[4*w], S.localBody + first + 4*w);
+        for (unsigned w = tid; 4*w < lbBytes; w += kBlock)
+            cpAsync4(&T.localBody[4*w], S.localBody + lbFirst + 4*w);
+    };
+    // wait for a stage filled by request(): mbarrier phase for bulk tiles, cp.async groups otherwise
+    unsigned bulkPhase[2] = {0u, 0u};
+    auto arrived = [&](int4 m, int st) {
+        if (bulkOK(m)) { mbarWait(&sm.bar[st], bulkPhase[st] & 1u); bulkPhase[st]++; }
+        cpWait<0>();
     };
 
     const int tile0 = blockIdx.x;
@@ -477,6 +533,9 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         if (tid == 0) {
             sm.meta[0] = S.tileMeta[tile0];
             if (tile0 + G < numTiles) sm.meta[1] = S.tileMeta[tile0 + G];
+            mbarInit(&sm.bar[0], 1);
+            mbarInit(&sm.bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         request(sm.meta[0], 0);
@@ -489,7 +548,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
                 if (tid < kWarps*6) sm.head[tid/6][tid%6] = 0.0;
             }
-            cpWait<0>();                                       // this tile (+ the next tile's descriptor) landed
+            arrived(m, it & 1);                                // this tile (+ the next tile's descriptor) landed
             __syncthreads();
             if (tile + G < numTiles) {
                 request(sm.meta[(it + 1) % 3], (it & 1) ^ 1);
@@ -501,7 +560,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             // SMALL (every body has <= kSmallBody atoms, e.g. water): each body's thread sums its own atoms straight
             // from the staged forces/coordinates in phase C - sequential order, no shuffles, no extra barrier.
             // Otherwise: thread per atom + warp-shuffle segmented scan, exactly as in part2Kernel.
-            const int shift = m.z & 3;
+            const int shift = m.z & 15;
             if (!SMALL) {
                 const int per = ((m.w + kBlock - 1)/kBlock)*32;
                 const int wBeg = warp*per, wEnd = min(wBeg + per, m.w);        // tile-local atom indices
@@ -519,10 +578,10 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     if (valid) {
                         key = T.localBody[j + shift];
                         const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
-                        const d3 f = {T.f[0][j], T.f[1][j], T.f[2][j]};
+                        const d3 f = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
                         const d4 q = {T.body[6][key], T.body[7][key], T.body[8][key], T.body[9][key]};
                         const d3 delta = bodyToSpace(q, d);
-                        T.f[0][j] = delta.x; T.f[1][j] = delta.y; T.f[2][j] = delta.z;     // kept for the velocities
+                        T.f[3*j] = delta.x; T.f[3*j + 1] = delta.y; T.f[3*j + 2] = delta.z;     // kept for the velocities
                         const d3 t = cross(delta, f);
                         v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = t.x; v[4] = t.y; v[5] = t.z;
                     }
@@ -562,9 +621,9 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     const int j0 = T.loc[tid] - m.z, j1 = (tid + 1 < m.y ? T.loc[tid + 1] - m.z : m.w);
                     for (int j = j0; j < j1; j++) {
                         const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
-                        const d3 f = {T.f[0][j], T.f[1][j], T.f[2][j]};
+                        const d3 f = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
                         const d3 delta = bodyToSpace(q, d);
-                        T.f[0][j] = delta.x; T.f[1][j] = delta.y; T.f[2][j] = delta.z;     // kept for the velocities
+                        T.f[3*j] = delta.x; T.f[3*j + 1] = delta.y; T.f[3*j + 2] = delta.z;     // kept for the velocities
                         F = F + f;
                         tau = tau + cross(delta, f);
                     }
@@ -605,7 +664,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             // ---- D: thread per atom: velocities at the end of this step, positions of the next
             for (int j = tid; j < m.w; j += kBlock) {
                 const int k = T.localBody[j + shift];
-                const d3 delta = {T.f[0][j], T.f[1][j], T.f[2][j]};
+                const d3 delta = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
                 const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
                 const d3 om = {sm.acc[3][k], sm.acc[4][k], sm.acc[5][k]};
                 const long long slot = atomSlot(S, S.numFree + m.z + j);
