@@ -141,6 +141,23 @@ typedef void (*rbk_force_fn)(const double* R, double* F, int numAtoms, void* use
 int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F,
                      rbk_force_fn forces, void* user, void* stream);
 
+/* The same step with the two host-side hooks the reference's Reference-platform kernel runs when the system
+ * has free atoms (ReferenceRigidBodyKernels.cpp:92-104):
+ *   constrainPositions(oldR, R, ...)  after Part 1 and before the forces - the place of
+ *       ReferenceConstraints::apply(oldPos, R, invMass, tol) and ReferenceVirtualSites::computePositions;
+ *       oldR holds the positions before the step, R the unconstrained new ones; return nonzero if R was changed
+ *       (it is then copied back to the device, where Part 2 turns R - savedPos into the velocity correction of
+ *       RigidBodySystem.cpp:196-197);
+ *   constrainVelocities(R, V, ...)    after Part 2 - ReferenceConstraints::applyToVelocities(R, V, invMass, tol);
+ *       return nonzero if V was changed (copied back to the device for the next step's free-atom kick).
+ * Either hook may be NULL.  Only free atoms and virtual sites may be modified: the positions and velocities of
+ * body atoms are outputs of the rigid-body state. */
+typedef int (*rbk_positions_fn)(const double* oldR, double* R, int numAtoms, void* user);
+typedef int (*rbk_velocities_fn)(const double* R, double* V, int numAtoms, void* user);
+int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, double* V, double* F,
+                           rbk_force_fn forces, rbk_positions_fn constrainPositions,
+                           rbk_velocities_fn constrainVelocities, void* user, void* stream);
+
 /* ---- OpenMM-CUDA boundary formats ------------------------------------------------------------
  * The device arrays OpenMM's CUDA platform hands to an integrator kernel (what the reference's CUDA kernels
  * read and write, platforms/cuda/src/kernels/rigidbodyintegrator.cu:30-64,270-279 and
@@ -157,6 +174,18 @@ int rbk_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
 int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
                      int paddedNumAtoms, int precision, void* stream);
 int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double* out, void* stream);
+
+/* Free-atom constraint hooks of the CUDA flow (CudaRigidBodyKernels.cpp:405-421; kernels freeAtomsDelta and the
+ * free-atom loop of integrateRigidBodyPart1, rigidbodyintegrator.cu:276-285, 303-312):
+ *   rbk_free_delta_openmm      posDelta[i].xyz = (v + f invMass dt/2) dt for every free atom (mixed4 array:
+ *                              float4 in single precision, double4 otherwise; .w untouched);
+ *   <caller>                   integration.applyConstraints(tol) corrects posDelta;
+ *   rbk_part1_delta_openmm     Part 1 in which free atoms move by posDelta instead of v dt;
+ *   <caller>                   computeVirtualSites, forces, rbk_part2_openmm, applyVelocityConstraints. */
+int rbk_free_delta_openmm(rbk_system* sys, double dt, const void* velm, const long long* force, int paddedNumAtoms,
+                          int precision, void* posDelta, void* stream);
+int rbk_part1_delta_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm,
+                           const long long* force, int paddedNumAtoms, int precision, const void* posDelta, void* stream);
 int rbk_update_device_openmm(rbk_system* sys, void* posq, void* posqCorrection, void* velm, const long long* force,
                              int paddedNumAtoms, int precision, int geometry, int velocities, void* stream);
 

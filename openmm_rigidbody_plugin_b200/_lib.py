@@ -15,6 +15,7 @@ RBK_OPENMM_SINGLE, RBK_OPENMM_MIXED, RBK_OPENMM_DOUBLE = 0, 1, 2
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 FORCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+HOOK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)     # rbk_positions_fn / rbk_velocities_fn
 
 # every symbol include/rbk.h declares, with its signature
 SIGNATURES = {
@@ -42,6 +43,11 @@ SIGNATURES = {
     "rbk_kinetic_host": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.c_void_p]),
     "rbk_download_bodies": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_void_p]),
     "rbk_execute_host": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, FORCE_FN, C.c_void_p, C.c_void_p]),
+    "rbk_execute_host_hooks": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, FORCE_FN, HOOK_FN, HOOK_FN,
+                                         C.c_void_p, C.c_void_p]),
+    "rbk_free_delta_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rbk_part1_delta_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p]),
 }
 
 _lib = None

@@ -70,7 +70,7 @@ struct rbk_system {
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaEvent_t evStart = nullptr, evForces = nullptr, evPart1 = nullptr, evPositions = nullptr;
     bool mirrorsLoaded = false;
-    std::vector<double> staging;
+    std::vector<double> staging, oldPositions;
 
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta);
@@ -479,6 +479,29 @@ int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
     return RBK_OK;
 }
 
+int rbk_free_delta_openmm(rbk_system* sys, double dt, const void* velm, const long long* force, int paddedNumAtoms,
+                          int precision, void* posDelta, void* stream) {
+    if (!sys || !posDelta) return fail(RBK_EINVAL, "rbk_free_delta_openmm: NULL argument");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_free_delta_openmm: body system not uploaded");
+    AtomView p, v, f;
+    int dummy = 0;
+    if (openmmViews(&dummy, &dummy, (void*) velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
+    const AtomView d{(double*) posDelta, 0, 0, v.fmt, nullptr};
+    RBK_CUDA(rbk::launchFreeDelta(sys->dev, dt, v, f, d, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_part1_delta_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm,
+                           const long long* force, int paddedNumAtoms, int precision, const void* posDelta, void* stream) {
+    if (!sys || !posDelta) return fail(RBK_EINVAL, "rbk_part1_delta_openmm: NULL argument");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part1_delta_openmm: body system not uploaded");
+    AtomView p, v, f;
+    if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
+    const AtomView d{(double*) posDelta, 0, 0, v.fmt, nullptr};
+    RBK_CUDA(rbk::launchPart1Delta(sys->dev, dt, p, v, f, d, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
 int rbk_update_device_openmm(rbk_system* sys, void* posq, void* posqCorrection, void* velm, const long long* force,
                              int paddedNumAtoms, int precision, int geometry, int velocities, void* stream) {
     if (!sys) return fail(RBK_EINVAL, "rbk_update_device_openmm: NULL system");
@@ -549,6 +572,12 @@ int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, do
 
 int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F, rbk_force_fn forces,
                      void* user, void* stream) {
+    return rbk_execute_host_hooks(sys, dt, steps, R, V, F, forces, nullptr, nullptr, user, stream);
+}
+
+int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, double* V, double* F, rbk_force_fn forces,
+                           rbk_positions_fn constrainPositions, rbk_velocities_fn constrainVelocities, void* user,
+                           void* stream) {
     if (!sys || !R || !V || !F) return fail(RBK_EINVAL, "rbk_execute_host: NULL argument");
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_execute_host: body system not uploaded");
     cudaStream_t st = (cudaStream_t) stream;
@@ -574,12 +603,18 @@ int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V
     const AtomView p{sys->mPos, 3, 1, rbk::FMT_F64, nullptr}, v{sys->mVel, 3, 1, rbk::FMT_F64, nullptr};
     for (int i = 0; i < steps; i++) {
         const AtomView fOld{sys->mForce, 3, 1, rbk::FMT_F64, nullptr}, fNew{sys->mForce2, 3, 1, rbk::FMT_F64, nullptr};
-        if (forces) {
-            // forces depend on the new positions: Part 1 -> positions to the host -> callback -> forces to the device
+        if (forces || constrainPositions) {
+            // forces depend on the new positions: Part 1 -> positions to the host -> hooks -> forces to the device
+            if (constrainPositions) {
+                sys->oldPositions.resize((size_t) sys->host.numAtoms*3);
+                std::memcpy(sys->oldPositions.data(), R, bytes);
+            }
             RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, fOld, st));
             RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
             RBK_CUDA(cudaStreamSynchronize(st));
-            forces(R, F, sys->host.numAtoms, user);
+            if (constrainPositions && constrainPositions(sys->oldPositions.data(), R, sys->host.numAtoms, user))
+                RBK_CUDA(cudaMemcpyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
+            if (forces) forces(R, F, sys->host.numAtoms, user);
             RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, st));
         }
         else {
@@ -598,7 +633,12 @@ int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V
         }
         RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, fNew, st));
         RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
-        if (!forces) RBK_CUDA(cudaStreamWaitEvent(st, sys->evPositions, 0));     // R is complete when `st` is
+        if (!forces && !constrainPositions) RBK_CUDA(cudaStreamWaitEvent(st, sys->evPositions, 0));     // R is complete when `st` is
+        if (constrainVelocities) {
+            RBK_CUDA(cudaStreamSynchronize(st));
+            if (constrainVelocities(R, V, sys->host.numAtoms, user))
+                RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+        }
         std::swap(sys->mForce, sys->mForce2);
     }
     RBK_CUDA(cudaStreamSynchronize(st));

@@ -61,6 +61,9 @@ struct AtomView {
 
 cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
+// free-atom constraint hooks: delta = (v + f invm dt/2) dt for every free atom; part 1 that advances free atoms by delta
+cudaError_t launchFreeDelta(const DeviceSystem& S, double dt, AtomView vel, AtomView force, AtomView delta, cudaStream_t st);
+cudaError_t launchPart1Delta(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, AtomView delta, cudaStream_t st);
 // part 2 of one step immediately followed by part 1 of the next (identical results, one pass over the data)
 cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
 // partial: scratch of 2*kKineticBlocks doubles; counter: zero-initialised unsigned; out: 2 doubles (device)

@@ -709,6 +709,29 @@ void launchFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, At
     if (S.numFree > 0) freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
 }
 
+// Free-atom constraint hooks (the reference's freeAtomsDelta pre-pass, rigidbodyintegrator.cu:276-285, and the free-atom
+// loop of its integrateRigidBodyPart1, :303-312).  CONSUME = false: delta = (v + f invm dt/2) dt, nothing else is
+// touched, so the caller's constraint solver can correct the displacement.  CONSUME = true: the first half kick of the
+// velocity, x += delta, savedPos = x.
+template <bool CONSUME>
+__global__ void __launch_bounds__(256) freeDeltaKernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel,
+                                                       const AtomView force, const AtomView delta) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= S.numFree) return;
+    const long long gi = atomSlot(S, k);
+    const d3 f = loadAtom<false>(force, gi);
+    d3 v = loadAtom<false>(vel, gi);
+    v = v + f*S.freeInvMass[k]*(0.5*dt);
+    if (!CONSUME) {
+        storeAtom<false>(delta, gi, v*dt);
+        return;
+    }
+    const d3 x = loadAtom<false>(pos, gi) + loadAtom<false>(delta, gi);
+    storeAtom<false>(pos, gi, x);
+    storePlane3(S.savedPos + k, S.freeStride, asStored<false>(pos, x));
+    storeAtom<false>(vel, gi, v);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kinetic energies: fixed-shape two-level tree (warp shuffles -> shared -> last CTA), no atomics
 // on the data path, so the two doubles are bit-reproducible from run to run.
@@ -772,7 +795,7 @@ __global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem 
 }
 
 template <bool EXACT, bool FUSED, bool NATIVE>
-cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st) {
     const size_t smem = FUSED ? sizeof(Part1Smem) : offsetof(Part1Smem, d);
     static bool configured[kMaxDevices] = {};                  // the attribute is per device
     int device = 0;
@@ -783,7 +806,7 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
         if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
     // persistent CTAs: one wave that fills every SM
-    launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
+    if (freeAtoms) launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
     const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
     if (tiles > 0) part1Kernel<EXACT, FUSED, NATIVE><<<tiles < resident ? tiles : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
@@ -813,17 +836,28 @@ bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
 }
 
 template <bool NATIVE>
-cudaError_t launchPart1Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+cudaError_t launchPart1Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st) {
     const bool exact = S.rotationMode == 0, fused = !S.splitPart1;
-    if (exact) return fused ? launchPart1Variant<true, true, NATIVE>(S, dt, pos, vel, force, st) : launchPart1Variant<true, false, NATIVE>(S, dt, pos, vel, force, st);
-    return fused ? launchPart1Variant<false, true, NATIVE>(S, dt, pos, vel, force, st) : launchPart1Variant<false, false, NATIVE>(S, dt, pos, vel, force, st);
+    if (exact) return fused ? launchPart1Variant<true, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<true, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st);
+    return fused ? launchPart1Variant<false, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<false, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st);
 }
 
 } // namespace
 
 cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
-    return nativeIO(pos, vel, force) ? launchPart1Formats<true>(S, dt, pos, vel, force, st) : launchPart1Formats<false>(S, dt, pos, vel, force, st);
+    return nativeIO(pos, vel, force) ? launchPart1Formats<true>(S, dt, pos, vel, force, true, st) : launchPart1Formats<false>(S, dt, pos, vel, force, true, st);
+}
+
+cudaError_t launchFreeDelta(const DeviceSystem& S, double dt, AtomView vel, AtomView force, AtomView delta, cudaStream_t st) {
+    if (S.numFree > 0) freeDeltaKernel<false><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, vel, vel, force, delta);
+    return cudaGetLastError();
+}
+
+cudaError_t launchPart1Delta(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, AtomView delta, cudaStream_t st) {
+    if (S.numFree > 0) freeDeltaKernel<true><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force, delta);
+    if (S.numTiles == 0) return cudaGetLastError();
+    return nativeIO(pos, vel, force) ? launchPart1Formats<true>(S, dt, pos, vel, force, false, st) : launchPart1Formats<false>(S, dt, pos, vel, force, false, st);
 }
 
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {

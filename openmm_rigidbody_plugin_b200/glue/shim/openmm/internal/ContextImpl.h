@@ -5,6 +5,7 @@
 #include "openmm/Platform.h"
 #include "openmm/System.h"
 #include "openmm/reference/ReferencePlatform.h"
+#include "openmm/reference/ReferenceVirtualSites.h"
 #include <vector>
 namespace OpenMM {
 class Context;
@@ -42,6 +43,7 @@ inline double ContextImpl::calcForcesAndEnergy(bool includeForces, bool includeE
     for (size_t i = 0; i < f.size(); i++) f[i] = Vec3();
     double energy = 0.0;
     for (int i = 0; i < system.getNumForces(); i++) energy += system.getForce(i).calcForcesAndEnergy(*d->positions, f);
+    if (includeForces) ReferenceVirtualSites::distributeForces(system, *d->positions, f);
     lastEnergy = energy;
     return energy;
 }

@@ -1,9 +1,10 @@
 // B200 kernel: every IntegrateRigidBodyStepKernel method forwards to the C ABI (include/rbk.h).
 // Step protocol = ReferenceIntegrateRigidBodyStepKernel::execute (platforms/reference/src/ReferenceRigidBodyKernels.cpp:82-108)
-// for systems without free-atom constraints / virtual sites: Part 1 -> forces at the new positions -> Part 2.
+// Part 1 -> [constraints among free atoms, virtual sites] -> forces at the new positions -> Part 2 -> [velocity constraints].
 #include "B200RigidBodyKernels.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/ContextImpl.h"
+#include "openmm/reference/ReferenceVirtualSites.h"
 
 using namespace RigidBodyPlugin;
 using namespace OpenMM;
@@ -15,9 +16,20 @@ static void check(int rc) {
 
 void B200IntegrateRigidBodyStepKernel::initialize(ContextImpl& contextRef, const RigidBodyIntegrator& integrator) {
     context = &contextRef;
-    if (contextRef.getSystem().getNumConstraints() != 0 && integrator.getRigidBodySystem().getNumFree() != 0)
-        throw OpenMMException("B200 rigid-body kernel: constraints between free atoms need OpenMM's constraint kernels, "
-                              "which are outside this implementation");
+    const System& sys = contextRef.getSystem();
+    const int numAtoms = sys.getNumParticles();
+    invMass.resize(numAtoms);                                   // ReferenceRigidBodyKernels.cpp:68-75
+    bool virtualSites = false;
+    for (int i = 0; i < numAtoms; i++) {
+        const double mass = sys.getParticleMass(i);
+        invMass[i] = mass == 0.0 ? 0.0 : 1.0/mass;
+        virtualSites = virtualSites || sys.isVirtualSite(i);
+    }
+    oldPos.resize(numAtoms);
+    // the reference calls the constraint solver whenever there are free atoms (a no-op without constraints) and
+    // ReferenceVirtualSites::computePositions always; the hooks are only installed when they have work to do
+    velocityHook = sys.getNumConstraints() != 0;
+    positionHook = velocityHook || virtualSites;
 }
 
 void B200IntegrateRigidBodyStepKernel::uploadBodySystem(RigidBodySystem& bodySystem) {
@@ -31,6 +43,26 @@ void B200IntegrateRigidBodyStepKernel::evaluateForces(const double*, double*, in
     static_cast<B200IntegrateRigidBodyStepKernel*>(self)->context->calcForcesAndEnergy(true, false);
 }
 
+// After Part 1: ReferenceConstraints::apply(oldPos, R, invMass, tol) when there are free atoms, then
+// ReferenceVirtualSites::computePositions (ReferenceRigidBodyKernels.cpp:98-100).  R aliases data.positions.
+int B200IntegrateRigidBodyStepKernel::constrainPositions(const double* oldR, double*, int numAtoms, void* selfPtr) {
+    B200IntegrateRigidBodyStepKernel* self = static_cast<B200IntegrateRigidBodyStepKernel*>(selfPtr);
+    const System& sys = self->context->getSystem();
+    if (self->velocityHook) {
+        for (int i = 0; i < numAtoms; i++) self->oldPos[i] = Vec3(oldR[3*i], oldR[3*i+1], oldR[3*i+2]);
+        self->data.constraints->apply(self->oldPos, *self->data.positions, self->invMass, self->tolerance);
+    }
+    ReferenceVirtualSites::computePositions(sys, *self->data.positions);
+    return 1;
+}
+
+// After Part 2: ReferenceConstraints::applyToVelocities(R, V, invMass, tol) (ReferenceRigidBodyKernels.cpp:103-104).
+int B200IntegrateRigidBodyStepKernel::constrainVelocities(const double*, double*, int, void* selfPtr) {
+    B200IntegrateRigidBodyStepKernel* self = static_cast<B200IntegrateRigidBodyStepKernel*>(selfPtr);
+    self->data.constraints->applyToVelocities(*self->data.positions, *self->data.velocities, self->invMass, self->tolerance);
+    return 1;
+}
+
 void B200IntegrateRigidBodyStepKernel::execute(ContextImpl& contextRef, const RigidBodyIntegrator& integrator) {
     if (system == NULL) throw OpenMMException("B200 rigid-body kernel: positions have not been set");
     vector<Vec3>& R = *data.positions;
@@ -38,7 +70,11 @@ void B200IntegrateRigidBodyStepKernel::execute(ContextImpl& contextRef, const Ri
     vector<Vec3>& F = *data.forces;
     const double dt = integrator.getStepSize();
     context = &contextRef;
-    check(rbk_execute_host(system, dt, 1, &R[0][0], &V[0][0], &F[0][0], &evaluateForces, this, NULL));
+    tolerance = integrator.getConstraintTolerance();
+    const bool freeAtoms = bodies != NULL && bodies->getNumFree() != 0;
+    check(rbk_execute_host_hooks(system, dt, 1, &R[0][0], &V[0][0], &F[0][0], &evaluateForces,
+                                 positionHook ? &constrainPositions : NULL,
+                                 velocityHook && freeAtoms ? &constrainVelocities : NULL, this, NULL));
     data.time += dt;
     data.stepCount++;
 }

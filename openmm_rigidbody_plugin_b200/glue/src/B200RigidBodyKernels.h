@@ -12,7 +12,8 @@ namespace RigidBodyPlugin {
 class B200IntegrateRigidBodyStepKernel : public IntegrateRigidBodyStepKernel {
 public:
     B200IntegrateRigidBodyStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::ReferencePlatform::PlatformData& data)
-        : IntegrateRigidBodyStepKernel(name, platform), data(data), system(NULL), context(NULL), bodies(NULL) {}
+        : IntegrateRigidBodyStepKernel(name, platform), data(data), system(NULL), context(NULL), bodies(NULL), tolerance(1e-5),
+          positionHook(false), velocityHook(false) {}
     void initialize(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator);
     void uploadBodySystem(RigidBodySystem& bodySystem);
     void execute(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator);
@@ -22,10 +23,16 @@ public:
     double getPotentialEnergyRefinement(const RigidBodyIntegrator& integrator);
 private:
     static void evaluateForces(const double* R, double* F, int numAtoms, void* self);
+    static int constrainPositions(const double* oldR, double* R, int numAtoms, void* self);
+    static int constrainVelocities(const double* R, double* V, int numAtoms, void* self);
     OpenMM::ReferencePlatform::PlatformData& data;
     rbk_system* system;                      // borrowed from the integrator's RigidBodySystem
     OpenMM::ContextImpl* context;
     RigidBodySystem* bodies;
+    std::vector<double> invMass;
+    std::vector<OpenMM::Vec3> oldPos;
+    double tolerance;
+    bool positionHook, velocityHook;
 };
 
 } // namespace RigidBodyPlugin

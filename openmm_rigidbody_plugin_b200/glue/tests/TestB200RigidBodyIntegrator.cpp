@@ -6,6 +6,7 @@
 #include "openmm/Context.h"
 #include "openmm/HarmonicBondForce.h"
 #include "openmm/OpenMMException.h"
+#include "openmm/VirtualSite.h"
 #include "openmm/reference/ReferencePlatform.h"
 #include <cmath>
 #include <cstdio>
@@ -112,6 +113,79 @@ static void testRigidWaters(Platform& platform, int mode) {
     ASSERT(integrator.getPotentialEnergyRefinement() == 0.0);
 }
 
+// Rigid waters + constrained free diatomics (+ a virtual site at one bond's midpoint): the path on which the reference's
+// kernel calls ReferenceConstraints::apply / applyToVelocities and ReferenceVirtualSites::computePositions
+// (ReferenceRigidBodyKernels.cpp:92-104).  Constraints hold to the integrator's tolerance, the velocity along each
+// constrained bond vanishes, energy is conserved, DOF = numFree - numConstraints + 6 per body (RigidBodySystem.cpp:130-134).
+static void testConstrainedFreeAtoms(Platform& platform) {
+    const int nMol = 16, nPairs = 12;
+    const double rOH = 0.09572, half = 0.5*104.52*M_PI/180.0, bond = 0.12;
+    System system;
+    vector<int> bodyIndices;
+    vector<Vec3> positions, velocities;
+    unsigned seed = 777u;
+    auto rnd = [&]() { seed = seed*1664525u + 1013904223u; return (seed >> 8)/16777216.0 - 0.5; };
+    for (int m = 0; m < nMol; m++) {
+        Vec3 c(0.35*(m % 4), 0.35*(m/4), 0.0);
+        system.addParticle(15.99943); system.addParticle(1.007947); system.addParticle(1.007947);
+        positions.push_back(c);
+        positions.push_back(c + Vec3(rOH*sin(half), 0, rOH*cos(half)));
+        positions.push_back(c + Vec3(-rOH*sin(half), 0, rOH*cos(half)));
+        for (int k = 0; k < 3; k++) { bodyIndices.push_back(m + 1); velocities.push_back(Vec3(rnd(), rnd(), rnd())); }
+    }
+    const int firstFree = 3*nMol;
+    HarmonicBondForce* bonds = new HarmonicBondForce();
+    for (int k = 0; k < nPairs; k++) {
+        Vec3 c(0.35*(k % 4) + 0.1, 0.35*(k/4) + 0.1, 0.4);
+        const int a = system.addParticle(14.0), b = system.addParticle(16.0);
+        positions.push_back(c);
+        positions.push_back(c + Vec3(bond, 0, 0));
+        Vec3 v(rnd(), rnd(), rnd()), w(0, rnd(), rnd());            // relative velocity perpendicular to the bond
+        velocities.push_back(v);
+        velocities.push_back(v + w);
+        bodyIndices.push_back(0); bodyIndices.push_back(0);
+        system.addConstraint(a, b, bond);
+        bonds->addBond(a, 3*k, 0.42, 800.0);                        // tie the diatomics to water oxygens
+        bonds->addBond(b, 3*((k + 5) % nMol) + 1, 0.45, 300.0);
+    }
+    const int site = system.addParticle(0.0);
+    system.setVirtualSite(site, new TwoParticleAverageSite(firstFree, firstFree + 1, 0.25, 0.75));
+    positions.push_back(positions[firstFree]*0.25 + positions[firstFree + 1]*0.75);
+    velocities.push_back(Vec3());
+    bodyIndices.push_back(0);
+    bonds->addBond(site, 0, 0.5, 100.0);                            // felt by the two particles that define the site
+    system.addForce(bonds);
+    RigidBodyIntegrator integrator(0.001, bodyIndices);
+    integrator.setConstraintTolerance(1e-9);
+    Context context(system, integrator, platform);
+    context.setPositions(positions);
+    context.setVelocities(velocities);
+    ASSERT(integrator.getRigidBodySystem().getNumBodies() == nMol);
+    ASSERT(integrator.getRigidBodySystem().getNumFree() == 2*nPairs);
+    ASSERT(integrator.getRigidBodySystem().getNumDOF() == 2*nPairs - nPairs + 6*nMol);
+    State s0 = context.getState(State::Energy);
+    const double e0 = s0.getKineticEnergy() + s0.getPotentialEnergy();
+    double moved = 0.0;
+    for (int block = 0; block < 10; block++) {
+        integrator.step(50);
+        State s = context.getState(State::Positions | State::Velocities | State::Energy);
+        const vector<Vec3>& R = s.getPositions();
+        const vector<Vec3>& V = s.getVelocities();
+        for (int k = 0; k < nPairs; k++) {
+            Vec3 r = R[firstFree + 2*k] - R[firstFree + 2*k + 1], v = V[firstFree + 2*k] - V[firstFree + 2*k + 1];
+            ASSERT_TOL(bond, sqrt(r.dot(r)), 1e-8);
+            ASSERT(fabs(r.dot(v)) < 1e-8);
+        }
+        ASSERT_VEC(R[firstFree]*0.25 + R[firstFree + 1]*0.75, R[site], 1e-14);
+        Vec3 a = R[1] - R[0];
+        ASSERT_TOL(rOH, sqrt(a.dot(a)), 1e-11);
+        ASSERT_TOL(e0, s.getKineticEnergy() + s.getPotentialEnergy(), 2e-3);
+        Vec3 d = R[firstFree] - positions[firstFree];
+        moved = max(moved, sqrt(d.dot(d)));
+    }
+    ASSERT(moved > 1e-3);
+}
+
 static void testErrors(Platform& platform) {
     System system;
     for (int i = 0; i < 4; i++) system.addParticle(12.0);
@@ -156,6 +230,7 @@ int main() {
         testSingleBond(*platform);
         testRigidWaters(*platform, 0);
         testRigidWaters(*platform, 3);
+        testConstrainedFreeAtoms(*platform);
     }
     catch (const exception& e) {
         cout << "exception: " << e.what() << endl;

@@ -16,6 +16,8 @@ Part 2, exactly where ReferenceIntegrateRigidBodyStepKernel::execute calls calcF
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from ._lib import OpenMMException
@@ -131,6 +133,47 @@ class RigidBodySystem:
         return self._i._lastKE[0] + self._i._lastKE[1]
 
 
+class _DistanceConstraints:
+    """Host stand-in for OpenMM's ReferenceConstraints (absent here): simultaneous SHAKE / RATTLE sweeps over the
+    System's distance constraints until every one is within `tol` (relative), vectorised over constraints."""
+
+    def __init__(self, system):
+        cons = [system.getConstraintParameters(i) for i in range(system.getNumConstraints())]
+        self.a = np.array([k[0] for k in cons], dtype=np.int64)
+        self.b = np.array([k[1] for k in cons], dtype=np.int64)
+        self.d2 = np.array([k[2] for k in cons], dtype=np.float64) ** 2
+        mass = np.array([system.getParticleMass(i) for i in range(system.getNumParticles())], dtype=np.float64)
+        self.invm = np.where(mass == 0.0, 0.0, 1.0 / np.where(mass == 0.0, 1.0, mass))
+        # atoms shared between constraints: damp the simultaneous update by the number of constraints per atom
+        count = np.bincount(np.concatenate([self.a, self.b]), minlength=len(mass))
+        self.scale = 1.0 / np.maximum(count[self.a], count[self.b])
+
+    def apply(self, old, new, tol):
+        a, b, wa, wb = self.a, self.b, self.invm[self.a], self.invm[self.b]
+        r0 = old[a] - old[b]
+        for _ in range(1000):
+            r = new[a] - new[b]
+            diff = self.d2 - np.einsum("ij,ij->i", r, r)
+            if np.all(np.abs(diff) <= 2.0 * tol * self.d2):
+                return
+            g = self.scale * diff / (2.0 * (wa + wb) * np.einsum("ij,ij->i", r0, r))
+            np.add.at(new, a, (g * wa)[:, None] * r0)
+            np.add.at(new, b, -(g * wb)[:, None] * r0)
+        raise OpenMMException("constraint solver (SHAKE) did not converge")
+
+    def applyToVelocities(self, R, V, tol):
+        a, b, wa, wb = self.a, self.b, self.invm[self.a], self.invm[self.b]
+        r = R[a] - R[b]
+        for _ in range(1000):
+            rv = np.einsum("ij,ij->i", r, V[a] - V[b])
+            if np.all(np.abs(rv) <= tol * self.d2):
+                return
+            g = self.scale * rv / ((wa + wb) * self.d2)
+            np.add.at(V, a, -(g * wa)[:, None] * r)
+            np.add.at(V, b, (g * wb)[:, None] * r)
+        raise OpenMMException("constraint solver (RATTLE) did not converge")
+
+
 class RigidBodyIntegrator:
     """openmmapi/src/RigidBodyIntegrator.cpp, same names, argument meaning and error behaviour."""
 
@@ -211,16 +254,27 @@ class RigidBodyIntegrator:
         if self._context is None:
             raise OpenMMException("This Integrator is not bound to a context!")             # :97-98
         c = self._context
-        if c.getSystem().getNumConstraints() > 0:
-            raise OpenMMException("free-atom constraints are enforced by OpenMM's own constraint kernels, which are "
-                                  "outside this path; remove them or run inside OpenMM")
-        cb = None
+        cb = hp = hv = None
+        n = c._R.shape[0]
         if c.getSystem().getNumForces() > 0:
-            n = c._R.shape[0]
-
             def cb(Rp, Fp, count, user):          # host force evaluation between Part 1 and Part 2
                 c._computeForces()
-        self._dev.execute_host(self._stepSize, int(steps), c._R, c._V, c._F, forces=cb)
+        if c.getSystem().getNumConstraints() > 0:
+            # constraints among free atoms: the two calls the reference kernel makes around the force evaluation
+            # (ReferenceRigidBodyKernels.cpp:98-104), here through rbk_execute_host_hooks
+            solver = _DistanceConstraints(c.getSystem())
+            tol = self._constraintTolerance
+
+            def hp(oldp, newp, count, user):
+                old = np.ctypeslib.as_array(C.cast(oldp, C.POINTER(C.c_double)), shape=(n, 3))
+                solver.apply(old, c._R, tol)
+                return 1
+
+            def hv(Rp, Vp, count, user):
+                solver.applyToVelocities(c._R, c._V, tol)
+                return 1
+        self._dev.execute_host(self._stepSize, int(steps), c._R, c._V, c._F, forces=cb, constrain_positions=hp,
+                               constrain_velocities=hv)
         c._time += self._stepSize * int(steps)
         c._stepCount += int(steps)
 

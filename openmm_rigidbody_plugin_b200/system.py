@@ -173,6 +173,15 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_part2_openmm(self.h, float(dt), _ptr(posq), _ptr(posqCorrection), _ptr(velm), _ptr(force),
                                         int(paddedNumAtoms), int(precision), _stream(stream)))
 
+    def free_delta_openmm(self, dt, velm, force, paddedNumAtoms, precision, posDelta, stream=None):
+        """posDelta.xyz = (v + f invMass dt/2) dt for the free atoms (the hook before integration.applyConstraints)."""
+        check(self.lib.rbk_free_delta_openmm(self.h, float(dt), _ptr(velm), _ptr(force), int(paddedNumAtoms), int(precision),
+                                             _ptr(posDelta), _stream(stream)))
+
+    def part1_delta_openmm(self, dt, posq, posqCorrection, velm, force, paddedNumAtoms, precision, posDelta, stream=None):
+        check(self.lib.rbk_part1_delta_openmm(self.h, float(dt), _ptr(posq), _ptr(posqCorrection), _ptr(velm), _ptr(force),
+                                              int(paddedNumAtoms), int(precision), _ptr(posDelta), _stream(stream)))
+
     def kinetic_openmm(self, velm, precision, stream=None):
         out = np.zeros(2)
         check(self.lib.rbk_kinetic_openmm(self.h, _ptr(velm), int(precision), _d(out), _stream(stream)))
@@ -191,7 +200,15 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_download_bodies(self.h, *[_d(o[k]) for k in ("rcm", "pcm", "q", "pi", "force", "torque")], _stream(stream)))
         return o
 
-    def execute_host(self, dt, steps, R, V, F, forces=None, stream=None):
-        """R, V, F: host float64 buffers [N,3] (numpy arrays or pinned torch CPU tensors), updated in place."""
+    def execute_host(self, dt, steps, R, V, F, forces=None, stream=None, constrain_positions=None, constrain_velocities=None):
+        """R, V, F: host float64 buffers [N,3] (numpy arrays or pinned torch CPU tensors), updated in place.
+        constrain_positions(oldR_ptr, R_ptr, n, user) / constrain_velocities(R_ptr, V_ptr, n, user) are the free-atom
+        constraint / virtual-site hooks of rbk_execute_host_hooks; they return nonzero when they changed the array."""
         cb = _lib.FORCE_FN(forces) if forces is not None else C.cast(None, _lib.FORCE_FN)
-        check(self.lib.rbk_execute_host(self.h, float(dt), int(steps), _ptr(R), _ptr(V), _ptr(F), cb, None, _stream(stream)))
+        if constrain_positions is None and constrain_velocities is None:
+            check(self.lib.rbk_execute_host(self.h, float(dt), int(steps), _ptr(R), _ptr(V), _ptr(F), cb, None, _stream(stream)))
+            return
+        hp = _lib.HOOK_FN(constrain_positions) if constrain_positions is not None else C.cast(None, _lib.HOOK_FN)
+        hv = _lib.HOOK_FN(constrain_velocities) if constrain_velocities is not None else C.cast(None, _lib.HOOK_FN)
+        check(self.lib.rbk_execute_host_hooks(self.h, float(dt), int(steps), _ptr(R), _ptr(V), _ptr(F), cb, hp, hv, None,
+                                              _stream(stream)))

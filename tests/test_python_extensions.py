@@ -247,3 +247,30 @@ def test_state_data_reporter_columns_and_dof():
     assert v[5] == -100.25 and v[6] == 43.0 and v[7] == pytest.approx(43.0 - 100.25)
     assert v[8] == pytest.approx(2 * 43.0 / (dof * MOLAR_GAS_CONSTANT_R)) and v[9:] == [30.5, 12.5]
     assert rep.describeNextReport(sim)[0] == 5
+
+
+def test_host_constraint_solver_chain():
+    """SHAKE / RATTLE stand-in used by the Python Context for constraints among free atoms (coupled constraints)."""
+    import numpy as np
+    from openmm_rigidbody_plugin_b200.integrator import System, _DistanceConstraints
+    system = System()
+    for m in (12.0, 14.0, 16.0, 1.0):
+        system.addParticle(m)
+    system.addConstraint(0, 1, 0.11)
+    system.addConstraint(1, 2, 0.13)
+    solver = _DistanceConstraints(system)
+    old = np.array([[0.0, 0.0, 0.0], [0.11, 0.0, 0.0], [0.11, 0.13, 0.0], [1.0, 1.0, 1.0]])
+    rng = np.random.default_rng(1)
+    new = old + 0.004 * rng.normal(size=old.shape)
+    free = new[3].copy()
+    com = (np.array([12.0, 14.0, 16.0])[:, None] * new[:3]).sum(0)
+    solver.apply(old, new, 1e-12)
+    assert abs(np.linalg.norm(new[0] - new[1]) - 0.11) < 1e-12 and abs(np.linalg.norm(new[1] - new[2]) - 0.13) < 1e-12
+    assert np.allclose((np.array([12.0, 14.0, 16.0])[:, None] * new[:3]).sum(0), com, atol=1e-13)     # momentum-conserving
+    assert np.array_equal(new[3], free)
+    V = rng.normal(size=old.shape)
+    p = (np.array([12.0, 14.0, 16.0])[:, None] * V[:3]).sum(0)
+    solver.applyToVelocities(new, V, 1e-12)
+    for a, b in ((0, 1), (1, 2)):
+        assert abs(np.dot(new[a] - new[b], V[a] - V[b])) < 1e-12
+    assert np.allclose((np.array([12.0, 14.0, 16.0])[:, None] * V[:3]).sum(0), p, atol=1e-13)
