@@ -189,6 +189,35 @@ int rbk_part1_delta_openmm(rbk_system* sys, double dt, void* posq, void* posqCor
 int rbk_update_device_openmm(rbk_system* sys, void* posq, void* posqCorrection, void* velm, const long long* force,
                              int paddedNumAtoms, int precision, int geometry, int velocities, void* stream);
 
+/* ---- refined ("shadow") energy diagnostics ---------------------------------------------------
+ * RigidBodyIntegrator::setComputeRefinedEnergies / getRefinedKineticEnergies / getPotentialEnergyRefinement
+ * (openmmapi/include/RigidBodyIntegrator.h:94-137, RigidBodyKernels.h:92-98), which the reference implements only in
+ * its CUDA platform (COMPMOD paths of platforms/cuda/src/kernels/rigidbodyintegrator.cu:238-243,276-296,318-321,380-384,
+ * 433-469; host side CudaRigidBodyKernels.cpp:118-194,405-438,481-494).  Once enabled, every Part 1 is preceded by a
+ * virtual backward step and every Part 2 followed by a virtual forward step per body (two extra rotations per
+ * body-step), accumulating third-order estimates of dr/dt and dq/dt; rbk_part2_part1 then runs the two kernels.
+ *   RBK_REFINED_ALL    bodies and free atoms (flows without free-atom constraints);
+ *   RBK_REFINED_BODIES bodies only - the caller accumulates the free-atom term itself with rbk_free_delta_openmm
+ *                      / rbk_free_dot_openmm around its constraint solver, like CudaRigidBodyKernels.cpp:405-438
+ *                      (factors -1, 5, 2; see DESIGN.md on the reference's -1).
+ * rbk_refined_kinetic: out[0] = translational, out[1] = rotational refined kinetic energy (1/(6 dt) applied);
+ * rbk_potential_refinement: out[0] = -(dt^2/24) [sum F.F/M + tau.(tau/I) + sum_free f.f/m].  Both synchronise. */
+#define RBK_REFINED_OFF    0
+#define RBK_REFINED_ALL    1
+#define RBK_REFINED_BODIES 2
+int rbk_set_refined_energies(rbk_system* sys, int mode, void* stream);
+int rbk_refined_kinetic(rbk_system* sys, double dt, const double* vel, int layout, long long stride, double* out, void* stream);
+int rbk_potential_refinement(rbk_system* sys, double dt, const double* force, int layout, long long stride, double* out,
+                             void* stream);
+int rbk_refined_kinetic_openmm(rbk_system* sys, double dt, const void* velm, int precision, double* out, void* stream);
+int rbk_potential_refinement_openmm(rbk_system* sys, double dt, const long long* force, int paddedNumAtoms, double* out,
+                                    void* stream);
+/* freeAtomsDot (rigidbodyintegrator.cu:291-297): posDot = (restart ? 0 : posDot) + factor * posDelta.xyz for free atoms */
+int rbk_free_dot_openmm(rbk_system* sys, const void* posDelta, int precision, double factor, int restart, void* stream);
+/* host-buffer variants for the rbk_execute_host flow (V / F: host VEC3 arrays as returned by the last step) */
+int rbk_refined_kinetic_host(rbk_system* sys, double dt, const double* V, double* out, void* stream);
+int rbk_potential_refinement_host(rbk_system* sys, double dt, const double* F, double* out, void* stream);
+
 /* rbk_kinetic for callers that hold velocities on the HOST (Reference-platform data): copies V into the
  * handle's device mirror (only free atoms need it) and runs the same device reduction. */
 int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream);

@@ -43,6 +43,14 @@ SIGNATURES = {
     "rbk_kinetic_host": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.c_void_p]),
     "rbk_download_bodies": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_void_p]),
     "rbk_execute_host": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, FORCE_FN, C.c_void_p, C.c_void_p]),
+    "rbk_set_refined_energies": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "rbk_refined_kinetic": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_longlong, _dp, C.c_void_p]),
+    "rbk_potential_refinement": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_longlong, _dp, C.c_void_p]),
+    "rbk_refined_kinetic_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, _dp, C.c_void_p]),
+    "rbk_potential_refinement_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, _dp, C.c_void_p]),
+    "rbk_free_dot_openmm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
+    "rbk_refined_kinetic_host": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, _dp, C.c_void_p]),
+    "rbk_potential_refinement_host": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, _dp, C.c_void_p]),
     "rbk_execute_host_hooks": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, FORCE_FN, HOOK_FN, HOOK_FN,
                                          C.c_void_p, C.c_void_p]),
     "rbk_free_delta_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -62,6 +62,8 @@ struct rbk_system {
     unsigned* dKinCounter = nullptr;
     double* dKinOut = nullptr;
     double* hKinOut = nullptr;       // pinned
+    int refinedMode = RBK_REFINED_OFF;
+    rbk::RefinedState refined{nullptr, nullptr, nullptr};
     // device mirrors for rbk_execute_host
     double* mPos = nullptr;
     double* mVel = nullptr;
@@ -75,7 +77,7 @@ struct rbk_system {
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta);
         cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
-        cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
+        cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (h2dStream) cudaStreamDestroy(h2dStream);
         if (d2hStream) cudaStreamDestroy(d2hStream);
         for (cudaEvent_t e : {evStart, evForces, evPart1, evPositions}) if (e) cudaEventDestroy(e);
@@ -397,13 +399,89 @@ int rbk_set_atom_location(rbk_system* sys, const int* location, void* stream) {
     return setLocation(sys, location, (cudaStream_t) stream);
 }
 
+namespace {
+// Part 1 / Part 2 with the refined-energy passes around them when the diagnostics are on (rbk_refined.cu)
+cudaError_t stepPart1(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView f, const AtomView* delta, cudaStream_t st) {
+    if (sys->refinedMode != RBK_REFINED_OFF) {
+        cudaError_t e = rbk::launchRefinedBodies(sys->dev, sys->refined, dt, 1, st);
+        if (e == cudaSuccess && sys->refinedMode == RBK_REFINED_ALL && !delta)
+            e = rbk::launchRefinedFree(sys->dev, sys->refined, dt, 1, v, f, st);
+        if (e != cudaSuccess) return e;
+    }
+    return delta ? rbk::launchPart1Delta(sys->dev, dt, p, v, f, *delta, st) : rbk::launchPart1(sys->dev, dt, p, v, f, st);
+}
+
+cudaError_t stepPart2(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView f, cudaStream_t st) {
+    cudaError_t e = rbk::launchPart2(sys->dev, dt, p, v, f, st);
+    if (e != cudaSuccess || sys->refinedMode == RBK_REFINED_OFF) return e;
+    e = rbk::launchRefinedBodies(sys->dev, sys->refined, dt, 2, st);
+    if (e == cudaSuccess && sys->refinedMode == RBK_REFINED_ALL) e = rbk::launchRefinedFree(sys->dev, sys->refined, dt, 2, v, f, st);
+    return e;
+}
+
+int reduceOut(rbk_system* sys, double* out, int count, cudaStream_t st) {
+    RBK_CUDA(cudaMemcpyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < count; i++) out[i] = sys->hKinOut[i];
+    return RBK_OK;
+}
+
+int needRefined(rbk_system* sys, const char* who) {
+    if (!sys) return fail(RBK_EINVAL, std::string(who) + ": NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, std::string(who) + ": body system not uploaded");
+    if (sys->refinedMode == RBK_REFINED_OFF) return fail(RBK_ESTATE, std::string(who) + ": refined energies are not enabled");
+    return RBK_OK;
+}
+} // namespace
+
+int rbk_set_refined_energies(rbk_system* sys, int mode, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_set_refined_energies: NULL system");
+    if (mode != RBK_REFINED_OFF && mode != RBK_REFINED_ALL && mode != RBK_REFINED_BODIES)
+        return fail(RBK_EINVAL, "rbk_set_refined_energies: unknown mode");
+    if (mode != RBK_REFINED_OFF) {
+        if (!sys->allocated) return fail(RBK_ESTATE, "rbk_set_refined_energies: call rbk_upload first");
+        if (!sys->refined.rdot) {
+            RBK_CUDA(devAlloc(sys->refined.rdot, sys->dev.bodyStride*3));
+            RBK_CUDA(devAlloc(sys->refined.qdot, sys->dev.bodyStride*4));
+            RBK_CUDA(devAlloc(sys->refined.posDot, sys->dev.freeStride*3));
+        }
+        cudaStream_t st = (cudaStream_t) stream;
+        RBK_CUDA(cudaMemsetAsync(sys->refined.rdot, 0, sys->dev.bodyStride*3*sizeof(double), st));
+        RBK_CUDA(cudaMemsetAsync(sys->refined.qdot, 0, sys->dev.bodyStride*4*sizeof(double), st));
+        RBK_CUDA(cudaMemsetAsync(sys->refined.posDot, 0, sys->dev.freeStride*3*sizeof(double), st));
+    }
+    sys->refinedMode = mode;
+    return RBK_OK;
+}
+
+int rbk_refined_kinetic(rbk_system* sys, double dt, const double* vel, int layout, long long stride, double* out, void* stream) {
+    if (int rc = needRefined(sys, "rbk_refined_kinetic")) return rc;
+    if (!out) return fail(RBK_EINVAL, "rbk_refined_kinetic: NULL argument");
+    AtomView v;
+    if (viewOf(vel, layout, stride, v)) return RBK_EINVAL;
+    cudaStream_t st = (cudaStream_t) stream;
+    RBK_CUDA(rbk::launchRefinedKinetic(sys->dev, sys->refined, dt, v, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
+    return reduceOut(sys, out, 2, st);
+}
+
+int rbk_potential_refinement(rbk_system* sys, double dt, const double* force, int layout, long long stride, double* out,
+                             void* stream) {
+    if (int rc = needRefined(sys, "rbk_potential_refinement")) return rc;
+    if (!out) return fail(RBK_EINVAL, "rbk_potential_refinement: NULL argument");
+    AtomView f;
+    if (viewOf(force, layout, stride, f)) return RBK_EINVAL;
+    cudaStream_t st = (cudaStream_t) stream;
+    RBK_CUDA(rbk::launchPotentialRefinement(sys->dev, sys->refined, dt, f, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
+    return reduceOut(sys, out, 1, st);
+}
+
 int rbk_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force, int layout, long long stride,
               void* stream) {
     if (!sys) return fail(RBK_EINVAL, "rbk_part1: NULL system");
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part1: body system not uploaded");
     AtomView p, v, f;
     if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
-    RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    RBK_CUDA(stepPart1(sys, dt, p, v, f, nullptr, (cudaStream_t) stream));
     return RBK_OK;
 }
 
@@ -413,7 +491,7 @@ int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const 
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2: body system not uploaded");
     AtomView p, v, f;
     if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
-    RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    RBK_CUDA(stepPart2(sys, dt, p, v, f, (cudaStream_t) stream));
     return RBK_OK;
 }
 
@@ -423,6 +501,11 @@ int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const 
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2_part1: body system not uploaded");
     AtomView p, v, f;
     if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
+    if (sys->refinedMode != RBK_REFINED_OFF) {          // the diagnostics sit between the two halves: no one-pass kernel
+        RBK_CUDA(stepPart2(sys, dt, p, v, f, (cudaStream_t) stream));
+        RBK_CUDA(stepPart1(sys, dt, p, v, f, nullptr, (cudaStream_t) stream));
+        return RBK_OK;
+    }
     RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, (cudaStream_t) stream));
     return RBK_OK;
 }
@@ -465,7 +548,7 @@ int rbk_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part1_openmm: body system not uploaded");
     AtomView p, v, f;
     if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
-    RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    RBK_CUDA(stepPart1(sys, dt, p, v, f, nullptr, (cudaStream_t) stream));
     return RBK_OK;
 }
 
@@ -475,7 +558,7 @@ int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2_openmm: body system not uploaded");
     AtomView p, v, f;
     if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
-    RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    RBK_CUDA(stepPart2(sys, dt, p, v, f, (cudaStream_t) stream));
     return RBK_OK;
 }
 
@@ -498,7 +581,7 @@ int rbk_part1_delta_openmm(rbk_system* sys, double dt, void* posq, void* posqCor
     AtomView p, v, f;
     if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
     const AtomView d{(double*) posDelta, 0, 0, v.fmt, nullptr};
-    RBK_CUDA(rbk::launchPart1Delta(sys->dev, dt, p, v, f, d, (cudaStream_t) stream));
+    RBK_CUDA(stepPart1(sys, dt, p, v, f, &d, (cudaStream_t) stream));
     return RBK_OK;
 }
 
@@ -521,6 +604,54 @@ int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double*
     out[0] = sys->hKinOut[0];
     out[1] = sys->hKinOut[1];
     return RBK_OK;
+}
+
+int rbk_free_dot_openmm(rbk_system* sys, const void* posDelta, int precision, double factor, int restart, void* stream) {
+    if (int rc = needRefined(sys, "rbk_free_dot_openmm")) return rc;
+    if (!posDelta) return fail(RBK_EINVAL, "rbk_free_dot_openmm: NULL argument");
+    const AtomView d{(double*) posDelta, 0, 0, precision == RBK_OPENMM_SINGLE ? rbk::FMT_REAL4_F32 : rbk::FMT_REAL4_F64, nullptr};
+    RBK_CUDA(rbk::launchFreeDot(sys->dev, sys->refined, d, factor, restart != 0, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_refined_kinetic_openmm(rbk_system* sys, double dt, const void* velm, int precision, double* out, void* stream) {
+    if (int rc = needRefined(sys, "rbk_refined_kinetic_openmm")) return rc;
+    if (!out) return fail(RBK_EINVAL, "rbk_refined_kinetic_openmm: NULL argument");
+    cudaStream_t st = (cudaStream_t) stream;
+    const AtomView v{(double*) velm, 0, 0, precision == RBK_OPENMM_SINGLE ? rbk::FMT_REAL4_F32 : rbk::FMT_REAL4_F64, nullptr};
+    RBK_CUDA(rbk::launchRefinedKinetic(sys->dev, sys->refined, dt, v, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
+    return reduceOut(sys, out, 2, st);
+}
+
+int rbk_potential_refinement_openmm(rbk_system* sys, double dt, const long long* force, int paddedNumAtoms, double* out,
+                                    void* stream) {
+    if (int rc = needRefined(sys, "rbk_potential_refinement_openmm")) return rc;
+    if (!out || paddedNumAtoms <= 0) return fail(RBK_EINVAL, "rbk_potential_refinement_openmm: bad argument");
+    cudaStream_t st = (cudaStream_t) stream;
+    const AtomView f{(double*) force, 1, (long long) paddedNumAtoms, rbk::FMT_FORCE_FIXED, nullptr};
+    RBK_CUDA(rbk::launchPotentialRefinement(sys->dev, sys->refined, dt, f, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
+    return reduceOut(sys, out, 1, st);
+}
+
+// host-buffer variants: after rbk_execute_host the handle's device mirrors hold the current V and F
+int rbk_refined_kinetic_host(rbk_system* sys, double dt, const double* V, double* out, void* stream) {
+    if (int rc = needRefined(sys, "rbk_refined_kinetic_host")) return rc;
+    if (!V || !out) return fail(RBK_EINVAL, "rbk_refined_kinetic_host: NULL argument");
+    if (!sys->mVel) return fail(RBK_ESTATE, "rbk_refined_kinetic_host: no step has been taken with rbk_execute_host");
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
+    if (sys->host.numFree > 0) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+    return rbk_refined_kinetic(sys, dt, sys->mVel, RBK_LAYOUT_VEC3, 0, out, stream);
+}
+
+int rbk_potential_refinement_host(rbk_system* sys, double dt, const double* F, double* out, void* stream) {
+    if (int rc = needRefined(sys, "rbk_potential_refinement_host")) return rc;
+    if (!F || !out) return fail(RBK_EINVAL, "rbk_potential_refinement_host: NULL argument");
+    if (!sys->mForce) return fail(RBK_ESTATE, "rbk_potential_refinement_host: no step has been taken with rbk_execute_host");
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
+    if (sys->host.numFree > 0) RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
+    return rbk_potential_refinement(sys, dt, sys->mForce, RBK_LAYOUT_VEC3, 0, out, stream);
 }
 
 int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream) {
@@ -609,7 +740,7 @@ int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, dou
                 sys->oldPositions.resize((size_t) sys->host.numAtoms*3);
                 std::memcpy(sys->oldPositions.data(), R, bytes);
             }
-            RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, fOld, st));
+            RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
             RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
             RBK_CUDA(cudaStreamSynchronize(st));
             if (constrainPositions && constrainPositions(sys->oldPositions.data(), R, sys->host.numAtoms, user))
@@ -624,14 +755,14 @@ int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, dou
             RBK_CUDA(cudaStreamWaitEvent(sys->h2dStream, sys->evStart, 0));
             RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, sys->h2dStream));
             RBK_CUDA(cudaEventRecord(sys->evForces, sys->h2dStream));
-            RBK_CUDA(rbk::launchPart1(sys->dev, dt, p, v, fOld, st));
+            RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
             RBK_CUDA(cudaEventRecord(sys->evPart1, st));
             RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
             RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
             RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
             RBK_CUDA(cudaStreamWaitEvent(st, sys->evForces, 0));
         }
-        RBK_CUDA(rbk::launchPart2(sys->dev, dt, p, v, fNew, st));
+        RBK_CUDA(stepPart2(sys, dt, p, v, fNew, st));
         RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
         if (!forces && !constrainPositions) RBK_CUDA(cudaStreamWaitEvent(st, sys->evPositions, 0));     // R is complete when `st` is
         if (constrainVelocities) {

@@ -71,6 +71,21 @@ constexpr int kKineticBlocks = 592;    // 148 SMs x 4
 // GPU-side body build (rbk_build.cu): geometry and/or dynamics of every body from the caller's atom arrays.
 cudaError_t launchBuild(const DeviceSystem& S, const double* atomMass, AtomView pos, AtomView vel, AtomView force,
                         double* dxyz, bool geometry, bool velocities, int* dofSum, cudaStream_t st);
+// Refined ("shadow") energy diagnostics (rbk_refined.cu): rdot = 3 planes, qdot = 4 planes of bodyStride doubles,
+// posDot = 3 planes of freeStride doubles.  phase 1 = before Part 1, phase 2 = after Part 2.
+struct RefinedState {
+    double* rdot;
+    double* qdot;
+    double* posDot;
+};
+cudaError_t launchRefinedBodies(const DeviceSystem& S, const RefinedState& X, double dt, int phase, cudaStream_t st);
+cudaError_t launchRefinedFree(const DeviceSystem& S, const RefinedState& X, double dt, int phase, AtomView vel, AtomView force,
+                              cudaStream_t st);
+cudaError_t launchFreeDot(const DeviceSystem& S, const RefinedState& X, AtomView delta, double factor, bool restart, cudaStream_t st);
+cudaError_t launchRefinedKinetic(const DeviceSystem& S, const RefinedState& X, double dt, AtomView vel, double* partial,
+                                 unsigned* counter, double* out, cudaStream_t st);
+cudaError_t launchPotentialRefinement(const DeviceSystem& S, const RefinedState& X, double dt, AtomView force, double* partial,
+                                      unsigned* counter, double* out, cudaStream_t st);
 int part1LaunchesPerStep(const DeviceSystem& S);   // 1 (fused) or 2 (rotation kernel + atom kernel)
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out, cudaStream_t st);
 

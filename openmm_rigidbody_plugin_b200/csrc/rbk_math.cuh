@@ -44,6 +44,7 @@ RBK_HD double dot(d3 a, d3 b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
 RBK_HD d3 cross(d3 a, d3 b) { return {a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x}; }
 RBK_HD d4 operator+(d4 a, d4 b) { return {a.w + b.w, a.x + b.x, a.y + b.y, a.z + b.z}; }
 RBK_HD d4 operator*(d4 a, double s) { return {a.w*s, a.x*s, a.y*s, a.z*s}; }
+RBK_HD d4 operator-(d4 a, d4 b) { return {a.w - b.w, a.x - b.x, a.y - b.y, a.z - b.z}; }
 RBK_HD double dot(d4 a, d4 b) { return a.w*b.w + a.x*b.x + a.y*b.y + a.z*b.z; }
 
 // B(q)v = q (x) (0,v),  C(q)v = (0,v) (x) q  and their transposes

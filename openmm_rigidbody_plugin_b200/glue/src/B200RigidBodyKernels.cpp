@@ -26,6 +26,7 @@ void B200IntegrateRigidBodyStepKernel::initialize(ContextImpl& contextRef, const
         virtualSites = virtualSites || sys.isVirtualSite(i);
     }
     oldPos.resize(numAtoms);
+    refined = integrator.getComputeRefinedEnergies();
     // the reference calls the constraint solver whenever there are free atoms (a no-op without constraints) and
     // ReferenceVirtualSites::computePositions always; the hooks are only installed when they have work to do
     velocityHook = sys.getNumConstraints() != 0;
@@ -36,6 +37,7 @@ void B200IntegrateRigidBodyStepKernel::uploadBodySystem(RigidBodySystem& bodySys
     bodies = &bodySystem;
     system = bodySystem.getHandle();
     check(rbk_upload(system, NULL));
+    if (refined) check(rbk_set_refined_energies(system, RBK_REFINED_ALL, NULL));
 }
 
 void B200IntegrateRigidBodyStepKernel::evaluateForces(const double*, double*, int, void* self) {
@@ -92,10 +94,20 @@ vector<double> B200IntegrateRigidBodyStepKernel::getKineticEnergies(const RigidB
     return ke;
 }
 
-// Refined ("shadow") energies are diagnostics of the reference's CUDA platform only; like its Reference platform
-// (ReferenceRigidBodyKernels.cpp:123-132) this implementation reports the plain kinetic energies and no refinement.
+// Refined ("shadow") energies: the diagnostics the reference has on its CUDA platform only
+// (CudaRigidBodyKernels.cpp:469-494); its Reference platform returns the plain energies / 0
+// (ReferenceRigidBodyKernels.cpp:123-132), which is also what is returned here until they are switched on
+// with RigidBodyIntegrator::setComputeRefinedEnergies(true) and a step has been taken.
 vector<double> B200IntegrateRigidBodyStepKernel::getRefinedKineticEnergies(const RigidBodyIntegrator& integrator) {
-    return getKineticEnergies(integrator);
+    if (!integrator.getComputeRefinedEnergies() || system == NULL || data.stepCount == 0) return getKineticEnergies(integrator);
+    vector<double> ke(2, 0.0);
+    check(rbk_refined_kinetic_host(system, integrator.getStepSize(), &(*data.velocities)[0][0], ke.data(), NULL));
+    return ke;
 }
 
-double B200IntegrateRigidBodyStepKernel::getPotentialEnergyRefinement(const RigidBodyIntegrator&) { return 0.0; }
+double B200IntegrateRigidBodyStepKernel::getPotentialEnergyRefinement(const RigidBodyIntegrator& integrator) {
+    if (!integrator.getComputeRefinedEnergies() || system == NULL || data.stepCount == 0) return 0.0;
+    double out[2] = {0.0, 0.0};
+    check(rbk_potential_refinement_host(system, integrator.getStepSize(), &(*data.forces)[0][0], out, NULL));
+    return out[0];
+}

@@ -13,7 +13,7 @@ class B200IntegrateRigidBodyStepKernel : public IntegrateRigidBodyStepKernel {
 public:
     B200IntegrateRigidBodyStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::ReferencePlatform::PlatformData& data)
         : IntegrateRigidBodyStepKernel(name, platform), data(data), system(NULL), context(NULL), bodies(NULL), tolerance(1e-5),
-          positionHook(false), velocityHook(false) {}
+          positionHook(false), velocityHook(false), refined(false) {}
     void initialize(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator);
     void uploadBodySystem(RigidBodySystem& bodySystem);
     void execute(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator);
@@ -32,7 +32,7 @@ private:
     std::vector<double> invMass;
     std::vector<OpenMM::Vec3> oldPos;
     double tolerance;
-    bool positionHook, velocityHook;
+    bool positionHook, velocityHook, refined;
 };
 
 } // namespace RigidBodyPlugin

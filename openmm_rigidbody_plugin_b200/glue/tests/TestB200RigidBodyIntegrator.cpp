@@ -186,6 +186,51 @@ static void testConstrainedFreeAtoms(Platform& platform) {
     ASSERT(moved > 1e-3);
 }
 
+// setComputeRefinedEnergies(true): the refined kinetic energies + potential refinement (the reference's CUDA-only
+// diagnostics, CudaRigidBodyKernels.cpp:469-494) make a total energy that fluctuates far less than the plain one.
+static void testRefinedEnergies(Platform& platform) {
+    const int nMol = 27;
+    const double rOH = 0.09572, half = 0.5*104.52*M_PI/180.0;
+    System system;
+    vector<int> bodyIndices;
+    vector<Vec3> positions, velocities;
+    unsigned seed = 4321u;
+    auto rnd = [&]() { seed = seed*1664525u + 1013904223u; return (seed >> 8)/16777216.0 - 0.5; };
+    for (int m = 0; m < nMol; m++) {
+        Vec3 c(0.35*(m % 3), 0.35*((m/3) % 3), 0.35*(m/9));
+        system.addParticle(15.99943); system.addParticle(1.007947); system.addParticle(1.007947);
+        positions.push_back(c);
+        positions.push_back(c + Vec3(rOH*sin(half), 0, rOH*cos(half)));
+        positions.push_back(c + Vec3(-rOH*sin(half), 0, rOH*cos(half)));
+        for (int k = 0; k < 3; k++) { bodyIndices.push_back(m + 1); velocities.push_back(Vec3(rnd(), rnd(), rnd())); }
+    }
+    HarmonicBondForce* bonds = new HarmonicBondForce();
+    for (int m = 0; m + 1 < nMol; m++) bonds->addBond(3*m, 3*(m + 1), 0.33, 2000.0);
+    for (int m = 0; m + 3 < nMol; m++) bonds->addBond(3*m + 1, 3*(m + 3) + 2, 0.36, 500.0);
+    system.addForce(bonds);
+    RigidBodyIntegrator integrator(0.001, bodyIndices);
+    integrator.setComputeRefinedEnergies(true);
+    Context context(system, integrator, platform);
+    context.setPositions(positions);
+    context.setVelocities(velocities);
+    vector<double> k0 = integrator.getKineticEnergies(), r0 = integrator.getRefinedKineticEnergies();
+    ASSERT(k0[0] == r0[0] && k0[1] == r0[1]);                      // nothing accumulated before the first step
+    ASSERT(integrator.getPotentialEnergyRefinement() == 0.0);
+    const int n = 200;
+    double sp = 0, sp2 = 0, sr = 0, sr2 = 0;
+    for (int i = 0; i < n; i++) {
+        integrator.step(1);
+        State s = context.getState(State::Energy);
+        vector<double> refined = integrator.getRefinedKineticEnergies();
+        const double plain = s.getKineticEnergy() + s.getPotentialEnergy();
+        const double shadow = refined[0] + refined[1] + s.getPotentialEnergy() + integrator.getPotentialEnergyRefinement();
+        sp += plain; sp2 += plain*plain; sr += shadow; sr2 += shadow*shadow;
+    }
+    const double stdPlain = sqrt(sp2/n - (sp/n)*(sp/n)), stdRefined = sqrt(fabs(sr2/n - (sr/n)*(sr/n)));
+    ASSERT(integrator.getPotentialEnergyRefinement() < 0.0);
+    ASSERT(stdRefined < 0.3*stdPlain);
+}
+
 static void testErrors(Platform& platform) {
     System system;
     for (int i = 0; i < 4; i++) system.addParticle(12.0);
@@ -231,6 +276,7 @@ int main() {
         testRigidWaters(*platform, 0);
         testRigidWaters(*platform, 3);
         testConstrainedFreeAtoms(*platform);
+        testRefinedEnergies(*platform);
     }
     catch (const exception& e) {
         cout << "exception: " << e.what() << endl;

@@ -248,6 +248,8 @@ class RigidBodyIntegrator:
         else:
             self._dev.update(V=c._V, geometry=False, velocities=True)
         self._dev.upload()
+        if self._computeRefinedEnergies:
+            self._dev.set_refined_energies(1)
 
     # -- stepping ---------------------------------------------------------------------------------
     def step(self, steps):
@@ -284,11 +286,18 @@ class RigidBodyIntegrator:
         return [self._lastKE[0], self._lastKE[1]]
 
     def getRefinedKineticEnergies(self):
-        # the Reference platform returns the plain kinetic energies (ReferenceRigidBodyKernels.cpp:123-128)
-        return self.getKineticEnergies()
+        # CudaRigidBodyKernels.cpp:469-476: the refined estimate when it was switched on, else the plain energies
+        # (the reference's Reference platform always returns the plain ones, ReferenceRigidBodyKernels.cpp:123-128)
+        if not self._computeRefinedEnergies or self._context._stepCount == 0:
+            return self.getKineticEnergies()
+        ke = self._dev.refined_kinetic_host(self._stepSize, self._context._V)
+        return [float(ke[0]), float(ke[1])]
 
     def getPotentialEnergyRefinement(self):
-        return 0.0                                   # ReferenceRigidBodyKernels.cpp:130-132
+        # CudaRigidBodyKernels.cpp:481-494: -(dt^2/24) sum of squared forces over masses / torques over inertia
+        if not self._computeRefinedEnergies or self._context._stepCount == 0:
+            return 0.0
+        return self._dev.potential_refinement_host(self._stepSize, self._context._F)
 
     def _computeKineticEnergy(self):
         return sum(self.getKineticEnergies())

@@ -187,6 +187,46 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_kinetic_openmm(self.h, _ptr(velm), int(precision), _d(out), _stream(stream)))
         return out
 
+    # ---- refined ("shadow") energy diagnostics (rbk_refined.cu)
+    def set_refined_energies(self, mode=1, stream=None):
+        """0 = off, 1 = bodies and free atoms, 2 = bodies only (caller drives free_dot_openmm)."""
+        check(self.lib.rbk_set_refined_energies(self.h, int(mode), _stream(stream)))
+
+    def refined_kinetic(self, dt, vel, layout=None, stream=None):
+        lay, stride = _layout(vel, layout)
+        out = np.zeros(2)
+        check(self.lib.rbk_refined_kinetic(self.h, float(dt), _ptr(vel), lay, stride, _d(out), _stream(stream)))
+        return out
+
+    def potential_refinement(self, dt, force, layout=None, stream=None):
+        lay, stride = _layout(force, layout)
+        out = np.zeros(2)
+        check(self.lib.rbk_potential_refinement(self.h, float(dt), _ptr(force), lay, stride, _d(out), _stream(stream)))
+        return float(out[0])
+
+    def refined_kinetic_openmm(self, dt, velm, precision, stream=None):
+        out = np.zeros(2)
+        check(self.lib.rbk_refined_kinetic_openmm(self.h, float(dt), _ptr(velm), int(precision), _d(out), _stream(stream)))
+        return out
+
+    def potential_refinement_openmm(self, dt, force, paddedNumAtoms, stream=None):
+        out = np.zeros(2)
+        check(self.lib.rbk_potential_refinement_openmm(self.h, float(dt), _ptr(force), int(paddedNumAtoms), _d(out), _stream(stream)))
+        return float(out[0])
+
+    def free_dot_openmm(self, posDelta, precision, factor, restart, stream=None):
+        check(self.lib.rbk_free_dot_openmm(self.h, _ptr(posDelta), int(precision), float(factor), int(bool(restart)), _stream(stream)))
+
+    def refined_kinetic_host(self, dt, V, stream=None):
+        out = np.zeros(2)
+        check(self.lib.rbk_refined_kinetic_host(self.h, float(dt), _ptr(V), _d(out), _stream(stream)))
+        return out
+
+    def potential_refinement_host(self, dt, F, stream=None):
+        out = np.zeros(2)
+        check(self.lib.rbk_potential_refinement_host(self.h, float(dt), _ptr(F), _d(out), _stream(stream)))
+        return float(out[0])
+
     def kinetic_host(self, V, stream=None):
         """Kinetic energies for host-resident velocities [N,3] (numpy or pinned torch CPU tensor)."""
         out = np.zeros(2)

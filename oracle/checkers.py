@@ -81,6 +81,12 @@ def _lib(kind: str):
         lib.orc_exact_rotation.restype = None
         lib.orc_nosquish_rotation.argtypes = [C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]
         lib.orc_nosquish_rotation.restype = None
+        lib.orc_set_refined.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_set_refined.restype = None
+        lib.orc_refined_kinetic.argtypes = [C.c_void_p, C.c_double, _dp]
+        lib.orc_refined_kinetic.restype = None
+        lib.orc_potential_refinement.argtypes = [C.c_void_p, C.c_double]
+        lib.orc_potential_refinement.restype = C.c_double
     _libs[kind] = lib
     return lib
 
@@ -146,6 +152,18 @@ class CpuStepper:
         R, V, F = (np.zeros((self.n, 3)) for _ in range(3))
         self._f("get_state")(self.h, _d(R), _d(V), _d(F))
         return R, V, F
+
+    # refined ("shadow") energies: oracle only - the reference has them on its CUDA platform alone
+    def set_refined(self, flag=True):
+        self.lib.orc_set_refined(self.h, int(bool(flag)))
+
+    def refined_kinetic(self, dt):
+        out = np.zeros(2)
+        self.lib.orc_refined_kinetic(self.h, float(dt), _d(out))
+        return out
+
+    def potential_refinement(self, dt):
+        return float(self.lib.orc_potential_refinement(self.h, float(dt)))
 
     def set_tether(self, k, E, charges, x0):
         E = np.ascontiguousarray(E, dtype=np.float64)

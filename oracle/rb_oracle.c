@@ -6,7 +6,9 @@
  * (oracle/_ref) it agrees to the last bit or very nearly so.  Citations are file:line relative
  * to /root/reference.
  *
- * Parity status: PINNED against oracle/_ref and tests/golden (tests/test_oracle.py).
+ * Parity status: PINNED against oracle/_ref and tests/golden (tests/test_oracle.py) for everything the reference's
+ * Reference platform computes (mapping, body build, Part 1, Part 2, kinetic energies).  The last section (refined
+ * energies, a CUDA-platform-only diagnostic of the reference) is PARITY UNPINNED - see its header.
  */
 #include "rb_oracle.h"
 #include <float.h>
@@ -501,6 +503,8 @@ typedef struct {
     double *R, *V, *F;
     int tether, alternate;
     double k, E[3], *charge, *x0;
+    int refined;                       /* refined-energy bookkeeping (see the last section of this file) */
+    double *rdot, *qdot, *posDot;
 } sys_t;
 
 /* cleanBodyIndices  RigidBodySystem.cpp:28-49 : distinct positive labels -> 1..nB in ascending label order */
@@ -580,6 +584,7 @@ void orc_destroy(void* h) {
     free(s->bodyIndex); free(s->atomIndex); free(s->mass); free(s->isVirtual); free(s->body);
     free(s->d); free(s->delta); free(s->freeInvMass); free(s->savedPos);
     free(s->R); free(s->V); free(s->F); free(s->charge); free(s->x0);
+    free(s->rdot); free(s->qdot); free(s->posDot);
     free(s);
 }
 
@@ -768,9 +773,13 @@ void orc_update(void* h, int geometry, int velocities) {
 }
 
 /* integratePart1  RigidBodySystem.cpp:170-187 */
+static void refined_part1(sys_t* s, double dt);
+static void refined_part2(sys_t* s, double dt);
+
 void orc_part1(void* h, double dt) {
     sys_t* s = (sys_t*) h;
     double halfDt = 0.5*dt;
+    if (s->refined) refined_part1(s, dt);
     for (int k = 0; k < s->numFree; k++) {
         int i = s->atomIndex[k];
         for (int c = 0; c < 3; c++) {
@@ -827,6 +836,7 @@ void orc_part2(void* h, double dt) {
         b->twoKt = dot3(b->pcm, vcm);
         b->twoKr = dot3(L, w);
     }
+    if (s->refined) refined_part2(s, dt);
 }
 
 /* ReferenceIntegrateRigidBodyStepKernel::execute without constraints / virtual sites
@@ -885,4 +895,136 @@ void orc_get_bodies(void* h, int* N, int* dof, int* loc, double* mass, double* I
 void orc_get_body_fixed(void* h, double* d) {
     sys_t* s = (sys_t*) h;
     memcpy(d, s->d, sizeof(double)*3*(size_t) s->numBodyAtoms);
+}
+
+/* -------------------------------------------------------------------------------------------
+ * Refined ("shadow") energies.  PARITY UNPINNED: the reference implements these diagnostics only in
+ * its CUDA platform (the COMPMOD paths of platforms/cuda/src/kernels/rigidbodyintegrator.cu:238-243,
+ * 276-296,318-321,380-384,433-469 driven by platforms/cuda/src/CudaRigidBodyKernels.cpp:118-194,
+ * 405-438,481-494), which needs OpenMM + a GPU and cannot run here; its Reference platform returns
+ * the plain energies.  This section restates those CUDA paths in fp64 on top of the Reference-
+ * platform step above (momentum p instead of the CUDA code's velocity v = p/m), for systems without
+ * constraints (the CUDA flow interleaves integration.applyConstraints with the free-atom passes).
+ *   bodies : rdot = 1/2 (r(-1) - 6 r0 + 3 r1 + 2 r(2)), qdot likewise (projected orthogonal to q), where
+ *            r(-1), q(-1) and r(2), q(2) are VIRTUAL backward / forward steps from the ends of the step;
+ *   free   : posDot = -(r(-1) - r0) + 5 (r1 - r0) + 2 (r(2) - r1)   [factors -1, 5, 2 as in the reference:
+ *            CudaRigidBodyKernels.cpp:412-413,430-436]
+ * KE_t = [sum_free posDot.v m/2 + sum_b rdot.p] / (6 dt), KE_r = sum_b qdot.pi / (6 dt),
+ * dU = -(dt^2/24) [sum_free f.f/m + sum_b (F.F/M + tau_b.(tau_b/I))].
+ * ----------------------------------------------------------------------------------------- */
+void orc_set_refined(void* h, int flag) {
+    sys_t* s = (sys_t*) h;
+    s->refined = flag != 0;
+    if (s->refined && !s->rdot) {
+        s->rdot = (double*) calloc((size_t) 3*(s->numBodies + 1), sizeof(double));
+        s->qdot = (double*) calloc((size_t) 4*(s->numBodies + 1), sizeof(double));
+        s->posDot = (double*) calloc((size_t) 3*(s->numFree + 1), sizeof(double));
+    }
+}
+
+/* Reference quirk, reproduced: the backward displacement enters posDot with factor -1
+ * (rdotFactor = -1, CudaRigidBodyKernels.cpp:412) where the derivative stencil r(-1) - 6 r0 + 3 r1 + 2 r(2) needs +1,
+ * so the reference's refined KE of FREE atoms is 4/3 of the kinetic energy for uniform motion (bodies are right).
+ * Building with -DORC_FREE_BACK_FACTOR=1.0 gives the consistent stencil (used once to confirm the diagnosis:
+ * the refined total energy of tethered free atoms then fluctuates 200x less than the plain one). */
+#ifndef ORC_FREE_BACK_FACTOR
+#define ORC_FREE_BACK_FACTOR -1.0
+#endif
+
+/* virtualRotation  rigidbodyintegrator.cu:238-243 */
+static void virtual_rotation(const sys_t* s, const body_t* b, double dt, double* q) {
+    double pi[4];
+    for (int c = 0; c < 4; c++) { q[c] = b->q[c]; pi[c] = b->pi[c] + b->torque[c]*dt; }
+    if (s->mode == 0) exact_rotation(dt, b->I, b->invI, q, pi);
+    else orc_nosquish_rotation(dt, s->mode, b->dof, b->invI, q, pi);
+}
+
+/* start of the step, before the first half kick: rigidbodyintegrator.cu:318-321; free atoms
+ * CudaRigidBodyKernels.cpp:406-417 (freeAtomsDelta with -dt, freeAtomsDot restart factor -1) and
+ * :428-430 (factor 5 on the displacement of this step, which without constraints is (v + dv) dt) */
+static void refined_part1(sys_t* s, double dt) {
+    double halfDt = 0.5*dt;
+    for (int k = 0; k < s->numFree; k++) {
+        int i = s->atomIndex[k];
+        for (int c = 0; c < 3; c++) {
+            double v = s->V[3*i+c], f = s->F[3*i+c], w = s->freeInvMass[k];
+            double back = (v + f*w*(0.5*-dt))*-dt;
+            double fwd = (v + f*w*halfDt)*dt;
+            s->posDot[3*k+c] = back*ORC_FREE_BACK_FACTOR;
+            s->posDot[3*k+c] += fwd*5.0;
+        }
+    }
+    for (int ib = 0; ib < s->numBodies; ib++) {
+        body_t* b = &s->body[ib];
+        double qv[4];
+        for (int c = 0; c < 3; c++) {
+            double dv = b->force[c]*(b->invMass*halfDt), v = b->pcm[c]*b->invMass;
+            s->rdot[3*ib+c] = b->rcm[c]*2.5 + (v - dv)*halfDt;
+        }
+        virtual_rotation(s, b, -dt, qv);
+        for (int c = 0; c < 4; c++) s->qdot[4*ib+c] = qv[c]*0.5 - b->q[c]*3.0;
+    }
+}
+
+/* end of the step, after the second half kick: rigidbodyintegrator.cu:380-384; free atoms
+ * CudaRigidBodyKernels.cpp:431-436 (freeAtomsDelta with the new velocities and forces, factor 2) */
+static void refined_part2(sys_t* s, double dt) {
+    double halfDt = 0.5*dt;
+    for (int k = 0; k < s->numFree; k++) {
+        int i = s->atomIndex[k];
+        for (int c = 0; c < 3; c++) {
+            double fwd = (s->V[3*i+c] + s->F[3*i+c]*s->freeInvMass[k]*halfDt)*dt;
+            s->posDot[3*k+c] += fwd*2.0;
+        }
+    }
+    for (int ib = 0; ib < s->numBodies; ib++) {
+        body_t* b = &s->body[ib];
+        double qv[4], proj;
+        for (int c = 0; c < 3; c++) {
+            double dv = b->force[c]*(b->invMass*halfDt), v = b->pcm[c]*b->invMass;
+            s->rdot[3*ib+c] = b->rcm[c]*2.5 + (v + dv)*dt - s->rdot[3*ib+c];
+        }
+        virtual_rotation(s, b, dt, qv);
+        for (int c = 0; c < 4; c++) s->qdot[4*ib+c] += b->q[c]*1.5 + qv[c];
+        proj = dot4(s->qdot + 4*ib, b->q);
+        for (int c = 0; c < 4; c++) s->qdot[4*ib+c] -= b->q[c]*proj;
+    }
+}
+
+/* refinedKineticEnergies  rigidbodyintegrator.cu:437-448 + the host sums and the 1/(6 dt) factor of
+ * CudaRigidBodyKernels.cpp:139-163 */
+void orc_refined_kinetic(void* h, double dt, double* out) {
+    sys_t* s = (sys_t*) h;
+    double kt = 0.0, kr = 0.0;
+    for (int k = 0; k < s->numFree; k++) {
+        const double* v = s->V + 3*s->atomIndex[k];
+        kt += dot3(s->posDot + 3*k, v)*(0.5/s->freeInvMass[k]);
+    }
+    for (int ib = 0; ib < s->numBodies; ib++) {
+        const body_t* b = &s->body[ib];
+        double v[3];
+        for (int c = 0; c < 3; c++) v[c] = b->pcm[c]*b->invMass;
+        kt += dot3(s->rdot + 3*ib, v)/b->invMass;
+        kr += dot4(s->qdot + 4*ib, b->pi);
+    }
+    out[0] = kt*(1.0/(6.0*dt));
+    out[1] = kr*(1.0/(6.0*dt));
+}
+
+/* potentialEnergyRefinement  rigidbodyintegrator.cu:454-469, CudaRigidBodyKernels.cpp:169-194,481-494 */
+double orc_potential_refinement(void* h, double dt) {
+    sys_t* s = (sys_t*) h;
+    double u = 0.0;
+    for (int k = 0; k < s->numFree; k++) {
+        const double* f = s->F + 3*s->atomIndex[k];
+        u += dot3(f, f)*s->freeInvMass[k];
+    }
+    for (int ib = 0; ib < s->numBodies; ib++) {
+        const body_t* b = &s->body[ib];
+        double tau[3], t2[3];
+        quatBt(b->q, b->torque, tau);
+        for (int c = 0; c < 3; c++) t2[c] = tau[c]*b->invI[c];
+        u += dot3(b->force, b->force)*b->invMass + dot3(t2, tau);
+    }
+    return -u*dt*dt/24.0;
 }

@@ -38,6 +38,11 @@ void orc_get_bodies(void* h, int* N, int* dof, int* loc, double* mass, double* I
                     double* pcm, double* q, double* pi, double* force, double* torque, double* twoK);
 void orc_get_body_fixed(void* h, double* d);
 
+/* Refined ("shadow") energies of the reference's CUDA platform, restated in fp64 (PARITY UNPINNED, see rb_oracle.c). */
+void   orc_set_refined(void* h, int flag);
+void   orc_refined_kinetic(void* h, double dt, double* out2);
+double orc_potential_refinement(void* h, double dt);
+
 /* Scalar special functions, exported for known-answer tests against mpmath/scipy. */
 void   orc_jacobi(double u, double m, double* sn, double* cn, double* dn);
 double orc_carlson_rc(double x, double y);
