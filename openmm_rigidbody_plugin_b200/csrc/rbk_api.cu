@@ -52,6 +52,7 @@ struct rbk_system {
     int* dLoc = nullptr;
     int4* dTileMeta = nullptr;
     int4* dBodyTileMeta = nullptr;
+    int4* dWarpTileMeta = nullptr;
     int* dAtomLoc = nullptr;
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
@@ -75,7 +76,7 @@ struct rbk_system {
     std::vector<double> staging, oldPositions;
 
     ~rbk_system() {
-        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta);
+        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta);
         cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (h2dStream) cudaStreamDestroy(h2dStream);
@@ -138,6 +139,15 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.splitPart1 = nB > 0 && (long long) nA > (long long) rbk::kSplitAtomsPerBody*nB;
     d.fusable = !d.splitPart1;
     for (const int4& t : meta) if (t.w > rbk::kTileAtoms) d.fusable = 0;
+    // one-warp tiles for the step-fused kernel: bodies of <= 4 atoms (water) - then the atom tiles above are exactly the
+    // consecutive groups of 128 bodies and these are their 32-body quarters (localBody & 31 = index in the quarter)
+    std::vector<int4> warpMeta;
+    if (d.fusable && nB > 0 && maxSize <= rbk::kWarpTileAtoms/32)
+        for (int b = 0; b < nB; b += 32) {
+            const int n = std::min(32, nB - b);
+            warpMeta.push_back(make_int4(b, n, loc[b], loc[b + n] - loc[b]));
+        }
+    d.numWarpTiles = (int) warpMeta.size();
     d.numFreeBlocks = (nF + rbk::kFreePerBlock - 1)/rbk::kFreePerBlock;
     d.rotationMode = h.rotationMode;
     d.maxBodySize = maxSize;
@@ -156,6 +166,9 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     if (bodyMeta.empty()) bodyMeta.push_back(make_int4(0, 0, 0, 0));
     RBK_CUDA(devAlloc(sys->dTileMeta, meta.size()));
     RBK_CUDA(devAlloc(sys->dBodyTileMeta, bodyMeta.size()));
+    if (warpMeta.empty()) warpMeta.push_back(make_int4(0, 0, 0, 0));
+    RBK_CUDA(devAlloc(sys->dWarpTileMeta, warpMeta.size()));
+    RBK_CUDA(cudaMemcpyAsync(sys->dWarpTileMeta, warpMeta.data(), warpMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaMemcpyAsync(sys->dTileMeta, meta.data(), meta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaMemcpyAsync(sys->dBodyTileMeta, bodyMeta.data(), bodyMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
@@ -184,6 +197,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.loc = sys->dLoc;
     d.tileMeta = sys->dTileMeta;
     d.bodyTileMeta = sys->dBodyTileMeta;
+    d.warpTileMeta = sys->dWarpTileMeta;
     d.atomLoc = nullptr;
     d.freeInvMass = sys->dFreeInvMass;
     d.savedPos = sys->dSavedPos;

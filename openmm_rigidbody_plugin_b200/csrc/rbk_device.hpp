@@ -27,12 +27,14 @@ constexpr int kTileAtoms = 512;
 constexpr int kLargeBodyTileAtoms = 768;   // atom-tile cap when bodies are large (see rbk_api.cu)
 constexpr int kMaxTileAtoms = 8192;
 constexpr int kSplitAtomsPerBody = 8;  // mean body size above which part 1 runs as rotation kernel + atom kernel
+constexpr int kWarpTileAtoms = 128;    // atom capacity of the one-warp tiles (32 bodies of <= 4 atoms) of the step-fused kernel
 constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
 
 struct DeviceSystem {
     int numBodies, numFree, numBodyAtoms, numTiles, numBodyTiles, numFreeBlocks;
     int rotationMode, maxBodySize, numSMs, splitPart1;
     int fusable;                 // every atom tile fits the shared-memory staging of the step-fused kernel
+    int numWarpTiles;            // > 0: bodies have <= 4 atoms and the step-fused kernel runs one warp per 32-body tile
     size_t bodyStride, atomStride, freeStride;
     double* state;
     const double* dxyz;
@@ -40,6 +42,7 @@ struct DeviceSystem {
     const int* loc;
     const int4* tileMeta;        // per atom tile: first body, #bodies, first body-atom, #atoms
     const int4* bodyTileMeta;    // per body tile, same fields
+    const int4* warpTileMeta;    // per one-warp tile (subdivision of the atom tiles), same fields
     const int* atomLoc;
     const double* freeInvMass;
     double* savedPos;

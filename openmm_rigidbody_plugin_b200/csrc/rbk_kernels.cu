@@ -339,19 +339,24 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
 constexpr int kFPlanes = 18;                        // r3 p3 q4 pi4 invm invI3
 constexpr int kSmallBody = 8;                       // bodies up to this size are reduced by their own thread
 
+// BODIES = threads per CTA = bodies per tile, ATOMS = atom capacity of a tile.  Two shapes are instantiated:
+// <128, 512> (four warps share a tile) and <32, 128> (ONE warp per CTA, for bodies of <= 4 atoms such as water: no
+// CTA-wide barrier ever waits for a slower warp, eight independent CTAs per SM).
+template <int BODIES, int ATOMS>
 struct FusedStage {
-    double body[kFPlanes][kBlock];
-    double f[3*kTileAtoms];                         // atom forces as xyzxyz..., later the arms delta = A^T(q) d
-    double d[3][kTileAtoms];
-    int loc[kBlock + 4];
-    unsigned char localBody[kTileAtoms + 32];
+    double body[kFPlanes][BODIES];
+    double f[3*ATOMS];                              // atom forces as xyzxyz..., later the arms delta = A^T(q) d
+    double d[3][ATOMS];
+    int loc[BODIES + 4];
+    unsigned char localBody[ATOMS + 32];
 };
+template <int BODIES, int ATOMS>
 struct FusedSmem {
-    FusedStage stage[2];
+    FusedStage<BODIES, ATOMS> stage[2];
     unsigned long long bar[2];                      // one mbarrier per stage (bulk-copy completion)
-    double acc[6][kBlock];
-    double head[kWarps][6];
-    int headKey[kWarps];
+    double acc[6][BODIES];
+    double head[BODIES/32][6];
+    int headKey[BODIES/32];
     int4 meta[3];
 };
 
@@ -384,15 +389,18 @@ __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.as
 // stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
 __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k == 14 ? (int) PL_INVM : (int) PL_INVI + (k - 15)); }
 
-template <bool EXACT, bool SMALL, bool NATIVE>
-__global__ void __launch_bounds__(kBlock, 2)
+template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS>
+__global__ void __launch_bounds__(BODIES, 256/BODIES)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smemRaw);
+    typedef FusedStage<BODIES, ATOMS> Stage;
+    FusedSmem<BODIES, ATOMS>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS>*>(smemRaw);
+    constexpr int kBlock = BODIES, kWarps = BODIES/32;          // shadow the file-level constants inside this kernel
+    const int4* const tileMeta = BODIES == 32 ? S.warpTileMeta : S.tileMeta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
     const size_t ld = S.bodyStride, as = S.atomStride;
-    const int numTiles = S.numTiles;
+    const int numTiles = BODIES == 32 ? S.numWarpTiles : S.numTiles;
 
     // A tile can arrive by bulk copies when every segment is 16-byte aligned and a multiple of 16 bytes long and the
     // tile's forces are one contiguous Vec3 range (water tiles always are); otherwise per-thread cp.async.
@@ -402,7 +410,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                ((S.numFree + m.z) & 1) == 0;
     };
     auto request = [&](int4 m, int st) {
-        FusedStage& T = sm.stage[st];
+        Stage& T = sm.stage[st];
         const int lbFirst = m.z & ~15;                         // 16-byte granules of the byte array
         const unsigned lbBytes = (unsigned) (((m.z + m.w - lbFirst) + 15) & ~15);
         if (bulkOK(m)) {
@@ -449,8 +457,8 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     const int tile0 = blockIdx.x;
     if (tile0 < numTiles) {
         if (tid == 0) {
-            sm.meta[0] = S.tileMeta[tile0];
-            if (tile0 + G < numTiles) sm.meta[1] = S.tileMeta[tile0 + G];
+            sm.meta[0] = tileMeta[tile0];
+            if (tile0 + G < numTiles) sm.meta[1] = tileMeta[tile0 + G];
             mbarInit(&sm.bar[0], 1);
             mbarInit(&sm.bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -460,7 +468,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         cpCommit();
         for (int tile = tile0, it = 0; tile < numTiles; tile += G, it++) {
             const int4 m = sm.meta[it % 3];
-            FusedStage& T = sm.stage[it & 1];
+            Stage& T = sm.stage[it & 1];
             if (!SMALL) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
@@ -470,7 +478,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             __syncthreads();
             if (tile + G < numTiles) {
                 request(sm.meta[(it + 1) % 3], (it & 1) ^ 1);
-                if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], S.tileMeta + tile + 2*G);
+                if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + tile + 2*G);
             }
             cpCommit();
 
@@ -581,7 +589,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
 
             // ---- D: thread per atom: velocities at the end of this step, positions of the next
             for (int j = tid; j < m.w; j += kBlock) {
-                const int k = T.localBody[j + shift];
+                const int k = T.localBody[j + shift] & (BODIES - 1);      // index inside the 128-body atom tile -> this tile
                 const d3 delta = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
                 const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
                 const d3 om = {sm.acc[3][k], sm.acc[4][k], sm.acc[5][k]};
@@ -732,21 +740,39 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     return cudaGetLastError();
 }
 
-template <bool EXACT, bool SMALL>
-cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+template <bool EXACT, bool SMALL, int BODIES, int ATOMS>
+cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    typedef FusedSmem<BODIES, ATOMS> Smem;
     static bool configured[kMaxDevices] = {};
     int device = 0;
     cudaGetDevice(&device);
     if (device < 0 || device >= kMaxDevices || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(FusedSmem));
+        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
     launchFree<3, true>(S, dt, pos, vel, force, st);
-    const int resident = S.numSMs*2;
-    if (S.numTiles > 0)
-        part2Part1Kernel<EXACT, SMALL, true><<<S.numTiles < resident ? S.numTiles : resident, kBlock, sizeof(FusedSmem), st>>>(S, dt, pos, vel, force);
+    const int tiles = BODIES == 32 ? S.numWarpTiles : S.numTiles;
+    static int perSM[kMaxDevices] = {};                        // persistent CTAs: one full wave, whatever fits
+    int blocks = device >= 0 && device < kMaxDevices ? perSM[device] : 0;
+    if (blocks == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS>, BODIES, sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        if (blocks < 1) blocks = 1;
+        if (device >= 0 && device < kMaxDevices) perSM[device] = blocks;
+    }
+    const int resident = S.numSMs*blocks;
+    if (tiles > 0)
+        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
+}
+
+template <bool EXACT, bool SMALL>
+cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    // one warp per CTA pays off where a tile's phases are long and uneven (exact rotation: 0.1445 -> 0.137 ms at 1 M
+    // waters); measured slower for NO-SQUISH (0.177 -> 0.197 ms), which keeps the four-warp tiles
+    if (EXACT && SMALL && S.numWarpTiles > 0) return launchFusedShape<EXACT, true, 32, kWarpTileAtoms>(S, dt, pos, vel, force, st);
+    return launchFusedShape<EXACT, SMALL, kBlock, kTileAtoms>(S, dt, pos, vel, force, st);
 }
 
 bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
