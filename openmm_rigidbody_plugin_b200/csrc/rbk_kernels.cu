@@ -350,9 +350,9 @@ struct FusedStage {
     int loc[BODIES + 4];
     unsigned char localBody[ATOMS + 32];
 };
-template <int BODIES, int ATOMS>
+template <int BODIES, int ATOMS, int STAGES>
 struct FusedSmem {
-    FusedStage<BODIES, ATOMS> stage[2];
+    FusedStage<BODIES, ATOMS> stage[STAGES];
     unsigned long long bar[2];                      // one mbarrier per stage (bulk-copy completion)
     double acc[6][BODIES];
     double head[BODIES/32][6];
@@ -389,12 +389,15 @@ __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.as
 // stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
 __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k == 14 ? (int) PL_INVM : (int) PL_INVI + (k - 15)); }
 
-template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS>
-__global__ void __launch_bounds__(BODIES, 256/BODIES)
+// STAGES = 2: the next tile is staged while the current one is processed (exact rotation: registers allow two CTAs of
+// 128 threads per SM anyway).  STAGES = 1: the next tile is requested when the current one is finished and the
+// smaller footprint lets four CTAs share an SM, which hide each other's load latency (NO-SQUISH: 112 registers).
+template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES>
+__global__ void __launch_bounds__(BODIES, (STAGES == 2 ? 256 : 512)/BODIES)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     typedef FusedStage<BODIES, ATOMS> Stage;
-    FusedSmem<BODIES, ATOMS>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS>*>(smemRaw);
+    FusedSmem<BODIES, ATOMS, STAGES>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS, STAGES>*>(smemRaw);
     constexpr int kBlock = BODIES, kWarps = BODIES/32;          // shadow the file-level constants inside this kernel
     const int4* const tileMeta = BODIES == 32 ? S.warpTileMeta : S.tileMeta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -468,19 +471,22 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         cpCommit();
         for (int tile = tile0, it = 0; tile < numTiles; tile += G, it++) {
             const int4 m = sm.meta[it % 3];
-            Stage& T = sm.stage[it & 1];
+            const int cur = STAGES == 2 ? (it & 1) : 0;
+            Stage& T = sm.stage[cur];
             if (!SMALL) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
                 if (tid < kWarps*6) sm.head[tid/6][tid%6] = 0.0;
             }
-            arrived(m, it & 1);                                // this tile (+ the next tile's descriptor) landed
+            arrived(m, cur);                                   // this tile (+ the next tile's descriptor) landed
             __syncthreads();
-            if (tile + G < numTiles) {
-                request(sm.meta[(it + 1) % 3], (it & 1) ^ 1);
-                if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + tile + 2*G);
+            if (STAGES == 2) {
+                if (tile + G < numTiles) {
+                    request(sm.meta[(it + 1) % 3], cur ^ 1);
+                    if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + tile + 2*G);
+                }
+                cpCommit();
             }
-            cpCommit();
 
             // ---- B: forces and torques -> per-body sums.
             // SMALL (every body has <= kSmallBody atoms, e.g. water): each body's thread sums its own atoms straight
@@ -601,6 +607,13 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 storeAtom<NATIVE>(pos, slot, atomPosition(r, q, d));
             }
             __syncthreads();
+            if (STAGES == 1) {                                 // the single stage is free again: request the next tile
+                if (tile + G < numTiles) {
+                    request(sm.meta[(it + 1) % 3], 0);
+                    if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + tile + 2*G);
+                }
+                cpCommit();
+            }
         }
         cpWait<0>();
     }
@@ -740,14 +753,14 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     return cudaGetLastError();
 }
 
-template <bool EXACT, bool SMALL, int BODIES, int ATOMS>
+template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES>
 cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    typedef FusedSmem<BODIES, ATOMS> Smem;
+    typedef FusedSmem<BODIES, ATOMS, STAGES> Smem;
     static bool configured[kMaxDevices] = {};
     int device = 0;
     cudaGetDevice(&device);
     if (device < 0 || device >= kMaxDevices || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
+        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
@@ -756,23 +769,24 @@ cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, Ato
     static int perSM[kMaxDevices] = {};                        // persistent CTAs: one full wave, whatever fits
     int blocks = device >= 0 && device < kMaxDevices ? perSM[device] : 0;
     if (blocks == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS>, BODIES, sizeof(Smem));
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES>, BODIES, sizeof(Smem));
         if (e != cudaSuccess) return e;
         if (blocks < 1) blocks = 1;
         if (device >= 0 && device < kMaxDevices) perSM[device] = blocks;
     }
     const int resident = S.numSMs*blocks;
     if (tiles > 0)
-        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(S, dt, pos, vel, force);
+        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 
 template <bool EXACT, bool SMALL>
 cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    // one warp per CTA pays off where a tile's phases are long and uneven (exact rotation: 0.1445 -> 0.137 ms at 1 M
-    // waters); measured slower for NO-SQUISH (0.177 -> 0.197 ms), which keeps the four-warp tiles
-    if (EXACT && SMALL && S.numWarpTiles > 0) return launchFusedShape<EXACT, true, 32, kWarpTileAtoms>(S, dt, pos, vel, force, st);
-    return launchFusedShape<EXACT, SMALL, kBlock, kTileAtoms>(S, dt, pos, vel, force, st);
+    // One warp per CTA pays off where a tile's phases are long and uneven (exact rotation: 0.1445 -> 0.137 ms at 1 M
+    // waters).  NO-SQUISH (112 registers) instead runs four single-stage CTAs of four warps per SM: mode 10
+    // 0.177 -> 0.150 ms, mode 3 0.110 ms; one-warp single-stage CTAs measured 0.147 / 0.118 ms, so the four-warp shape stays.
+    if (EXACT && SMALL && S.numWarpTiles > 0) return launchFusedShape<EXACT, true, 32, kWarpTileAtoms, 2>(S, dt, pos, vel, force, st);
+    return launchFusedShape<EXACT, SMALL, kBlock, kTileAtoms, EXACT ? 2 : 1>(S, dt, pos, vel, force, st);
 }
 
 bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
