@@ -223,6 +223,8 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log lines ("NCCL version ..." at NCCL_DEBUG=VERSION/WARN) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # one independent replica per GPU, distinct seed per replica (BASELINE.json: replicas only)
