@@ -392,7 +392,9 @@ __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k 
 // STAGES = 2: the next tile is staged while the current one is processed (exact rotation: registers allow two CTAs of
 // 128 threads per SM anyway).  STAGES = 1: the next tile is requested when the current one is finished and the
 // smaller footprint lets four CTAs share an SM, which hide each other's load latency (NO-SQUISH: 112 registers).
-template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES>
+// P1ONLY: Part 1 alone through the same pipeline (the step's opening launch and callers that evaluate forces between
+// two launches): no forces are staged, the stored F and tau planes take their place in the stage, Part 2's phases drop out.
+template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY>
 __global__ void __launch_bounds__(BODIES, (STAGES == 2 ? 256 : 512)/BODIES)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -409,8 +411,8 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     // tile's forces are one contiguous Vec3 range (water tiles always are); otherwise per-thread cp.async.
     const bool contiguousForces = S.atomLoc == nullptr && force.sa == 3 && force.sc == 1 && (reinterpret_cast<size_t>(force.p) & 15) == 0;
     auto bulkOK = [&](int4 m) {
-        return contiguousForces && (m.x & 3) == 0 && (m.y & 3) == 0 && (m.z & 1) == 0 && (m.w & 1) == 0 &&
-               ((S.numFree + m.z) & 1) == 0;
+        return (P1ONLY || (contiguousForces && ((S.numFree + m.z) & 1) == 0)) && (m.x & 3) == 0 && (m.y & 3) == 0 &&
+               (m.z & 1) == 0 && (m.w & 1) == 0;
     };
     auto request = [&](int4 m, int st) {
         Stage& T = sm.stage[st];
@@ -419,14 +421,18 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         if (bulkOK(m)) {
             if (tid == 0) {
                 fenceProxyAsync();                             // earlier generic-proxy writes to this stage are ordered first
-                mbarExpectTx(&sm.bar[st], (unsigned) (kFPlanes*8*m.y + 4*m.y + 48*m.w) + lbBytes);
+                mbarExpectTx(&sm.bar[st], (unsigned) ((kFPlanes + (P1ONLY ? 6 : 0))*8*m.y + 4*m.y + (P1ONLY ? 24 : 48)*m.w) + lbBytes);
                 const double* g = S.state + (size_t) m.x;
 #pragma unroll
                 for (int k = 0; k < kFPlanes; k++) bulkCopy(&T.body[k][0], g + fusedGlobalPlane(k)*ld, 8u*m.y, &sm.bar[st]);
                 bulkCopy(&T.loc[0], S.loc + m.x, 4u*m.y, &sm.bar[st]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) bulkCopy(&T.d[c][0], S.dxyz + (size_t) m.z + c*as, 8u*m.w, &sm.bar[st]);
-                bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
+                if (P1ONLY) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) bulkCopy(&T.f[k*BODIES], g + ((int) PL_F + k)*ld, 8u*m.y, &sm.bar[st]);
+                }
+                else bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
                 bulkCopy(&T.localBody[0], S.localBody + lbFirst, lbBytes, &sm.bar[st]);
             }
             return;
@@ -436,16 +442,22 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
 #pragma unroll
             for (int k = 0; k < kFPlanes; k++) cpAsync8(&T.body[k][tid], g + fusedGlobalPlane(k)*ld);
             cpAsync4(&T.loc[tid], S.loc + m.x + tid);
+            if (P1ONLY) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) cpAsync8(&T.f[k*BODIES + tid], g + ((int) PL_F + k)*ld);
+            }
         }
         for (int j = tid; j < m.w; j += kBlock) {
             const double* g = S.dxyz + (size_t) (m.z + j);
             cpAsync8(&T.d[0][j], g);
             cpAsync8(&T.d[1][j], g + as);
             cpAsync8(&T.d[2][j], g + 2*as);
-            const double* fp = force.p + atomSlot(S, S.numFree + m.z + j)*force.sa;
-            cpAsync8(&T.f[3*j], fp);
-            cpAsync8(&T.f[3*j + 1], fp + force.sc);
-            cpAsync8(&T.f[3*j + 2], fp + 2*force.sc);
+            if (!P1ONLY) {
+                const double* fp = force.p + atomSlot(S, S.numFree + m.z + j)*force.sa;
+                cpAsync8(&T.f[3*j], fp);
+                cpAsync8(&T.f[3*j + 1], fp + force.sc);
+                cpAsync8(&T.f[3*j + 2], fp + 2*force.sc);
+            }
         }
         for (unsigned w = tid; 4*w < lbBytes; w += kBlock)
             cpAsync4(&T.localBody[4*w], S.localBody + lbFirst + 4*w);
@@ -473,7 +485,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             const int4 m = sm.meta[it % 3];
             const int cur = STAGES == 2 ? (it & 1) : 0;
             Stage& T = sm.stage[cur];
-            if (!SMALL) {
+            if (!SMALL && !P1ONLY) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
                 if (tid < kWarps*6) sm.head[tid/6][tid%6] = 0.0;
@@ -493,7 +505,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             // from the staged forces/coordinates in phase C - sequential order, no shuffles, no extra barrier.
             // Otherwise: thread per atom + warp-shuffle segmented scan, exactly as in part2Kernel.
             const int shift = m.z & 15;
-            if (!SMALL) {
+            if (!SMALL && !P1ONLY) {
                 const int per = ((m.w + kBlock - 1)/kBlock)*32;
                 const int wBeg = warp*per, wEnd = min(wBeg + per, m.w);        // tile-local atom indices
                 int firstKey = -1;
@@ -549,7 +561,11 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 d3 p = {B[3][tid], B[4][tid], B[5][tid]};
                 d4 q = {B[6][tid], B[7][tid], B[8][tid], B[9][tid]};
                 d3 F = {0.0, 0.0, 0.0}, tau = {0.0, 0.0, 0.0};
-                if (SMALL) {
+                if (P1ONLY) {
+                    F = {T.f[tid], T.f[BODIES + tid], T.f[2*BODIES + tid]};
+                    tau = {T.f[3*BODIES + tid], T.f[4*BODIES + tid], T.f[5*BODIES + tid]};
+                }
+                else if (SMALL) {
                     const int j0 = T.loc[tid] - m.z, j1 = (tid + 1 < m.y ? T.loc[tid + 1] - m.z : m.w);
                     for (int j = j0; j < j1; j++) {
                         const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
@@ -576,18 +592,22 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 d4 pi = {B[10][tid], B[11][tid], B[12][tid], B[13][tid]};
                 const double invm = B[14][tid];
                 const d3 invI = {B[15][tid], B[16][tid], B[17][tid]};
-                d3 vcm, om;
-                bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
-                sm.acc[0][tid] = vcm.x; sm.acc[1][tid] = vcm.y; sm.acc[2][tid] = vcm.z;
-                sm.acc[3][tid] = om.x; sm.acc[4][tid] = om.y; sm.acc[5][tid] = om.z;
+                if (!P1ONLY) {
+                    d3 vcm, om;
+                    bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
+                    sm.acc[0][tid] = vcm.x; sm.acc[1][tid] = vcm.y; sm.acc[2][tid] = vcm.z;
+                    sm.acc[3][tid] = om.x; sm.acc[4][tid] = om.y; sm.acc[5][tid] = om.z;
+                }
                 bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
                 double* s = S.state + (size_t) (m.x + tid);
                 storePlane3(s + PL_R*ld, ld, r);
                 storePlane3(s + PL_P*ld, ld, p);
                 storePlane4(s + PL_Q*ld, ld, q);
                 storePlane4(s + PL_PI*ld, ld, pi);
-                storePlane3(s + PL_F*ld, ld, F);
-                storePlane3(s + PL_TAU*ld, ld, tau);
+                if (!P1ONLY) {
+                    storePlane3(s + PL_F*ld, ld, F);
+                    storePlane3(s + PL_TAU*ld, ld, tau);
+                }
                 B[0][tid] = r.x; B[1][tid] = r.y; B[2][tid] = r.z;
                 B[6][tid] = q.w; B[7][tid] = q.x; B[8][tid] = q.y; B[9][tid] = q.z;
             }
@@ -596,11 +616,13 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             // ---- D: thread per atom: velocities at the end of this step, positions of the next
             for (int j = tid; j < m.w; j += kBlock) {
                 const int k = T.localBody[j + shift] & (BODIES - 1);      // index inside the 128-body atom tile -> this tile
-                const d3 delta = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
-                const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
-                const d3 om = {sm.acc[3][k], sm.acc[4][k], sm.acc[5][k]};
                 const long long slot = atomSlot(S, S.numFree + m.z + j);
-                storeAtom<NATIVE>(vel, slot, atomVelocity(vcm, om, delta));
+                if (!P1ONLY) {
+                    const d3 delta = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
+                    const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
+                    const d3 om = {sm.acc[3][k], sm.acc[4][k], sm.acc[5][k]};
+                    storeAtom<NATIVE>(vel, slot, atomVelocity(vcm, om, delta));
+                }
                 const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
                 const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
                 const d3 r = {B[0][k], B[1][k], B[2][k]};
@@ -753,30 +775,31 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     return cudaGetLastError();
 }
 
-template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES>
-cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES, bool P1ONLY>
+cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
+                             bool freeAtoms = true) {
     typedef FusedSmem<BODIES, ATOMS, STAGES> Smem;
     static bool configured[kMaxDevices] = {};
     int device = 0;
     cudaGetDevice(&device);
     if (device < 0 || device >= kMaxDevices || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
+        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
-    launchFree<3, true>(S, dt, pos, vel, force, st);
+    if (freeAtoms) launchFree<P1ONLY ? 1 : 3, true>(S, dt, pos, vel, force, st);
     const int tiles = BODIES == 32 ? S.numWarpTiles : S.numTiles;
     static int perSM[kMaxDevices] = {};                        // persistent CTAs: one full wave, whatever fits
     int blocks = device >= 0 && device < kMaxDevices ? perSM[device] : 0;
     if (blocks == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES>, BODIES, sizeof(Smem));
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY>, BODIES, sizeof(Smem));
         if (e != cudaSuccess) return e;
         if (blocks < 1) blocks = 1;
         if (device >= 0 && device < kMaxDevices) perSM[device] = blocks;
     }
     const int resident = S.numSMs*blocks;
     if (tiles > 0)
-        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(S, dt, pos, vel, force);
+        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 
@@ -785,8 +808,8 @@ cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView
     // One warp per CTA pays off where a tile's phases are long and uneven (exact rotation: 0.1445 -> 0.137 ms at 1 M
     // waters).  NO-SQUISH (112 registers) instead runs four single-stage CTAs of four warps per SM: mode 10
     // 0.177 -> 0.150 ms, mode 3 0.110 ms; one-warp single-stage CTAs measured 0.147 / 0.118 ms, so the four-warp shape stays.
-    if (EXACT && SMALL && S.numWarpTiles > 0) return launchFusedShape<EXACT, true, 32, kWarpTileAtoms, 2>(S, dt, pos, vel, force, st);
-    return launchFusedShape<EXACT, SMALL, kBlock, kTileAtoms, EXACT ? 2 : 1>(S, dt, pos, vel, force, st);
+    if (EXACT && SMALL && S.numWarpTiles > 0) return launchFusedShape<EXACT, true, 32, kWarpTileAtoms, 2, false>(S, dt, pos, vel, force, st);
+    return launchFusedShape<EXACT, SMALL, kBlock, kTileAtoms, EXACT ? 2 : 1, false>(S, dt, pos, vel, force, st);
 }
 
 bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
@@ -796,6 +819,9 @@ bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
 template <bool NATIVE>
 cudaError_t launchPart1Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st) {
     const bool exact = S.rotationMode == 0, fused = !S.splitPart1;
+    // exact rotation on water-like bodies, fp64 arrays: Part 1 alone through the TMA-staged one-warp-tile pipeline
+    if (NATIVE && exact && S.numWarpTiles > 0)
+        return launchFusedShape<true, true, 32, kWarpTileAtoms, 2, true>(S, dt, pos, vel, force, st, freeAtoms);
     if (exact) return fused ? launchPart1Variant<true, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<true, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st);
     return fused ? launchPart1Variant<false, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<false, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st);
 }
