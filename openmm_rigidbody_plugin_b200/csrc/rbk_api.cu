@@ -4,6 +4,8 @@
 #include "rbk_device.hpp"
 #include "rbk_host.hpp"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -53,6 +55,7 @@ struct rbk_system {
     int4* dTileMeta = nullptr;
     int4* dBodyTileMeta = nullptr;
     int4* dWarpTileMeta = nullptr;
+    rbk::TileMaps tileMaps{};        // TMA descriptors of the one-warp-tile pipeline (valid when dev.tileMaps != NULL)
     int* dAtomLoc = nullptr;
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
@@ -87,6 +90,38 @@ struct rbk_system {
 };
 
 namespace {
+
+// TMA descriptors (CUtensorMap) for the one-warp-tile pipeline: the state planes as a 2-D fp64 tensor [NPLANES][bodyStride]
+// with boxes of 32 bodies x 18 / 24 planes, the body-frame coordinates as [3][atomStride] with a box of kWarpTileAtoms x 3.
+// cuTensorMapEncodeTiled is a driver-API call; it is looked up at run time so that librbk does not link libcuda.
+// Returns false when the driver does not offer it - the kernels then use 1-D bulk copies.
+bool encodeTileMaps(rbk_system* sys) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static_assert(sizeof(rbk::TensorMapBlob) == sizeof(CUtensorMap), "TensorMapBlob must match CUtensorMap");
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult found = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &found) != cudaSuccess ||
+        found != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    const EncodeFn encode = (EncodeFn) fn;
+    const DeviceSystem& d = sys->dev;
+    const cuuint32_t ones[2] = {1, 1};
+    auto make = [&](rbk::TensorMapBlob& out, void* base, size_t inner, int rows, int boxInner, int boxRows) {
+        const cuuint64_t dims[2] = {(cuuint64_t) inner, (cuuint64_t) rows};
+        const cuuint64_t strides[1] = {(cuuint64_t) inner*sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t) boxInner, (cuuint32_t) boxRows};
+        return encode(reinterpret_cast<CUtensorMap*>(&out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, ones,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    return make(sys->tileMaps.state18, sys->dState, d.bodyStride, rbk::NPLANES, 32, 18) &&
+           make(sys->tileMaps.state24, sys->dState, d.bodyStride, rbk::NPLANES, 32, 24) &&
+           make(sys->tileMaps.dxyz, sys->dDxyz, d.atomStride, 3, rbk::kWarpTileAtoms, 3);
+}
 
 // Cut the body list into tiles (<= kBlock bodies, <= kMaxTileAtoms atoms unless one body is larger) and
 // allocate + fill everything that does not change between uploads.
@@ -161,6 +196,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(devAlloc(sys->dState, d.bodyStride*rbk::NPLANES));
     RBK_CUDA(devAlloc(sys->dDxyz, d.atomStride*3));
     RBK_CUDA(devAlloc(sys->dLocalBody, local.size()));
+    loc.resize(loc.size() + 32, loc.back());                  // one-warp tiles copy 32 offsets whatever the tile holds
     RBK_CUDA(devAlloc(sys->dLoc, loc.size()));
     if (meta.empty()) meta.push_back(make_int4(0, 0, 0, 0));
     if (bodyMeta.empty()) bodyMeta.push_back(make_int4(0, 0, 0, 0));
@@ -198,6 +234,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.tileMeta = sys->dTileMeta;
     d.bodyTileMeta = sys->dBodyTileMeta;
     d.warpTileMeta = sys->dWarpTileMeta;
+    d.tileMaps = d.numWarpTiles > 0 && encodeTileMaps(sys) ? &sys->tileMaps : nullptr;
     d.atomLoc = nullptr;
     d.freeInvMass = sys->dFreeInvMass;
     d.savedPos = sys->dSavedPos;

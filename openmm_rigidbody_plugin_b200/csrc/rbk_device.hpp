@@ -2,7 +2,7 @@
 //
 // HBM layout (all fp64 unless noted; see DESIGN.md "Data layout"):
 //   body state : NPLANES structure-of-arrays planes of bodyStride doubles each
-//                r[3] p[3] q[4] pi[4] F[3] tau[3] invm I[3] invI[3]          (27 planes)
+//                r[3] p[3] q[4] pi[4] invm invI[3] F[3] tau[3] I[3]          (27 planes)
 //   body atoms : dxyz = 3 planes of atomStride doubles (body-frame coordinates, body-major order),
 //                localBody = 1 byte per body atom (index of its body inside its tile)
 //   maps       : loc[nB+1] prefix offsets, tile descriptors int4[nTiles], atomLoc[numActualAtoms] (or NULL = identity)
@@ -14,8 +14,10 @@
 
 namespace rbk {
 
+// Plane order: what the step-fused kernel stages comes first (r p q pi 1/m 1/I = planes 0..17), then what Part 1 alone
+// needs on top (F tau = 18..23), so that ONE 2-D TMA box (rows = planes, columns = a tile's bodies) fetches either set.
 enum Plane : int {
-    PL_R = 0, PL_P = 3, PL_Q = 6, PL_PI = 10, PL_F = 14, PL_TAU = 17, PL_INVM = 20, PL_I = 21, PL_INVI = 24, NPLANES = 27
+    PL_R = 0, PL_P = 3, PL_Q = 6, PL_PI = 10, PL_INVM = 14, PL_INVI = 15, PL_F = 18, PL_TAU = 21, PL_I = 24, NPLANES = 27
 };
 
 constexpr int kBlock = 128;            // threads per CTA = max bodies per tile
@@ -30,6 +32,8 @@ constexpr int kSplitAtomsPerBody = 8;  // mean body size above which part 1 runs
 constexpr int kWarpTileAtoms = 128;    // atom capacity of the one-warp tiles (32 bodies of <= 4 atoms) of the step-fused kernel
 constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
 
+struct TileMaps;
+
 struct DeviceSystem {
     int numBodies, numFree, numBodyAtoms, numTiles, numBodyTiles, numFreeBlocks;
     int rotationMode, maxBodySize, numSMs, splitPart1;
@@ -43,6 +47,7 @@ struct DeviceSystem {
     const int4* tileMeta;        // per atom tile: first body, #bodies, first body-atom, #atoms
     const int4* bodyTileMeta;    // per body tile, same fields
     const int4* warpTileMeta;    // per one-warp tile (subdivision of the atom tiles), same fields
+    const TileMaps* tileMaps;    // HOST pointer (kernel-parameter copies are made at launch); NULL = no TMA tensor path
     const int* atomLoc;
     const double* freeInvMass;
     double* savedPos;
@@ -76,6 +81,17 @@ cudaError_t launchBuild(const DeviceSystem& S, const double* atomMass, AtomView 
                         double* dxyz, bool geometry, bool velocities, int* dofSum, cudaStream_t st);
 // Refined ("shadow") energy diagnostics (rbk_refined.cu): rdot = 3 planes, qdot = 4 planes of bodyStride doubles,
 // posDot = 3 planes of freeStride doubles.  phase 1 = before Part 1, phase 2 = after Part 2.
+// Opaque storage for a CUtensorMap (TMA descriptor, 128 bytes, 64-byte aligned); encoded on the host in rbk_api.cu.
+struct alignas(64) TensorMapBlob {
+    unsigned long long opaque[16];
+};
+// Descriptors of the one-warp-tile pipeline: state planes as a 2-D tensor [NPLANES][bodyStride] with boxes of
+// 32 bodies x 18 planes (step-fused kernel) or x 24 planes (Part 1 alone), body-frame coordinates as [3][atomStride]
+// with a box of kWarpTileAtoms atoms x 3 planes.
+struct TileMaps {
+    TensorMapBlob state18, state24, dxyz;
+};
+
 struct RefinedState {
     double* rdot;
     double* qdot;

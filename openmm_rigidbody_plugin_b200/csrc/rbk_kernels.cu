@@ -72,13 +72,15 @@ __device__ __forceinline__ void cpAsync16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// smem plane k of a stage <-> global state plane (the I planes 21..23 are not needed on the device path)
-__device__ __forceinline__ int globalPlane(int k) { return k < 21 ? k : k + 3; }
+// smem plane k of a part1Kernel stage (r p q pi | F tau | 1/m | 1/I) <-> global state plane
+__device__ __forceinline__ int globalPlane(int k) {
+    return k < 14 ? k : (k < 17 ? (int) PL_F + (k - 14) : (k < 20 ? (int) PL_TAU + (k - 17) : (k == 20 ? (int) PL_INVM : (int) PL_INVI + (k - 21))));
+}
 
 template <bool EXACT, bool FUSED, bool NATIVE>
 __global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT)
 part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+    extern __shared__ __align__(128) unsigned char smemRaw[];
     Part1Smem& sm = *reinterpret_cast<Part1Smem*>(smemRaw);
     const int tid = threadIdx.x;
     const int G = gridDim.x;
@@ -343,7 +345,7 @@ constexpr int kSmallBody = 8;                       // bodies up to this size ar
 // <128, 512> (four warps share a tile) and <32, 128> (ONE warp per CTA, for bodies of <= 4 atoms such as water: no
 // CTA-wide barrier ever waits for a slower warp, eight independent CTAs per SM).
 template <int BODIES, int ATOMS>
-struct FusedStage {
+struct alignas(128) FusedStage {                    // 128-byte alignment: destination of TMA tensor copies
     double body[kFPlanes][BODIES];
     double f[3*ATOMS];                              // atom forces as xyzxyz..., later the arms delta = A^T(q) d
     double d[3][ATOMS];
@@ -384,6 +386,11 @@ __device__ __forceinline__ void bulkCopy(void* smem, const void* gmem, unsigned 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smemAddr(smem)), "l"(gmem), "r"(bytes), "r"(smemAddr(bar)) : "memory");
 }
+// 2-D TMA tensor copy: the box described by `map` at element coordinates (x, y) -> shared memory (128-byte aligned)
+__device__ __forceinline__ void tmaLoad2D(void* smem, const TensorMapBlob* map, int x, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smemAddr(smem)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smemAddr(bar)) : "memory");
+}
 __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
@@ -396,8 +403,9 @@ __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k 
 // two launches): no forces are staged, the stored F and tau planes take their place in the stage, Part 2's phases drop out.
 template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY>
 __global__ void __launch_bounds__(BODIES, (STAGES == 2 ? 256 : 512)/BODIES)
-part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force,
+                 const __grid_constant__ TileMaps maps, const bool useMaps) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
     typedef FusedStage<BODIES, ATOMS> Stage;
     FusedSmem<BODIES, ATOMS, STAGES>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS, STAGES>*>(smemRaw);
     constexpr int kBlock = BODIES, kWarps = BODIES/32;          // shadow the file-level constants inside this kernel
@@ -414,10 +422,29 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         return (P1ONLY || (contiguousForces && ((S.numFree + m.z) & 1) == 0)) && (m.x & 3) == 0 && (m.y & 3) == 0 &&
                (m.z & 1) == 0 && (m.w & 1) == 0;
     };
+    auto tensorOK = [&](int4 m) {
+        return BODIES == 32 && useMaps && (P1ONLY || (contiguousForces && ((S.numFree + m.z) & 1) == 0 && (m.w & 1) == 0));
+    };
     auto request = [&](int4 m, int st) {
         Stage& T = sm.stage[st];
         const int lbFirst = m.z & ~15;                         // 16-byte granules of the byte array
         const unsigned lbBytes = (unsigned) (((m.z + m.w - lbFirst) + 15) & ~15);
+        if (tensorOK(m)) {
+            // one-warp tiles: the tile's state planes are ONE 2-D box (32 bodies x 18 or 24 planes), its body-frame
+            // coordinates another (ATOMS atoms x 3 planes; atoms past the tile are fetched and ignored, past the array
+            // zero-filled) - five copies per tile instead of 24, and no alignment rule on the tile's offsets
+            if (tid == 0) {
+                fenceProxyAsync();
+                constexpr unsigned boxBytes = (P1ONLY ? 24u : 18u)*BODIES*8u + 3u*ATOMS*8u + 4u*BODIES;
+                mbarExpectTx(&sm.bar[st], boxBytes + (P1ONLY ? 0u : 24u*m.w) + lbBytes);
+                tmaLoad2D(&T.body[0][0], P1ONLY ? &maps.state24 : &maps.state18, m.x, 0, &sm.bar[st]);
+                tmaLoad2D(&T.d[0][0], &maps.dxyz, m.z, 0, &sm.bar[st]);
+                bulkCopy(&T.loc[0], S.loc + m.x, 4u*BODIES, &sm.bar[st]);
+                if (!P1ONLY) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
+                bulkCopy(&T.localBody[0], S.localBody + lbFirst, lbBytes, &sm.bar[st]);
+            }
+            return;
+        }
         if (bulkOK(m)) {
             if (tid == 0) {
                 fenceProxyAsync();                             // earlier generic-proxy writes to this stage are ordered first
@@ -465,7 +492,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     // wait for a stage filled by request(): mbarrier phase for bulk tiles, cp.async groups otherwise
     unsigned bulkPhase[2] = {0u, 0u};
     auto arrived = [&](int4 m, int st) {
-        if (bulkOK(m)) { mbarWait(&sm.bar[st], bulkPhase[st] & 1u); bulkPhase[st]++; }
+        if (tensorOK(m) || bulkOK(m)) { mbarWait(&sm.bar[st], bulkPhase[st] & 1u); bulkPhase[st]++; }
         cpWait<0>();
     };
 
@@ -799,7 +826,12 @@ cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, Ato
     }
     const int resident = S.numSMs*blocks;
     if (tiles > 0)
-        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(S, dt, pos, vel, force);
+    {
+        static const TileMaps noMaps = {};
+        const bool useMaps = BODIES == 32 && S.tileMaps != nullptr;
+        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(
+            S, dt, pos, vel, force, useMaps ? *S.tileMaps : noMaps, useMaps);
+    }
     return cudaGetLastError();
 }
 
