@@ -490,9 +490,12 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             cpAsync4(&T.localBody[4*w], S.localBody + lbFirst + 4*w);
     };
     // wait for a stage filled by request(): mbarrier phase for bulk tiles, cp.async groups otherwise
-    unsigned bulkPhase[2] = {0u, 0u};
+    unsigned phase0 = 0u, phase1 = 0u;                         // mbarrier phase parity per stage (scalars: stay in registers)
     auto arrived = [&](int4 m, int st) {
-        if (tensorOK(m) || bulkOK(m)) { mbarWait(&sm.bar[st], bulkPhase[st] & 1u); bulkPhase[st]++; }
+        if (tensorOK(m) || bulkOK(m)) {
+            mbarWait(&sm.bar[st], st ? phase1 : phase0);
+            if (st) phase1 ^= 1u; else phase0 ^= 1u;
+        }
         cpWait<0>();
     };
 
