@@ -55,6 +55,7 @@ struct rbk_system {
     int4* dTileMeta = nullptr;
     int4* dBodyTileMeta = nullptr;
     int4* dWarpTileMeta = nullptr;
+    int* dTileCounter = nullptr;
     rbk::TileMaps tileMaps{};        // TMA descriptors of the one-warp-tile pipeline (valid when dev.tileMaps != NULL)
     int* dAtomLoc = nullptr;
     double* dFreeInvMass = nullptr;
@@ -79,7 +80,7 @@ struct rbk_system {
     std::vector<double> staging, oldPositions;
 
     ~rbk_system() {
-        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta);
+        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter);
         cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (h2dStream) cudaStreamDestroy(h2dStream);
@@ -234,6 +235,9 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.tileMeta = sys->dTileMeta;
     d.bodyTileMeta = sys->dBodyTileMeta;
     d.warpTileMeta = sys->dWarpTileMeta;
+    RBK_CUDA(devAlloc(sys->dTileCounter, 1));
+    RBK_CUDA(cudaMemsetAsync(sys->dTileCounter, 0, sizeof(int), st));
+    d.tileCounter = sys->dTileCounter;
     d.tileMaps = d.numWarpTiles > 0 && encodeTileMaps(sys) ? &sys->tileMaps : nullptr;
     d.atomLoc = nullptr;
     d.freeInvMass = sys->dFreeInvMass;
@@ -378,6 +382,7 @@ int rbk_upload(rbk_system* sys, void* stream) {
         rc = setLocation(sys, nullptr, st);
         if (rc != RBK_OK) return rc;
     }
+    RBK_CUDA(cudaMemsetAsync(sys->dTileCounter, 0, sizeof(int), st));     // self-resetting per launch; re-armed here in case one failed
     const HostModel& h = sys->host;
     const DeviceSystem& d = sys->dev;
     const size_t ld = d.bodyStride;

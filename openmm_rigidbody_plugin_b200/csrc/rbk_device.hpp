@@ -49,6 +49,7 @@ struct DeviceSystem {
     const int4* warpTileMeta;    // per one-warp tile (subdivision of the atom tiles), same fields
     const TileMaps* tileMaps;    // HOST pointer (kernel-parameter copies are made at launch); NULL = no TMA tensor path
     const int* atomLoc;
+    int* tileCounter;            // zero between launches: tiles claimed so far by the persistent step-fused kernel
     const double* freeInvMass;
     double* savedPos;
 };

@@ -360,6 +360,7 @@ struct FusedSmem {
     double head[BODIES/32][6];
     int headKey[BODIES/32];
     int4 meta[3];
+    int tileIdx[3];                                 // tile numbers of the current, next and next-but-one tile (ring)
 };
 
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier completion: one elected thread moves a whole plane
@@ -499,11 +500,22 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         cpWait<0>();
     };
 
+    // Tiles: the first G are the CTAs' own (blockIdx), every later one is claimed from a global counter, one claim ahead
+    // of the prefetch - a CTA held up by a slow tile (sub-stepped bodies) simply claims fewer.  Every CTA stops at its first
+    // out-of-range claim, so a launch makes exactly numTiles claims and the last one puts the counter back to zero.
+    auto claim = [&]() {
+        const int old = atomicAdd(S.tileCounter, 1);
+        if (old == numTiles - 1) *S.tileCounter = 0;
+        return G + old;
+    };
     const int tile0 = blockIdx.x;
     if (tile0 < numTiles) {
         if (tid == 0) {
+            const int tile1 = claim();
+            sm.tileIdx[0] = tile0;
+            sm.tileIdx[1] = tile1;
             sm.meta[0] = tileMeta[tile0];
-            if (tile0 + G < numTiles) sm.meta[1] = tileMeta[tile0 + G];
+            if (tile1 < numTiles) sm.meta[1] = tileMeta[tile1];
             mbarInit(&sm.bar[0], 1);
             mbarInit(&sm.bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -511,7 +523,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         __syncthreads();
         request(sm.meta[0], 0);
         cpCommit();
-        for (int tile = tile0, it = 0; tile < numTiles; tile += G, it++) {
+        for (int it = 0; sm.tileIdx[it % 3] < numTiles; it++) {
             const int4 m = sm.meta[it % 3];
             const int cur = STAGES == 2 ? (it & 1) : 0;
             Stage& T = sm.stage[cur];
@@ -523,9 +535,13 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             arrived(m, cur);                                   // this tile (+ the next tile's descriptor) landed
             __syncthreads();
             if (STAGES == 2) {
-                if (tile + G < numTiles) {
+                if (sm.tileIdx[(it + 1) % 3] < numTiles) {
                     request(sm.meta[(it + 1) % 3], cur ^ 1);
-                    if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + tile + 2*G);
+                    if (tid == 0) {
+                        const int after = claim();
+                        sm.tileIdx[(it + 2) % 3] = after;
+                        if (after < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + after);
+                    }
                 }
                 cpCommit();
             }
@@ -660,9 +676,13 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             }
             __syncthreads();
             if (STAGES == 1) {                                 // the single stage is free again: request the next tile
-                if (tile + G < numTiles) {
+                if (sm.tileIdx[(it + 1) % 3] < numTiles) {
                     request(sm.meta[(it + 1) % 3], 0);
-                    if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + tile + 2*G);
+                    if (tid == 0) {
+                        const int after = claim();
+                        sm.tileIdx[(it + 2) % 3] = after;
+                        if (after < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + after);
+                    }
                 }
                 cpCommit();
             }
