@@ -28,18 +28,26 @@ int rbkh_exact_series(int order, double dt, const double* I, double* q, double* 
     d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};
     bool ok = false;
     switch (order) {
-    case 6: ok = exactRotationSeries<6>(dt, inv, qq, pp); break;
-    case 8: ok = exactRotationSeries<8>(dt, inv, qq, pp); break;
-    case 10: ok = exactRotationSeries<10>(dt, inv, qq, pp); break;
-    case 12: ok = exactRotationSeries<12>(dt, inv, qq, pp); break;
-    case 14: ok = exactRotationSeries<14>(dt, inv, qq, pp); break;
-    case 16: ok = exactRotationSeries<16>(dt, inv, qq, pp); break;
-    case 20: ok = exactRotationSeries<20>(dt, inv, qq, pp); break;
+    case 6: ok = exactRotationSeries<6>(dt, inv, qq, pp) == 0.0; break;
+    case 8: ok = exactRotationSeries<8>(dt, inv, qq, pp) == 0.0; break;
+    case 10: ok = exactRotationSeries<10>(dt, inv, qq, pp) == 0.0; break;
+    case 12: ok = exactRotationSeries<12>(dt, inv, qq, pp) == 0.0; break;
+    case 14: ok = exactRotationSeries<14>(dt, inv, qq, pp) == 0.0; break;
+    case 16: ok = exactRotationSeries<16>(dt, inv, qq, pp) == 0.0; break;
+    case 20: ok = exactRotationSeries<20>(dt, inv, qq, pp) == 0.0; break;
     default: return -1;
     }
     q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z;
     pi[0] = pp.w; pi[1] = pp.x; pi[2] = pp.y; pi[3] = pp.z;
     return ok ? 1 : 0;
+}
+
+// The fast path's overshoot of its truncation bound at the production order (0 = converged): what the retry path
+// turns into a number of sub-steps.  q, pi are not modified.
+double rbkh_series_excess(double dt, const double* I, const double* q, const double* pi) {
+    d3 inv = {1.0/I[0], 1.0/I[1], 1.0/I[2]};
+    d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};
+    return exactRotationSeries<kSeriesOrder>(dt, inv, qq, pp);
 }
 
 void rbkh_nosquish(double dt, int n, const double* invI, double* q, double* pi) {

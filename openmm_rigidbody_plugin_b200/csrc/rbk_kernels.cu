@@ -53,6 +53,7 @@ constexpr int kP1Planes = 24;                       // r3 p3 q4 pi4 F3 tau3 invm
 struct Part1Smem {
     double body[2][kP1Planes][kBlock];
     int4 meta[3];                                   // ring: descriptors of the current, next and next-but-one tile
+    int tileIdx[3];                                 // ring: their tile numbers (claimed dynamically after the first wave)
     double d[3][kTileAtoms];                        // FUSED only (the !FUSED kernel allocates up to here)
     unsigned char localBody[kTileAtoms + 16];
 };
@@ -108,25 +109,38 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
             cpAsync4(&sm.localBody[4*w], S.localBody + first + 4*w);
     };
 
+    // the first G tiles are the CTAs' own, later ones are claimed from the global counter (see part2Part1Kernel)
+    auto claim = [&]() {
+        const int old = atomicAdd(S.tileCounter, 1);
+        if (old == numTiles - 1) *S.tileCounter = 0;
+        return G + old;
+    };
     const int tile0 = blockIdx.x;
     if (tile0 < numTiles) {
         if (tid == 0) {
+            const int tile1 = claim();
+            sm.tileIdx[0] = tile0;
+            sm.tileIdx[1] = tile1;
             sm.meta[0] = tiles[tile0];
-            if (tile0 + G < numTiles) sm.meta[1] = tiles[tile0 + G];
+            if (tile1 < numTiles) sm.meta[1] = tiles[tile1];
         }
         __syncthreads();
         requestBody(sm.meta[0], 0);
         cpCommit();
-        for (int tile = tile0, it = 0; tile < numTiles; tile += G, it++) {
+        for (int it = 0; sm.tileIdx[it % 3] < numTiles; it++) {
             const int stage = it & 1;
             const int4 m = sm.meta[it % 3];
             if (FUSED) requestAtoms(m);
             cpCommit();
             cpWait<1>();                                       // body state of this tile (+ descriptor of the next) landed
             __syncthreads();
-            if (tile + G < numTiles) {
+            if (sm.tileIdx[(it + 1) % 3] < numTiles) {
                 requestBody(sm.meta[(it + 1) % 3], stage ^ 1);
-                if (tid == 0 && tile + 2*G < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tiles + tile + 2*G);
+                if (tid == 0) {
+                    const int after = claim();
+                    sm.tileIdx[(it + 2) % 3] = after;
+                    if (after < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tiles + after);
+                }
             }
             cpCommit();
 

@@ -379,10 +379,51 @@ RBK_HD_NOINLINE void exactRotationElliptic(double dt, d3 I, d3 invI, d4& q, d4& 
 // terms and the caller falls back to exactRotationElliptic when the check fails (large |omega| dt).
 // Also valid where the elliptic route is not (symmetric, spherical and linear tops).
 // ---------------------------------------------------------------------------------------------
+// Returns 0 when the truncation check passed (q, pi advanced), otherwise by how much the tail exceeds its bound
+// (a ratio > 1, possibly inf/NaN; q, pi untouched) - what the retry path needs to pick its number of sub-steps.
+//
+// Choice of the reduction axis.  theta's integrand has the pole L - l0(t) = 0: with the angular momentum almost along
+// +axis 1 the reciprocal series converges slowly (or not within a step).  Nothing in the derivation singles out axis 1 -
+// the same formulas hold for any body axis taken as "axis 1" after a cyclic relabelling (x,y,z) -> (y,z,x) or (z,x,y),
+// which is the proper rotation q -> q (x) 1/2(1,+-1,+-1,+-1) of the body frame.  Each body therefore uses the axis on which
+// its angular momentum has the SMALLEST (most negative) component, so that L - l0 >= 0.42 L: at 300 K and 1 fs no water in
+// 4096 then fails order 12 (0.7 % with the fixed axis; order 14 was needed before), and the nearly linear triatomics of the
+// mixed benchmark that needed up to 40 sub-steps converge directly.
+RBK_HD d4 quatTimesDiag(d4 q, double s) {                  // q (x) 1/2 (1, s, s, s), s = +-1
+    return {0.5*(q.w - s*(q.x + q.y + q.z)), 0.5*(q.x + s*(q.w + q.y - q.z)),
+            0.5*(q.y + s*(q.w - q.x + q.z)), 0.5*(q.z + s*(q.w + q.x - q.y))};
+}
+
 template <int K>
-RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
-    const d3 l0 = quatBt(q, pi)*0.5;
-    if (l0.y*l0.y + l0.z*l0.z < DBL_EPSILON) { uniaxial<0>(dt, invI.x, q, pi); return true; }
+RBK_HD double exactRotationSeriesAxis1(double dt, d3 invI, d3 l0, d4& q, d3& lOut);
+
+template <int K>
+RBK_HD double exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
+    const d3 l = quatBt(q, pi)*0.5;
+    const int j = l.y < l.x ? (l.z < l.y ? 2 : 1) : (l.z < l.x ? 2 : 0);       // argmin: the new "axis 1"
+    const double s = j == 1 ? 1.0 : -1.0;
+    const d3 lp = j == 0 ? l : (j == 1 ? d3{l.y, l.z, l.x} : d3{l.z, l.x, l.y});
+    const d3 invIp = j == 0 ? invI : (j == 1 ? d3{invI.y, invI.z, invI.x} : d3{invI.z, invI.x, invI.y});
+    d4 qp = j == 0 ? q : quatTimesDiag(q, s);
+    d3 ln;
+    const double excess = exactRotationSeriesAxis1<K>(dt, invIp, lp, qp, ln);
+    if (excess != 0.0) return excess;
+    q = j == 0 ? qp : quatTimesDiag(qp, -s);
+    const d3 lb = j == 0 ? ln : (j == 1 ? d3{ln.z, ln.x, ln.y} : d3{ln.y, ln.z, ln.x});
+    pi = quatB(q, lb*2.0);
+    return 0.0;
+}
+
+// The series proper, reduction about axis 1 of the (relabelled) body frame: advances q and returns the new body-frame
+// angular momentum in lOut.
+template <int K>
+RBK_HD double exactRotationSeriesAxis1(double dt, d3 invI, d3 l0, d4& q, d3& lOut) {
+    if (l0.y*l0.y + l0.z*l0.z < DBL_EPSILON) {             // rotation about axis 1 itself
+        d4 pi = quatB(q, l0*2.0);
+        uniaxial<0>(dt, invI.x, q, pi);
+        lOut = quatBt(q, pi)*0.5;
+        return 0.0;
+    }
     const double Lsq = l0.y*l0.y + l0.z*l0.z + l0.x*l0.x;
     const double L = sqrt(Lsq);
     const double twoT = l0.x*l0.x*invI.x + l0.y*l0.y*invI.y + l0.z*l0.z*invI.z;
@@ -437,7 +478,7 @@ RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
     // truncation check on the last two orders of every series (relative to L, resp. r[0])
     const double tailR = fabs(r[K]) + fabs(r[K - 1]);
 #ifndef RBK_EXPERIMENT_SKIP_CHECK
-    if (!(tailL <= 2.0e-16*L && tailR <= 2.0e-16*fabs(r[0]))) return false;
+    if (!(tailL <= 2.0e-16*L && tailR <= 2.0e-16*fabs(r[0]))) return fmax(tailL/(2.0e-16*L), tailR/(2.0e-16*fabs(r[0])));
 #endif
     const double theta = 0.5*dt*(L*invI.x + (twoT - Lsq*invI.x)*sr);
     double st, ct;
@@ -449,24 +490,29 @@ RBK_HD bool exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
     d4 qn = zz*dot(z0, q) + quatC(zz, quatCt(z0, q));
     qn = qn*rsqrtd(dot(qn, qn));
     q = qn;
-    pi = quatB(qn, d3{sx, sy, sz}*2.0);
-    return true;
+    lOut = {sx, sy, sz};
+    return 0.0;
 }
 
 #ifndef RBK_SERIES_ORDER
-#define RBK_SERIES_ORDER 14
+#define RBK_SERIES_ORDER 12
 #endif
 constexpr int kSeriesOrder = RBK_SERIES_ORDER;
 
-// Slow path of mode 0 (rare; kept out of line so that the fast path stays straight-line code): the step is
-// redone as 2, then 4 exact sub-steps - the composition of exact flows is exact and every halving shrinks the
-// series tail by 2^order - and only then by the elliptic-integral route, which needs I = 1/invI.
-RBK_HD_NOINLINE void exactRotationRetry(double dt, d3 invI, d4& q, d4& pi) {
-    for (int n = 2; n <= 4; n <<= 1) {
+// Slow path of mode 0 (rare; kept out of line so that the fast path stays straight-line code).  The composition of
+// exact flows is exact, and with n sub-steps the order-k coefficient shrinks by n^k: the number of sub-steps is taken
+// from how far the failed attempt overshot its bound (excess^(1/(K-1)), with a margin), so that one retry normally
+// suffices - a slow body holds up its whole warp, and with few tiles per CTA the whole launch.  Only when that would
+// need more than kMaxSubSteps, or still fails, the elliptic-integral route (which needs I = 1/invI) takes over.
+constexpr int kMaxSubSteps = 32;
+RBK_HD_NOINLINE void exactRotationRetry(double dt, d3 invI, d4& q, d4& pi, double excess) {
+    const double want = 1.25*exp2(log2(excess)/(kSeriesOrder - 1));
+    if (want <= (double) kMaxSubSteps) {                       // false for inf / NaN as well
+        const int n = want < 2.0 ? 2 : (int) ceil(want);
         d4 q1 = q, p1 = pi;
         const double h = dt/n;
         bool ok = true;
-        for (int i = 0; i < n && ok; i++) ok = exactRotationSeries<kSeriesOrder>(h, invI, q1, p1);
+        for (int i = 0; i < n && ok; i++) ok = exactRotationSeries<kSeriesOrder>(h, invI, q1, p1) == 0.0;
         if (ok) { q = q1; pi = p1; return; }
     }
 #ifndef RBK_EXPERIMENT_NO_ELLIPTIC
@@ -478,7 +524,8 @@ RBK_HD_NOINLINE void exactRotationRetry(double dt, d3 invI, d4& q, d4& pi) {
 // Mode 0 entry point used by the step: one series step over dt; if its truncation check fails (fast rotor /
 // long step) the retry path above.
 RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
-    if (!exactRotationSeries<kSeriesOrder>(dt, invI, q, pi)) exactRotationRetry(dt, invI, q, pi);
+    const double excess = exactRotationSeries<kSeriesOrder>(dt, invI, q, pi);
+    if (excess != 0.0) exactRotationRetry(dt, invI, q, pi, excess);
 }
 
 } // namespace rbk
