@@ -31,7 +31,9 @@ int rbkh_exact_series(int order, double dt, const double* I, double* q, double* 
     case 6: ok = exactRotationSeries<6>(dt, inv, qq, pp) == 0.0; break;
     case 8: ok = exactRotationSeries<8>(dt, inv, qq, pp) == 0.0; break;
     case 10: ok = exactRotationSeries<10>(dt, inv, qq, pp) == 0.0; break;
+    case 11: ok = exactRotationSeries<11>(dt, inv, qq, pp) == 0.0; break;
     case 12: ok = exactRotationSeries<12>(dt, inv, qq, pp) == 0.0; break;
+    case 13: ok = exactRotationSeries<13>(dt, inv, qq, pp) == 0.0; break;
     case 14: ok = exactRotationSeries<14>(dt, inv, qq, pp) == 0.0; break;
     case 16: ok = exactRotationSeries<16>(dt, inv, qq, pp) == 0.0; break;
     case 20: ok = exactRotationSeries<20>(dt, inv, qq, pp) == 0.0; break;
