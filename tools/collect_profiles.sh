@@ -14,9 +14,9 @@ python bench.py --molecules 250000 --no-cpu-baseline >> $O/${R}_bench_other_conf
 python bench.py --no-fuse --no-cpu-baseline --no-e2e >> $O/${R}_bench_other_configs.jsonl 2>> $O/${R}_bench_err.log
 ncu --metrics gpu__time_duration.sum --clock-control none -s 8 -c 30 --csv --log-file $O/${R}_launches.csv \
     python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:part2Part1Kernel -s 3 -c 1 -o $O/${R}_fused_mode0 \
+ncu --set full --clock-control none --import-source on -k regex:part2Part1Kernel -s 4 -c 1 -o $O/${R}_fused_mode0 \
     python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:part1Kernel -s 3 -c 1 -o $O/${R}_part1_mode0 \
+ncu --set full --clock-control none --import-source on -k regex:part2Part1Kernel -s 3 -c 1 -o $O/${R}_part1_mode0 \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-fuse > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:part2Kernel -s 3 -c 1 -o $O/${R}_part2 \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-fuse > /dev/null 2>&1
