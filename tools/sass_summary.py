@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel SASS mnemonic histogram of librbk.so (cuobjdump -sass), the evidence for what the kernels use:
-LDGSTS = cp.async staging, UBLKCP + SYNCS = TMA bulk copies (cp.async.bulk) completing on an mbarrier, SHFL = warp-shuffle segmented reduction, DFMA/DMUL/DADD = fp64 pipe, MUFU.RCP64H/RSQ64H
+LDGSTS = cp.async staging, UBLKCP + SYNCS = TMA bulk copies (cp.async.bulk) completing on an mbarrier, UTMALDG = 2-D TMA tensor copies, SHFL = warp-shuffle segmented reduction, DFMA/DMUL/DADD = fp64 pipe, MUFU.RCP64H/RSQ64H
 = fp64 reciprocal / rsqrt seeds, no HMMA/UTC*MMA (nothing here is a dense contraction).
 
     python tools/sass_summary.py > profiles/rNN_sass_summary.txt ; the full listing goes to profiles/rNN_librbk_sass.txt.gz
@@ -39,7 +39,7 @@ def main():
             base[o.split(".")[0]] += n
         print(f"== {name}\n   {tot} SASS instructions")
         print("   " + ", ".join(f"{o} {n}" for o, n in base.most_common(14)))
-        special = {k: v for k, v in ops.items() if k.startswith(("LDGSTS", "SHFL", "MUFU", "BAR", "LDGDEPBAR", "DEPBAR", "UBLKCP", "SYNCS", "FENCE", "HMMA", "UTC", "ATOM", "RED", "STL", "LDL"))}
+        special = {k: v for k, v in ops.items() if k.startswith(("LDGSTS", "SHFL", "MUFU", "BAR", "LDGDEPBAR", "DEPBAR", "UBLKCP", "UTMALDG", "UTMAPF", "SYNCS", "FENCE", "HMMA", "UTC", "ATOM", "RED", "STL", "LDL"))}
         print("   notable: " + ", ".join(f"{k} {v}" for k, v in sorted(special.items())))
         print()
 
