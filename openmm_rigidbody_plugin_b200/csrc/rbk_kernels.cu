@@ -7,7 +7,8 @@
 //                     reconstruction, warp-shuffle segmented reduction of force and torque
 // exchanging per-body quantities (q, r, v_cm, omega) through shared memory, so the rotation update
 // and the atom scatter are ONE kernel and nothing per-body is re-read from HBM.  CTAs past the last
-// tile integrate the free atoms (velocity Verlet).  No atomics anywhere: results are bit-reproducible.
+// tile integrate the free atoms (velocity Verlet).  No atomics on the data path (the persistent kernels' tile counter only
+// decides which CTA takes a tile): results are bit-reproducible.
 //
 // Reference behaviour reproduced: RigidBodySystem::integratePart1/2, computeKineticEnergies
 // (openmmapi/src/RigidBodySystem.cpp:170-220); this is NOT a port of platforms/cuda/src/kernels/*.cu
