@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--no-fuse", action="store_true", help="step with separate part1/part2 launches only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dt-fs", type=float, default=1.0, help="time step in fs (BASELINE: 1 fs)")
     return ap.parse_args()
 
 
@@ -394,7 +395,9 @@ def run_b200_arm(args):
 
 
 def main():
+    global DT
     args = parse_args()
+    DT = args.dt_fs * 1e-3
     if args.impl == "reference":
         run_reference_arm(args)
     else:
