@@ -184,6 +184,9 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
             warpMeta.push_back(make_int4(b, n, loc[b], loc[b + n] - loc[b]));
         }
     d.numWarpTiles = (int) warpMeta.size();
+    d.stageBodies = 4;
+    if (large)
+        for (const int4& t : meta) if (t.w <= rbk::kLargeBodyTileAtoms) d.stageBodies = std::max(d.stageBodies, (t.y + 3) & ~3);
     d.numFreeBlocks = (nF + rbk::kFreePerBlock - 1)/rbk::kFreePerBlock;
     d.rotationMode = h.rotationMode;
     d.maxBodySize = maxSize;
@@ -252,15 +255,11 @@ int setLocation(rbk_system* sys, const int* location, cudaStream_t st) {
     const int* src = location ? location : h.atomIndex.data();
     bool identity = true;
     for (int i = 0; i < n && identity; i++) identity = src[i] == i;
-    if (identity) {
-        sys->dev.atomLoc = nullptr;
-        return RBK_OK;
-    }
-    for (int i = 0; i < n; i++)
+    for (int i = 0; i < n && !identity; i++)
         if (src[i] < 0) return fail(RBK_EINVAL, "rbk_set_atom_location: negative location");
-    RBK_CUDA(cudaMemcpyAsync(sys->dAtomLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
-    RBK_CUDA(cudaStreamSynchronize(st));
-    sys->dev.atomLoc = sys->dAtomLoc;
+    if (!identity) RBK_CUDA(cudaMemcpyAsync(sys->dAtomLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaStreamSynchronize(st));             // `location` is the caller's
+    sys->dev.atomLoc = identity ? nullptr : sys->dAtomLoc;
     return RBK_OK;
 }
 

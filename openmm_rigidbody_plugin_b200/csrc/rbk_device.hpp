@@ -26,7 +26,12 @@ constexpr int kBlock = 128;            // threads per CTA = max bodies per tile
 // (<=128 bodies, <=kMaxTileAtoms atoms) drive the stand-alone rotation kernel used when bodies are large,
 // so that its thread-per-body phase runs full warps.  For small bodies (water) the two coincide.
 constexpr int kTileAtoms = 512;
-constexpr int kLargeBodyTileAtoms = 768;   // atom-tile cap when bodies are large (see rbk_api.cu)
+#ifndef RBK_LARGE_PER_THREAD
+#define RBK_LARGE_PER_THREAD 2
+#endif
+constexpr int kLargePerThread = RBK_LARGE_PER_THREAD;          // atoms per thread of the large-body atom kernels
+constexpr int kLargeBodyTileAtoms = kBlock*kLargePerThread;    // atom-tile cap when bodies are large: a tile's forces and
+                                                               // arms are staged in shared memory by part2LargeKernel
 constexpr int kMaxTileAtoms = 8192;
 constexpr int kSplitAtomsPerBody = 8;  // mean body size above which part 1 runs as rotation kernel + atom kernel
 constexpr int kWarpTileAtoms = 128;    // atom capacity of the one-warp tiles (32 bodies of <= 4 atoms) of the step-fused kernel
@@ -39,6 +44,7 @@ struct DeviceSystem {
     int rotationMode, maxBodySize, numSMs, splitPart1;
     int fusable;                 // every atom tile fits the shared-memory staging of the step-fused kernel
     int numWarpTiles;            // > 0: bodies have <= 4 atoms and the step-fused kernel runs one warp per 32-body tile
+    int stageBodies;             // large-body systems: most bodies in any atom tile of <= kLargeBodyTileAtoms atoms (multiple of 4)
     size_t bodyStride, atomStride, freeStride;
     double* state;
     const double* dxyz;

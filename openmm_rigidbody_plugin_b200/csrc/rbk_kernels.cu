@@ -197,13 +197,28 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
 }
 
 // Positions of the body atoms from the updated (r, q): one CTA per atom tile, thread per atom.
-// Second half of part 1 for large-body systems (see part1Kernel, !FUSED).
+// Second half of part 1 for large-body systems (see part1Kernel, !FUSED).  Each thread requests the coordinates, body
+// bytes and array slots of kLargePerThread atoms (a whole tile in one round) before it touches any of them - the slot
+// look-up in atomLoc is not a dependent load in front of the store any more; the kernel is a pure stream and lives on
+// the number of loads in flight.
 template <bool NATIVE>
 __global__ void __launch_bounds__(kBlock) atomPositionKernel(const DeviceSystem S, const AtomView pos) {
     __shared__ double sB[7][kBlock];
     const int tid = threadIdx.x;
     const int4 m = S.tileMeta[blockIdx.x];
     const size_t ld = S.bodyStride, as = S.atomStride;
+    const int a1 = m.z + m.w;
+    int key[kLargePerThread], slot[kLargePerThread];
+    d3 d[kLargePerThread];
+#pragma unroll
+    for (int u = 0; u < kLargePerThread; u++) {
+        const int a = m.z + tid + u*kBlock;
+        if (a < a1) {
+            key[u] = S.localBody[a];
+            slot[u] = S.atomLoc ? S.atomLoc[S.numFree + a] : S.numFree + a;
+            d[u] = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+        }
+    }
     if (tid < m.y) {
         const double* s = S.state + (size_t) (m.x + tid);
         const d3 r = loadPlane3(s + PL_R*ld, ld);
@@ -212,12 +227,22 @@ __global__ void __launch_bounds__(kBlock) atomPositionKernel(const DeviceSystem 
         sB[3][tid] = q.w; sB[4][tid] = q.x; sB[5][tid] = q.y; sB[6][tid] = q.z;
     }
     __syncthreads();
-    for (int a = m.z + tid; a < m.z + m.w; a += kBlock) {
+#pragma unroll
+    for (int u = 0; u < kLargePerThread; u++) {
+        const int a = m.z + tid + u*kBlock;
+        if (a < a1) {
+            const int k = key[u];
+            const d3 r = {sB[0][k], sB[1][k], sB[2][k]};
+            const d4 q = {sB[3][k], sB[4][k], sB[5][k], sB[6][k]};
+            storeAtom<NATIVE>(pos, slot[u], atomPosition(r, q, d[u]));
+        }
+    }
+    for (int a = m.z + tid + kLargePerThread*kBlock; a < a1; a += kBlock) {      // a single body larger than a tile
         const int k = S.localBody[a];
-        const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+        const d3 dd = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
         const d3 r = {sB[0][k], sB[1][k], sB[2][k]};
         const d4 q = {sB[3][k], sB[4][k], sB[5][k], sB[6][k]};
-        storeAtom<NATIVE>(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, d));
+        storeAtom<NATIVE>(pos, atomSlot(S, S.numFree + a), atomPosition(r, q, dd));
     }
 }
 
@@ -340,6 +365,294 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
             storeAtom<NATIVE>(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Part 2 for large-body systems (mean body size > kSplitAtomsPerBody; atom tiles of <= kLargeBodyTileAtoms atoms).
+//
+// The bucket for big bodies of the size-bucketed reduction: with tens of atoms per body a shuffle scan spends
+// 5 levels x 6 doubles of SHFL/select/add on every 32 atoms (ncu on config 4: 28 % of the executed instructions,
+// issue-bound at 3.4 TB/s).  Here a tile's forces and space-frame arms delta = A^T(q) d are staged in shared memory by
+// the atoms' threads (coalesced loads, kLargePerThread atoms in flight per thread), and then ONE THREAD PER
+// (body, component) walks its body's atoms sequentially - the reference's own summation order
+// (RigidBody::forceAndTorque, openmmapi/src/RigidBody.cpp:174-183), no shuffles, no atomics, deterministic.  The arms
+// stay in shared memory for the velocity phase, so the body-frame coordinates are read once and rotated once.
+// A body larger than a tile is alone in its tile and is reduced by the whole CTA (strided partial sums, fixed tree).
+// ------------------------------------------------------------------------------------------------
+// Persistent CTAs (one wave) walk the tiles round-robin behind a three-deep cp.async pipeline: while tile i is processed,
+// tile i+1's coordinates, forces, body bytes and body state arrive in the other shared-memory stage, tile i+2's per-body
+// offsets and first slots in a small ring, and tile i+3's descriptor - so no request ever waits for a load it depends on
+// (the one-CTA-per-tile version of this kernel spent its life in five dependent phases, and a request that looked every
+// atom up in atomLoc stalled on that load: ncu, 34 % of the samples; moving whole-body runs instead cost 27 % of the
+// executed instructions).  The atoms' array slots therefore travel with the per-body offsets, two tiles ahead.
+#ifndef RBK_P2L_MINBLOCKS
+#define RBK_P2L_MINBLOCKS 5                         // measured on config 4 (tile atoms x CTAs/SM): 256x5 0.272 ms/step, 256x6 0.292,
+#endif                                              // 384x4 0.285, 512x3 0.276; the shuffle-scan part2Kernel 0.279 - 0.291
+#ifndef RBK_P2L_THREADS
+#define RBK_P2L_THREADS 128
+#endif
+constexpr int kP2LThreads = RBK_P2L_THREADS;        // eight warps share a tile: the phases are chains of dependent fp64 /
+                                                    // shared-memory operations and need warps to hide them (32 per SM)
+constexpr int kP2LLanes = kP2LThreads/16;           // lanes per body in the reduction (16 bodies per pass)
+constexpr int kP2LStatePlanes = 15;                 // q4 p3 pi4 invm invI3
+struct Part2LargeLayout {                           // byte offsets inside one stage / the CTA's shared memory
+    int f, st, key, stageBytes, acc, ring, ringBytes, meta, total;
+};
+__host__ __device__ inline Part2LargeLayout part2LargeLayout(int NB) {
+    constexpr int A = kLargeBodyTileAtoms;
+    Part2LargeLayout L;
+    L.f = 3*A*8;                                    // d[3][A] sits at offset 0
+    L.st = L.f + 3*A*8;
+    L.key = L.st + kP2LStatePlanes*NB*8;
+    L.stageBytes = (L.key + A + 16 + 127) & ~127;
+    L.acc = 2*L.stageBytes;
+    L.ring = L.acc + 6*NB*8;                        // 3 x { int loc[NB + 4]; int slot[A]; }
+    L.ringBytes = (NB + 4 + A)*4;
+    L.meta = (L.ring + 3*L.ringBytes + 15) & ~15;   // int4[4]
+    L.total = L.meta + 4*16;
+    return L;
+}
+
+template <bool NATIVE>
+__global__ void __launch_bounds__(kP2LThreads, RBK_P2L_MINBLOCKS) part2LargeKernel(const DeviceSystem S, const double dt, const AtomView pos,
+                                                                             const AtomView vel, const AtomView force) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    constexpr int A = kLargeBodyTileAtoms;
+    constexpr int kBlock = kP2LThreads, kWarps = kP2LThreads/32;          // shadow the file-level constants inside this kernel
+    const int NB = S.stageBodies;
+    const Part2LargeLayout L = part2LargeLayout(NB);
+    double* const sAcc = reinterpret_cast<double*>(smemRaw + L.acc);      // [6][NB] (F, tau), later (v_cm, omega_space)
+    int4* const sMeta = reinterpret_cast<int4*>(smemRaw + L.meta);        // ring of 4 tile descriptors
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, numTiles = S.numTiles;
+    const size_t ld = S.bodyStride, as = S.atomStride;
+    const int* const atomLoc = S.atomLoc;
+
+    auto ringLoc = [&](int i) { return reinterpret_cast<int*>(smemRaw + L.ring + (i % 3)*L.ringBytes); };
+    auto ringSlot = [&](int i) { return ringLoc(i) + NB + 4; };
+    // per-body atom offsets and per-atom array slots of this CTA's i-th tile
+    auto requestBodies = [&](int i) {
+        const int4 m = sMeta[i & 3];
+        if (tid < m.y) cpAsync4(ringLoc(i) + tid, S.loc + m.x + tid);
+        if (atomLoc != nullptr && m.w <= A) {
+            const int* g = atomLoc + S.numFree + m.z;
+            int* r = ringSlot(i);
+            for (int j = tid; j < m.w; j += kBlock) cpAsync4(r + j, g + j);
+        }
+    };
+    // coordinates, forces, body bytes and body state of this CTA's i-th tile
+    auto requestData = [&](int i, int stage) {
+        const int4 m = sMeta[i & 3];
+        unsigned char* T = smemRaw + stage*L.stageBytes;
+        double* sD = reinterpret_cast<double*>(T);
+        double* sF = reinterpret_cast<double*>(T + L.f);
+        double* sSt = reinterpret_cast<double*>(T + L.st);
+        const int nb = m.y, a0 = m.z, na = m.w;
+        if (tid < nb) {
+            const double* g = S.state + (size_t) (m.x + tid);
+#pragma unroll
+            for (int k = 0; k < 4; k++) cpAsync8(&sSt[k*NB + tid], g + (PL_Q + k)*ld);
+#pragma unroll
+            for (int k = 0; k < 3; k++) cpAsync8(&sSt[(4 + k)*NB + tid], g + (PL_P + k)*ld);
+#pragma unroll
+            for (int k = 0; k < 4; k++) cpAsync8(&sSt[(7 + k)*NB + tid], g + (PL_PI + k)*ld);
+            cpAsync8(&sSt[11*NB + tid], g + PL_INVM*ld);
+#pragma unroll
+            for (int k = 0; k < 3; k++) cpAsync8(&sSt[(12 + k)*NB + tid], g + (PL_INVI + k)*ld);
+        }
+        if (na > A) return;                                      // one body larger than a tile: its atoms are read in place
+        for (int j = tid; j < na; j += kBlock) {
+            const double* g = S.dxyz + (size_t) (a0 + j);
+            cpAsync8(&sD[j], g);
+            cpAsync8(&sD[A + j], g + as);
+            cpAsync8(&sD[2*A + j], g + 2*as);
+        }
+        const int* slots = ringSlot(i);
+        for (int j = tid; j < na; j += kBlock) {
+            const int slot = atomLoc != nullptr ? slots[j] : S.numFree + a0 + j;
+            if (NATIVE) {
+                const double* fp = force.p + slot*force.sa;
+                cpAsync8(&sF[3*j], fp);
+                cpAsync8(&sF[3*j + 1], fp + force.sc);
+                cpAsync8(&sF[3*j + 2], fp + 2*force.sc);
+            }
+            else {
+                const d3 f = loadAtom<false>(force, slot);
+                sF[3*j] = f.x; sF[3*j + 1] = f.y; sF[3*j + 2] = f.z;
+            }
+        }
+        const int first = a0 & ~3;                               // 4-byte granules of the byte array
+        for (int w = tid; 4*w < a0 + na - first; w += kBlock) cpAsync4(T + L.key + 4*w, S.localBody + first + 4*w);
+    };
+
+    const int tile0 = blockIdx.x;
+    if (tile0 >= numTiles) return;
+    if (tid < 3 && tile0 + tid*G < numTiles) sMeta[tid] = S.tileMeta[tile0 + tid*G];
+    __syncthreads();
+    requestBodies(0);
+    if (tile0 + G < numTiles) requestBodies(1);
+    cpCommit();
+    cpWait<0>();
+    __syncthreads();
+    requestData(0, 0);
+    cpCommit();
+    int it = 0;
+    for (int tile = tile0; tile < numTiles; tile += G, it++) {
+        const int cur = it & 1;
+        cpWait<0>();                                             // tile `it`, the bodies of it+1 and the descriptor of it+2 have landed
+        __syncthreads();
+        const int4 m = sMeta[it & 3];
+        if (tile + G < numTiles) requestData(it + 1, cur ^ 1);
+        if (tile + 2*G < numTiles) requestBodies(it + 2);
+        if (tid == 0 && tile + 3*G < numTiles) cpAsync16(&sMeta[(it + 3) & 3], S.tileMeta + tile + 3*G);
+        cpCommit();
+
+        unsigned char* T = smemRaw + cur*L.stageBytes;
+        double* const sD = reinterpret_cast<double*>(T);          // [3][A] body-frame coordinates, then the arms delta
+        double* const sF = reinterpret_cast<double*>(T + L.f);    // [3*A] forces xyzxyz...
+        double* const sSt = reinterpret_cast<double*>(T + L.st);  // [15][NB]
+        const int* const sLoc = ringLoc(it);
+        const int* const sSlot = ringSlot(it);
+        const unsigned char* const sKey = T + L.key + (m.z & 3);
+        const int nb = m.y, a0 = m.z, na = m.w;
+
+        if (na > A) {                                            // ---- one body larger than a tile: CTA-wide reduction
+            double* s = S.state + (size_t) m.x;
+            const d4 q = {sSt[0], sSt[NB], sSt[2*NB], sSt[3*NB]};
+            double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int a = a0 + tid; a < a0 + na; a += kBlock) {
+                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+                const d3 f = loadAtom<NATIVE>(force, atomSlot(S, S.numFree + a));
+                const d3 t = cross(bodyToSpace(q, d), f);
+                v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], off);
+            if (lane == 0)
+#pragma unroll
+                for (int k = 0; k < 6; k++) sF[warp*6 + k] = v[k];
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll
+                for (int w = 1; w < kWarps; w++)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) v[k] += sF[w*6 + k];
+                const d3 F = {v[0], v[1], v[2]}, tau = {v[3], v[4], v[5]};
+                d3 p = {sSt[4*NB], sSt[5*NB], sSt[6*NB]};
+                d4 pi = {sSt[7*NB], sSt[8*NB], sSt[9*NB], sSt[10*NB]};
+                d3 vcm, om;
+                bodyPart2(dt, F, tau, sSt[11*NB], d3{sSt[12*NB], sSt[13*NB], sSt[14*NB]}, q, p, pi, vcm, om);
+                storePlane3(s + PL_P*ld, ld, p);
+                storePlane4(s + PL_PI*ld, ld, pi);
+                storePlane3(s + PL_F*ld, ld, F);
+                storePlane3(s + PL_TAU*ld, ld, tau);
+                sD[0] = vcm.x; sD[1] = vcm.y; sD[2] = vcm.z; sD[3] = om.x; sD[4] = om.y; sD[5] = om.z;
+            }
+            __syncthreads();
+            const d3 vcm = {sD[0], sD[1], sD[2]}, om = {sD[3], sD[4], sD[5]};
+            for (int a = a0 + tid; a < a0 + na; a += kBlock) {
+                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+                storeAtom<NATIVE>(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- B: thread per atom: arms delta = A^T(q) d, in place
+        for (int j = tid; j < na; j += kBlock) {
+            {
+                const int k = sKey[j];
+                const d4 q = {sSt[k], sSt[NB + k], sSt[2*NB + k], sSt[3*NB + k]};
+                const d3 delta = bodyToSpace(q, d3{sD[j], sD[A + j], sD[2*A + j]});
+                sD[j] = delta.x; sD[A + j] = delta.y; sD[2*A + j] = delta.z;
+            }
+        }
+        __syncthreads();
+
+        // ---- B2: kP2LLanes lanes per body: lane g sums atoms g, g+kP2LLanes, ... of its body in order, then a fixed butterfly
+        constexpr int kLanes = kP2LLanes;
+        for (int b0 = 0; b0 < nb; b0 += kBlock/kLanes) {
+            if (b0 + warp*(32/kLanes) >= nb) break;              // warp-uniform: none of this warp's four bodies exists
+            const int b = b0 + tid/kLanes, g = tid % kLanes;
+            double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (b < nb) {
+                const int j1 = (b + 1 < nb ? sLoc[b + 1] : a0 + na) - a0;
+                for (int j = sLoc[b] - a0 + g; j < j1; j += kLanes) {
+                    const d3 delta = {sD[j], sD[A + j], sD[2*A + j]};
+                    const d3 f = {sF[3*j], sF[3*j + 1], sF[3*j + 2]};
+                    const d3 t = cross(delta, f);
+                    v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
+                }
+            }
+#pragma unroll
+            for (int off = kLanes/2; off > 0; off >>= 1)
+#pragma unroll
+                for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], off);
+            if (b < nb && g == 0)
+#pragma unroll
+                for (int k = 0; k < 6; k++) sAcc[k*NB + b] = v[k];
+        }
+        __syncthreads();
+
+        if (tid < nb) {                                          // ---- C: thread per body, second kick
+            const d3 F = {sAcc[tid], sAcc[NB + tid], sAcc[2*NB + tid]};
+            const d3 tau = {sAcc[3*NB + tid], sAcc[4*NB + tid], sAcc[5*NB + tid]};
+            const d4 q = {sSt[tid], sSt[NB + tid], sSt[2*NB + tid], sSt[3*NB + tid]};
+            d3 p = {sSt[4*NB + tid], sSt[5*NB + tid], sSt[6*NB + tid]};
+            d4 pi = {sSt[7*NB + tid], sSt[8*NB + tid], sSt[9*NB + tid], sSt[10*NB + tid]};
+            const double invm = sSt[11*NB + tid];
+            const d3 invI = {sSt[12*NB + tid], sSt[13*NB + tid], sSt[14*NB + tid]};
+            d3 vcm, om;
+            bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
+            double* s = S.state + (size_t) (m.x + tid);
+            storePlane3(s + PL_P*ld, ld, p);
+            storePlane4(s + PL_PI*ld, ld, pi);
+            storePlane3(s + PL_F*ld, ld, F);
+            storePlane3(s + PL_TAU*ld, ld, tau);
+            sAcc[tid] = vcm.x; sAcc[NB + tid] = vcm.y; sAcc[2*NB + tid] = vcm.z;
+            sAcc[3*NB + tid] = om.x; sAcc[4*NB + tid] = om.y; sAcc[5*NB + tid] = om.z;
+        }
+        __syncthreads();
+
+        for (int j = tid; j < na; j += kBlock) {                 // ---- D: thread per atom, velocities
+            {
+                const int k = sKey[j];
+                const d3 delta = {sD[j], sD[A + j], sD[2*A + j]};
+                const d3 vcm = {sAcc[k], sAcc[NB + k], sAcc[2*NB + k]};
+                const d3 om = {sAcc[3*NB + k], sAcc[4*NB + k], sAcc[5*NB + k]};
+                storeAtom<NATIVE>(vel, atomLoc != nullptr ? sSlot[j] : S.numFree + a0 + j, atomVelocity(vcm, om, delta));
+            }
+        }
+        __syncthreads();                                         // the stage, the ring slot and sAcc are reused
+    }
+    cpWait<0>();
+}
+
+template <bool NATIVE>
+cudaError_t launchPart2Large(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    const size_t smem = (size_t) part2LargeLayout(S.stageBodies).total;
+    static size_t configured[kMaxDevices] = {};                // the attribute is per device; grows with the largest system seen
+    static int perSM[kMaxDevices] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    const bool cached = device >= 0 && device < kMaxDevices;
+    if (!cached || configured[device] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(part2LargeKernel<NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        if (cached) { configured[device] = smem; perSM[device] = 0; }
+    }
+    int blocks = cached ? perSM[device] : 0;
+    if (blocks == 0) {                                           // persistent CTAs: one full wave, whatever fits
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2LargeKernel<NATIVE>, kP2LThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (blocks < 1) blocks = 1;
+        if (cached) perSM[device] = blocks;
+    }
+    const int resident = S.numSMs*blocks;
+    part2LargeKernel<NATIVE><<<S.numTiles < resident ? S.numTiles : resident, kP2LThreads, smem, st>>>(S, dt, pos, vel, force);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -914,25 +1227,35 @@ cudaError_t launchPart1Delta(const DeviceSystem& S, double dt, AtomView pos, Ato
     return nativeIO(pos, vel, force) ? launchPart1Formats<true>(S, dt, pos, vel, force, false, st) : launchPart1Formats<false>(S, dt, pos, vel, force, false, st);
 }
 
+namespace {
+template <bool NATIVE>
+cudaError_t launchPart2Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st) {
+    if (freeAtoms) launchFree<2, NATIVE>(S, dt, pos, vel, force, st);
+#ifndef RBK_P2_OLD
+    if (S.numTiles > 0 && S.splitPart1) return launchPart2Large<NATIVE>(S, dt, pos, vel, force, st);
+#endif
+    if (S.numTiles > 0) part2Kernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, dt, pos, vel, force);
+    return cudaGetLastError();
+}
+} // namespace
+
 cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
-    if (nativeIO(pos, vel, force)) {
-        launchFree<2, true>(S, dt, pos, vel, force, st);
-        if (S.numTiles > 0) part2Kernel<true><<<S.numTiles, kBlock, 0, st>>>(S, dt, pos, vel, force);
-    }
-    else {
-        launchFree<2, false>(S, dt, pos, vel, force, st);
-        if (S.numTiles > 0) part2Kernel<false><<<S.numTiles, kBlock, 0, st>>>(S, dt, pos, vel, force);
-    }
-    return cudaGetLastError();
+    return nativeIO(pos, vel, force) ? launchPart2Formats<true>(S, dt, pos, vel, force, true, st)
+                                     : launchPart2Formats<false>(S, dt, pos, vel, force, true, st);
 }
 
 cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
     // the one-pass kernel stages fp64 forces with cp.async; other formats / large bodies take the two kernels
     if (!S.fusable || !nativeIO(pos, vel, force)) {
-        cudaError_t e = launchPart2(S, dt, pos, vel, force, st);
-        return e != cudaSuccess ? e : launchPart1(S, dt, pos, vel, force, st);
+        // the free atoms still take both halves in ONE launch (same arithmetic, one pass over their data)
+        const bool native = nativeIO(pos, vel, force);
+        if (native) launchFree<3, true>(S, dt, pos, vel, force, st); else launchFree<3, false>(S, dt, pos, vel, force, st);
+        if (S.numTiles == 0) return cudaGetLastError();
+        cudaError_t e = native ? launchPart2Formats<true>(S, dt, pos, vel, force, false, st) : launchPart2Formats<false>(S, dt, pos, vel, force, false, st);
+        if (e != cudaSuccess) return e;
+        return native ? launchPart1Formats<true>(S, dt, pos, vel, force, false, st) : launchPart1Formats<false>(S, dt, pos, vel, force, false, st);
     }
     const bool small = S.maxBodySize <= kSmallBody;
     if (S.rotationMode == 0) return small ? launchFused<true, true>(S, dt, pos, vel, force, st) : launchFused<true, false>(S, dt, pos, vel, force, st);
