@@ -1,0 +1,83 @@
+"""GPU tests of the large-body bucket (mean body size > 8 atoms): part2LargeKernel (persistent cp.async pipeline, arms
+staged in shared memory, per-body sums in atom order) and the unrolled atomPositionKernel, against the CPU oracle.
+
+Cases the mixed-system tests elsewhere do not reach: no free atoms at all (identity atom map: the kernels compute slots
+instead of reading atomLoc), runs of tiny bodies next to big ones (many bodies per 256-atom tile: several passes of the
+8-lanes-per-body reduction and a large per-tile body stage), bodies exactly at / just over the tile capacity (the
+CTA-wide single-body path), SoA planes, permuted atoms, and both stepping protocols (part1/part2 and part2_part1).
+Reference behaviour: RigidBody::forceAndTorque / updateAtomicVelocities / updateAtomicPositions
+(openmmapi/src/RigidBody.cpp:148-183) driven as in ReferenceRigidBodyKernels.cpp:82-108.
+"""
+import numpy as np
+import pytest
+
+import common
+from common import GpuStepper
+from oracle.checkers import CpuStepper
+from test_gpu_parity import compare_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(sizes, n_free, seed):
+    """Bodies of the given sizes (Gaussian clouds) followed by n_free free atoms; labels 1..nb."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    sizes = np.asarray(sizes)
+    body = np.concatenate([np.repeat(np.arange(1, len(sizes) + 1), sizes), np.zeros(n_free, np.int64)]).astype(np.int32)
+    n = body.shape[0]
+    centres = rng.uniform(0, 30, (len(sizes) + 1, 3))
+    R = centres[np.where(body > 0, body - 1, len(sizes))] + rng.standard_normal((n, 3)) * 0.2
+    if n_free:
+        R[body == 0] = rng.uniform(0, 30, (n_free, 3))
+    return {"bodyIndices": body, "masses": rng.uniform(1.0, 16.0, n), "R": R, "V": rng.standard_normal((n, 3)) * 0.3,
+            "F": rng.standard_normal((n, 3)) * 100.0, "charges": rng.uniform(-0.5, 0.5, n)}
+
+
+def _run_pair(sysd, mode, layout, shuffle, fused, steps=3, dt=0.001, tol=2e-9):
+    o = CpuStepper("oracle", sysd["bodyIndices"], sysd["masses"], mode)
+    s = GpuStepper(sysd["bodyIndices"], sysd["masses"], mode, layout=layout, shuffle=shuffle)
+    s.fused = fused
+    for st in (o, s):
+        common.init_like_reference(st, sysd, tether=True)
+        st.step(dt, steps)
+    R, V, _ = o.get_state()
+    compare_state(("large", mode, layout, shuffle, fused), s, R, V, o.kinetic(), o.bodies(), tol=tol)
+    out = s.get_state()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+@pytest.mark.parametrize("layout", ["vec3", "soa"])
+def test_identity_atom_map_no_free_atoms(mode, layout):
+    rng = np.random.Generator(np.random.Philox(key=301))
+    sysd = _system(rng.integers(9, 61, size=500), 0, seed=302)
+    _run_pair(sysd, mode, layout, False, fused=True)
+    _run_pair(sysd, mode, layout, False, fused=False)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_many_tiny_bodies_between_big_ones(shuffle):
+    """Mean size > 8 but long runs of 3-atom bodies: up to 85 bodies in one 256-atom tile."""
+    sizes = ([3] * 170 + [200] * 12 + [4, 5, 3, 60, 3, 3, 97]) * 3
+    sysd = _system(sizes, 40, seed=303)
+    a = _run_pair(sysd, 0, "vec3", shuffle, fused=True)
+    b = _run_pair(sysd, 0, "vec3", shuffle, fused=False)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])      # same kernels either way: bit-identical
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_bodies_at_and_over_the_tile_capacity(mode):
+    """255/256/257-atom bodies (the last is alone in its tile and reduced by the whole CTA), a 513- and a 3000-atom body."""
+    sizes = [255, 256, 257, 9, 513, 31, 3000, 12, 256, 10]
+    sysd = _system(sizes, 5, seed=304)
+    _run_pair(sysd, mode, "vec3", True, fused=True, dt=0.0005)
+    _run_pair(sysd, mode, "soa", False, fused=False, dt=0.0005)
+
+
+def test_bit_reproducible_large_bodies():
+    rng = np.random.Generator(np.random.Philox(key=305))
+    sysd = _system(rng.integers(3, 61, size=800), 300, seed=306)
+    a = _run_pair(sysd, 0, "vec3", True, fused=True)
+    b = _run_pair(sysd, 0, "vec3", True, fused=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
