@@ -322,6 +322,12 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: non-finite kinetic energy after the timed region")
 
     value = world * nB * args.steps / (ms * 1e-3)
+    # kernels launched inside the timed region (librbk's launch structure, rbk_kernels.cu launchPart1 / launchPart2 /
+    # launchPart2Part1): free atoms have their own launch; large bodies split part 1 into rotation + position kernels
+    large, fr = nB > 0 and nA > 8 * nB, 1 if nF > 0 else 0
+    per_p1, per_p2 = fr + (2 if large else 1 if nB else 0), fr + (1 if nB else 0)
+    per_pp = fr + (3 if large else 1 if nB else 0)
+    gpu_launches = args.steps * (per_p1 + per_p2) if args.no_fuse else per_p1 + (args.steps - 1) * per_pp + per_p2
     bytes1 = P1_BODY * nB + P1_ATOM * nA + FREE_P1 * nF
     bytes2 = P2_BODY * nB + P2_ATOM * nA + FREE_P2 * nF
     peak, peak_src = measured_peak()
@@ -331,7 +337,7 @@ def run_b200_arm(args):
     ach = dom[1] / (dom[2] * 1e-3) / 1e9
     step_ach = (bytes1 + bytes2) / ((ms / args.steps) * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"rbk::{dom[0]}Kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "bound": "hbm", "kernel": f"rbk::{'part2Large' if large and dom[0] == 'part2' else dom[0]}Kernel" + (" (+ freeAtomsKernel of the same call)" if fr and tf is None else ""), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
         "traffic": ncu_traffic(f"{dom[0]}_mode{args.mode}_{args.workload}{args.molecules}"),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[2],
         "kernels": {"part1": {"ms": t1, "bytes": bytes1, "GBps": bytes1 / (t1 * 1e-3) / 1e9},
@@ -385,7 +391,7 @@ def run_b200_arm(args):
                        "layout": args.layout, "dt_ps": DT, "bodies": nB, "body_atoms": nA, "free_atoms": nF,
                        "l2": "no flush needed: the per-step working set (state + atoms, >500 MB at 1M waters) exceeds the 126 MB L2"},
             "ns_per_day": (args.steps / (ms * 1e-3)) * DT * 1e-3 * 86400.0,
-            "clocks": clk, "e2e": e2e, "gpu_launches": launches * (2 if (nA > 8 * nB and not args.no_fuse) else 1) if not args.no_fuse else (3 if nA > 8 * nB else 2) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
             "kinetic_energy_kJmol": {"start": [float(ke_start[0]), float(ke_start[1])], "end": [float(ke[0]), float(ke[1])],
                                      "note": "translational, rotational; the workload stays at its initial ~300 K state"},
         }
