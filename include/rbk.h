@@ -113,7 +113,10 @@ int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const 
  * Bit-identical to calling rbk_part2 then rbk_part1 with the same arguments; the body state makes one round trip
  * through HBM instead of two and the body-frame coordinates are read once.  On return `vel` holds the velocities at the
  * end of step k and `pos` the positions after Part 1 of step k+1 (exactly the state the reference is in when it
- * evaluates forces). */
+ * evaluates forces).  Stream semantics: everything is ordered after the work already queued on `stream`, and `stream`
+ * continues only when the whole call's work is done; for systems of large bodies WITH free atoms the free atoms are
+ * integrated on a second stream owned by the handle, forked from and joined back to `stream` with events (no host
+ * synchronisation; the pattern is legal under stream capture). */
 int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force,
                     int layout, long long stride, void* stream);
 

@@ -74,6 +74,7 @@ struct rbk_system {
     double* mVel = nullptr;
     double* mForce = nullptr;
     double* mForce2 = nullptr;       // second force mirror: new forces land here while part 1 still reads the old ones
+    rbk::SideStream side{nullptr, nullptr, nullptr};       // free atoms of large-body steps (created on first use)
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaEvent_t evStart = nullptr, evForces = nullptr, evPart1 = nullptr, evPositions = nullptr;
     bool mirrorsLoaded = false;
@@ -83,6 +84,9 @@ struct rbk_system {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter);
         cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
+        if (side.stream) cudaStreamDestroy(side.stream);
+        if (side.fork) cudaEventDestroy(side.fork);
+        if (side.join) cudaEventDestroy(side.join);
         if (h2dStream) cudaStreamDestroy(h2dStream);
         if (d2hStream) cudaStreamDestroy(d2hStream);
         for (cudaEvent_t e : {evStart, evForces, evPart1, evPositions}) if (e) cudaEventDestroy(e);
@@ -561,7 +565,16 @@ int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const 
         RBK_CUDA(stepPart1(sys, dt, p, v, f, nullptr, (cudaStream_t) stream));
         return RBK_OK;
     }
-    RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, (cudaStream_t) stream));
+    const rbk::SideStream* side = nullptr;
+    if (sys->dev.splitPart1 && sys->dev.numFree > 0 && sys->dev.numTiles > 0) {
+        if (!sys->side.stream) {
+            RBK_CUDA(cudaStreamCreateWithFlags(&sys->side.stream, cudaStreamNonBlocking));
+            RBK_CUDA(cudaEventCreateWithFlags(&sys->side.fork, cudaEventDisableTiming));
+            RBK_CUDA(cudaEventCreateWithFlags(&sys->side.join, cudaEventDisableTiming));
+        }
+        side = &sys->side;
+    }
+    RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, (cudaStream_t) stream, side));
     return RBK_OK;
 }
 

@@ -79,8 +79,15 @@ cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView
 // free-atom constraint hooks: delta = (v + f invm dt/2) dt for every free atom; part 1 that advances free atoms by delta
 cudaError_t launchFreeDelta(const DeviceSystem& S, double dt, AtomView vel, AtomView force, AtomView delta, cudaStream_t st);
 cudaError_t launchPart1Delta(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, AtomView delta, cudaStream_t st);
+// A second stream of the system's own plus the two events that fork it from / join it to the caller's stream: large-body
+// steps integrate the free atoms there, next to the body kernels (disjoint atoms, no data dependence).
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
 // part 2 of one step immediately followed by part 1 of the next (identical results, one pass over the data)
-cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
+cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
+                             const SideStream* side = nullptr);
 // partial: scratch of 2*kKineticBlocks doubles; counter: zero-initialised unsigned; out: 2 doubles (device)
 constexpr int kKineticBlocks = 592;    // 148 SMs x 4
 // GPU-side body build (rbk_build.cu): geometry and/or dynamics of every body from the caller's atom arrays.

@@ -412,8 +412,13 @@ __host__ __device__ inline Part2LargeLayout part2LargeLayout(int NB) {
     return L;
 }
 
+#ifdef RBK_P2L_MAXNREG
+#define RBK_P2L_REGCAP __maxnreg__(RBK_P2L_MAXNREG)
+#else
+#define RBK_P2L_REGCAP __launch_bounds__(kP2LThreads, RBK_P2L_MINBLOCKS)
+#endif
 template <bool NATIVE>
-__global__ void __launch_bounds__(kP2LThreads, RBK_P2L_MINBLOCKS) part2LargeKernel(const DeviceSystem S, const double dt, const AtomView pos,
+__global__ void RBK_P2L_REGCAP part2LargeKernel(const DeviceSystem S, const double dt, const AtomView pos,
                                                                              const AtomView vel, const AtomView force) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     constexpr int A = kLargeBodyTileAtoms;
@@ -1042,6 +1047,11 @@ __global__ void __launch_bounds__(256) freeAtomsKernel(const DeviceSystem S, con
     storeAtom<NATIVE>(vel, gi, v);
 }
 
+#ifndef RBK_SIDE_FREE_THREADS
+#define RBK_SIDE_FREE_THREADS 64
+#endif
+constexpr int kSideFreeThreads = RBK_SIDE_FREE_THREADS;                // CTA size of the free-atom launch that shares the SMs with the body kernels
+
 template <int PHASE, bool NATIVE>
 void launchFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     if (S.numFree > 0) freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
@@ -1244,17 +1254,37 @@ cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView
                                      : launchPart2Formats<false>(S, dt, pos, vel, force, true, st);
 }
 
-cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
+                             const SideStream* side) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
     // the one-pass kernel stages fp64 forces with cp.async; other formats / large bodies take the two kernels
     if (!S.fusable || !nativeIO(pos, vel, force)) {
-        // the free atoms still take both halves in ONE launch (same arithmetic, one pass over their data)
+        // the free atoms still take both halves in ONE launch (same arithmetic, one pass over their data).  Large-body
+        // systems: that launch goes to the side stream, AFTER the persistent part2LargeKernel has taken its SMs - the
+        // free atoms' small CTAs run in the registers the body kernels leave unused and in their tails (disjoint atoms,
+        // no data dependence); the caller's stream continues when both are done.
         const bool native = nativeIO(pos, vel, force);
-        if (native) launchFree<3, true>(S, dt, pos, vel, force, st); else launchFree<3, false>(S, dt, pos, vel, force, st);
+        const bool overlap = side != nullptr && side->stream != nullptr && S.numFree > 0 && S.numTiles > 0 && S.splitPart1;
+        if (overlap) {
+            cudaError_t e = cudaEventRecord(side->fork, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+            if (e != cudaSuccess) return e;
+        }
+        else if (native) launchFree<3, true>(S, dt, pos, vel, force, st);
+        else launchFree<3, false>(S, dt, pos, vel, force, st);
         if (S.numTiles == 0) return cudaGetLastError();
         cudaError_t e = native ? launchPart2Formats<true>(S, dt, pos, vel, force, false, st) : launchPart2Formats<false>(S, dt, pos, vel, force, false, st);
         if (e != cudaSuccess) return e;
-        return native ? launchPart1Formats<true>(S, dt, pos, vel, force, false, st) : launchPart1Formats<false>(S, dt, pos, vel, force, false, st);
+        if (overlap) {
+            const int blocks = (S.numFree + kSideFreeThreads - 1)/kSideFreeThreads;
+            if (native) freeAtomsKernel<3, true><<<blocks, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
+            else freeAtomsKernel<3, false><<<blocks, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
+            e = cudaEventRecord(side->join, side->stream);
+            if (e != cudaSuccess) return e;
+        }
+        e = native ? launchPart1Formats<true>(S, dt, pos, vel, force, false, st) : launchPart1Formats<false>(S, dt, pos, vel, force, false, st);
+        if (e != cudaSuccess) return e;
+        return overlap ? cudaStreamWaitEvent(st, side->join, 0) : cudaSuccess;
     }
     const bool small = S.maxBodySize <= kSmallBody;
     if (S.rotationMode == 0) return small ? launchFused<true, true>(S, dt, pos, vel, force, st) : launchFused<true, false>(S, dt, pos, vel, force, st);
