@@ -385,14 +385,12 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
 // (the one-CTA-per-tile version of this kernel spent its life in five dependent phases, and a request that looked every
 // atom up in atomLoc stalled on that load: ncu, 34 % of the samples; moving whole-body runs instead cost 27 % of the
 // executed instructions).  The atoms' array slots therefore travel with the per-body offsets, two tiles ahead.
-#ifndef RBK_P2L_MINBLOCKS
-#define RBK_P2L_MINBLOCKS 5                         // measured on config 4 (tile atoms x CTAs/SM): 256x5 0.272 ms/step, 256x6 0.292,
-#endif                                              // 384x4 0.285, 512x3 0.276; the shuffle-scan part2Kernel 0.279 - 0.291
+// Five CTAs per SM (shared memory: two 256-atom stages + rings, ~38 KB each).  Measured on config 4 (tile atoms x CTAs/SM):
+// 256x5 0.272 ms/step, 256x6 0.292, 384x4 0.285, 512x3 0.276; the shuffle-scan part2Kernel 0.279 - 0.291.
 #ifndef RBK_P2L_THREADS
 #define RBK_P2L_THREADS 128
 #endif
 constexpr int kP2LThreads = RBK_P2L_THREADS;        // (256 threads per tile measured slower: 0.346 vs 0.313 ms/step on config 4)
-constexpr int kP2LLanes = kP2LThreads/16;           // lanes per body in the reduction (16 bodies per pass)
 constexpr int kP2LStatePlanes = 15;                 // q4 p3 pi4 invm invI3
 struct Part2LargeLayout {                           // byte offsets inside one stage / the CTA's shared memory
     int f, st, key, stageBytes, acc, ring, ringBytes, meta, total;
@@ -412,11 +410,13 @@ __host__ __device__ inline Part2LargeLayout part2LargeLayout(int NB) {
     return L;
 }
 
-#ifdef RBK_P2L_MAXNREG
-#define RBK_P2L_REGCAP __maxnreg__(RBK_P2L_MAXNREG)
-#else
-#define RBK_P2L_REGCAP __launch_bounds__(kP2LThreads, RBK_P2L_MINBLOCKS)
+// 88 registers (ptxas would take 94 of the 102 that five CTAs allow): 5 x 128 x 88 leaves 9216 registers per SM, room
+// for two of the 64-thread free-atom CTAs that run on the side stream next to this kernel (config 4: 0.264 -> 0.254 ms/step;
+// 80 registers slow this kernel down: 0.290).
+#ifndef RBK_P2L_MAXNREG
+#define RBK_P2L_MAXNREG 88
 #endif
+#define RBK_P2L_REGCAP __maxnreg__(RBK_P2L_MAXNREG)
 template <bool NATIVE>
 __global__ void RBK_P2L_REGCAP part2LargeKernel(const DeviceSystem S, const double dt, const AtomView pos,
                                                                              const AtomView vel, const AtomView force) {
@@ -575,23 +575,28 @@ __global__ void RBK_P2L_REGCAP part2LargeKernel(const DeviceSystem S, const doub
         }
         __syncthreads();
 
-        // ---- B2: kP2LLanes lanes per body: lane g sums atoms g, g+kP2LLanes, ... of its body in order, then a fixed butterfly
-        constexpr int kLanes = kP2LLanes;
-        for (int b0 = 0; b0 < nb; b0 += kBlock/kLanes) {
-            if (b0 + warp*(32/kLanes) >= nb) break;              // warp-uniform: none of this warp's four bodies exists
-            const int b = b0 + tid/kLanes, g = tid % kLanes;
+        // ---- B2: a lane group per body - 16 lanes when the tile holds at most kBlock/16 bodies (the usual case for large
+        // bodies), else 8: lane g sums atoms g, g+lanes, ... of its body in order, then a fixed butterfly over the group
+        const int lg = nb <= kBlock/16 ? 4 : 3, lanes = 1 << lg;
+        for (int b0 = 0; b0 < nb; b0 += kBlock >> lg) {
+            if (b0 + ((warp*32) >> lg) >= nb) break;             // warp-uniform: none of this warp's bodies exists
+            const int b = b0 + (tid >> lg), g = tid & (lanes - 1);
             double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             if (b < nb) {
                 const int j1 = (b + 1 < nb ? sLoc[b + 1] : a0 + na) - a0;
-                for (int j = sLoc[b] - a0 + g; j < j1; j += kLanes) {
+                for (int j = sLoc[b] - a0 + g; j < j1; j += lanes) {
                     const d3 delta = {sD[j], sD[A + j], sD[2*A + j]};
                     const d3 f = {sF[3*j], sF[3*j + 1], sF[3*j + 2]};
                     const d3 t = cross(delta, f);
                     v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
                 }
             }
+            if (lg == 4) {                                       // warp-uniform
 #pragma unroll
-            for (int off = kLanes/2; off > 0; off >>= 1)
+                for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], 8);
+            }
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1)
 #pragma unroll
                 for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], off);
             if (b < nb && g == 0)
