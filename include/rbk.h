@@ -115,7 +115,7 @@ int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const 
  * end of step k and `pos` the positions after Part 1 of step k+1 (exactly the state the reference is in when it
  * evaluates forces).  Stream semantics: everything is ordered after the work already queued on `stream`, and `stream`
  * continues only when the whole call's work is done; for systems of large bodies WITH free atoms the free atoms are
- * integrated on a second stream owned by the handle, forked from and joined back to `stream` with events (no host
+ * integrated (here and in rbk_part1 / rbk_part2) on a second stream owned by the handle, forked from and joined back to `stream` with events (no host
  * synchronisation; the pattern is legal under stream capture). */
 int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force,
                     int layout, long long stride, void* stream);

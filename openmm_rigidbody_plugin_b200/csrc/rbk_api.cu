@@ -459,6 +459,25 @@ int rbk_set_atom_location(rbk_system* sys, const int* location, void* stream) {
 }
 
 namespace {
+// The handle's second stream (large-body systems with free atoms only; created on first use, NULL when it cannot be)
+const rbk::SideStream* sideStream(rbk_system* sys) {
+    if (!(sys->dev.splitPart1 && sys->dev.numFree > 0 && sys->dev.numTiles > 0)) return nullptr;
+    if (!sys->side.stream) {
+        rbk::SideStream s{nullptr, nullptr, nullptr};
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            if (s.stream) cudaStreamDestroy(s.stream);
+            if (s.fork) cudaEventDestroy(s.fork);
+            if (s.join) cudaEventDestroy(s.join);
+            cudaGetLastError();
+            return nullptr;                                  // the kernels then run in one stream
+        }
+        sys->side = s;
+    }
+    return &sys->side;
+}
+
 // Part 1 / Part 2 with the refined-energy passes around them when the diagnostics are on (rbk_refined.cu)
 cudaError_t stepPart1(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView f, const AtomView* delta, cudaStream_t st) {
     if (sys->refinedMode != RBK_REFINED_OFF) {
@@ -467,11 +486,11 @@ cudaError_t stepPart1(rbk_system* sys, double dt, AtomView p, AtomView v, AtomVi
             e = rbk::launchRefinedFree(sys->dev, sys->refined, dt, 1, v, f, st);
         if (e != cudaSuccess) return e;
     }
-    return delta ? rbk::launchPart1Delta(sys->dev, dt, p, v, f, *delta, st) : rbk::launchPart1(sys->dev, dt, p, v, f, st);
+    return delta ? rbk::launchPart1Delta(sys->dev, dt, p, v, f, *delta, st) : rbk::launchPart1(sys->dev, dt, p, v, f, st, sideStream(sys));
 }
 
 cudaError_t stepPart2(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView f, cudaStream_t st) {
-    cudaError_t e = rbk::launchPart2(sys->dev, dt, p, v, f, st);
+    cudaError_t e = rbk::launchPart2(sys->dev, dt, p, v, f, st, sideStream(sys));
     if (e != cudaSuccess || sys->refinedMode == RBK_REFINED_OFF) return e;
     e = rbk::launchRefinedBodies(sys->dev, sys->refined, dt, 2, st);
     if (e == cudaSuccess && sys->refinedMode == RBK_REFINED_ALL) e = rbk::launchRefinedFree(sys->dev, sys->refined, dt, 2, v, f, st);
@@ -565,16 +584,7 @@ int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const 
         RBK_CUDA(stepPart1(sys, dt, p, v, f, nullptr, (cudaStream_t) stream));
         return RBK_OK;
     }
-    const rbk::SideStream* side = nullptr;
-    if (sys->dev.splitPart1 && sys->dev.numFree > 0 && sys->dev.numTiles > 0) {
-        if (!sys->side.stream) {
-            RBK_CUDA(cudaStreamCreateWithFlags(&sys->side.stream, cudaStreamNonBlocking));
-            RBK_CUDA(cudaEventCreateWithFlags(&sys->side.fork, cudaEventDisableTiming));
-            RBK_CUDA(cudaEventCreateWithFlags(&sys->side.join, cudaEventDisableTiming));
-        }
-        side = &sys->side;
-    }
-    RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, (cudaStream_t) stream, side));
+    RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, (cudaStream_t) stream, sideStream(sys)));
     return RBK_OK;
 }
 

@@ -74,8 +74,11 @@ struct AtomView {
     void* aux;
 };
 
-cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
-cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st);
+struct SideStream;
+cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
+                        const SideStream* side = nullptr);
+cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
+                        const SideStream* side = nullptr);
 // free-atom constraint hooks: delta = (v + f invm dt/2) dt for every free atom; part 1 that advances free atoms by delta
 cudaError_t launchFreeDelta(const DeviceSystem& S, double dt, AtomView vel, AtomView force, AtomView delta, cudaStream_t st);
 cudaError_t launchPart1Delta(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, AtomView delta, cudaStream_t st);

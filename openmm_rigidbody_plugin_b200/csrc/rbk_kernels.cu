@@ -1062,6 +1062,22 @@ void launchFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, At
     if (S.numFree > 0) freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
 }
 
+// Free atoms of a large-body launch sequence on the side stream: fork before the body kernels are launched, the free-atom
+// kernel after the first (persistent) body kernel has taken its SMs, join when the sequence is complete.
+inline bool sideUsable(const DeviceSystem& S, const SideStream* side) {
+    return side != nullptr && side->stream != nullptr && S.numFree > 0 && S.numTiles > 0 && S.splitPart1;
+}
+inline cudaError_t sideFork(const SideStream* side, cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(side->fork, st);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(side->stream, side->fork, 0);
+}
+template <int PHASE, bool NATIVE>
+cudaError_t sideFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, const SideStream* side) {
+    freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + kSideFreeThreads - 1)/kSideFreeThreads, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
+    return cudaEventRecord(side->join, side->stream);
+}
+inline cudaError_t sideJoin(const SideStream* side, cudaStream_t st) { return cudaStreamWaitEvent(st, side->join, 0); }
+
 // Free-atom constraint hooks (the reference's freeAtomsDelta pre-pass, rigidbodyintegrator.cu:276-285, and the free-atom
 // loop of its integrateRigidBodyPart1, :303-312).  CONSUME = false: delta = (v + f invm dt/2) dt, nothing else is
 // touched, so the caller's constraint solver can correct the displacement.  CONSUME = true: the first half kick of the
@@ -1148,7 +1164,8 @@ __global__ void __launch_bounds__(kKinThreads) kineticKernel(const DeviceSystem 
 }
 
 template <bool EXACT, bool FUSED, bool NATIVE>
-cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st) {
+cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st,
+                               const SideStream* side = nullptr) {
     const size_t smem = FUSED ? sizeof(Part1Smem) : offsetof(Part1Smem, d);
     static bool configured[kMaxDevices] = {};                  // the attribute is per device
     int device = 0;
@@ -1159,11 +1176,21 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
         if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
     // persistent CTAs: one wave that fills every SM
-    if (freeAtoms) launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
+    const bool overlap = !FUSED && freeAtoms && sideUsable(S, side);
+    if (overlap) {
+        cudaError_t e = sideFork(side, st);
+        if (e != cudaSuccess) return e;
+    }
+    else if (freeAtoms) launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
     const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
     if (tiles > 0) part1Kernel<EXACT, FUSED, NATIVE><<<tiles < resident ? tiles : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
+    if (overlap) {
+        cudaError_t e = sideFree<1, NATIVE>(S, dt, pos, vel, force, side);
+        if (e != cudaSuccess) return e;
+    }
     if (!FUSED && S.numTiles > 0) atomPositionKernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, pos);
+    if (overlap) return sideJoin(side, st);
     return cudaGetLastError();
 }
 
@@ -1214,20 +1241,21 @@ bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
 }
 
 template <bool NATIVE>
-cudaError_t launchPart1Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st) {
+cudaError_t launchPart1Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st,
+                               const SideStream* side = nullptr) {
     const bool exact = S.rotationMode == 0, fused = !S.splitPart1;
     // exact rotation on water-like bodies, fp64 arrays: Part 1 alone through the TMA-staged one-warp-tile pipeline
     if (NATIVE && exact && S.numWarpTiles > 0)
         return launchFusedShape<true, true, 32, kWarpTileAtoms, 2, true>(S, dt, pos, vel, force, st, freeAtoms);
-    if (exact) return fused ? launchPart1Variant<true, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<true, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st);
-    return fused ? launchPart1Variant<false, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<false, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st);
+    if (exact) return fused ? launchPart1Variant<true, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<true, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st, side);
+    return fused ? launchPart1Variant<false, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<false, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st, side);
 }
 
 } // namespace
 
-cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+cudaError_t launchPart1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st, const SideStream* side) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
-    return nativeIO(pos, vel, force) ? launchPart1Formats<true>(S, dt, pos, vel, force, true, st) : launchPart1Formats<false>(S, dt, pos, vel, force, true, st);
+    return nativeIO(pos, vel, force) ? launchPart1Formats<true>(S, dt, pos, vel, force, true, st, side) : launchPart1Formats<false>(S, dt, pos, vel, force, true, st, side);
 }
 
 cudaError_t launchFreeDelta(const DeviceSystem& S, double dt, AtomView vel, AtomView force, AtomView delta, cudaStream_t st) {
@@ -1243,20 +1271,31 @@ cudaError_t launchPart1Delta(const DeviceSystem& S, double dt, AtomView pos, Ato
 
 namespace {
 template <bool NATIVE>
-cudaError_t launchPart2Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st) {
-    if (freeAtoms) launchFree<2, NATIVE>(S, dt, pos, vel, force, st);
+cudaError_t launchPart2Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st,
+                               const SideStream* side = nullptr) {
+    const bool overlap = freeAtoms && sideUsable(S, side);
+    if (overlap) {
+        cudaError_t e = sideFork(side, st);
+        if (e != cudaSuccess) return e;
+    }
+    else if (freeAtoms) launchFree<2, NATIVE>(S, dt, pos, vel, force, st);
 #ifndef RBK_P2_OLD
-    if (S.numTiles > 0 && S.splitPart1) return launchPart2Large<NATIVE>(S, dt, pos, vel, force, st);
+    if (S.numTiles > 0 && S.splitPart1) {
+        cudaError_t e = launchPart2Large<NATIVE>(S, dt, pos, vel, force, st);
+        if (e != cudaSuccess || !overlap) return e;
+        e = sideFree<2, NATIVE>(S, dt, pos, vel, force, side);
+        return e != cudaSuccess ? e : sideJoin(side, st);
+    }
 #endif
     if (S.numTiles > 0) part2Kernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 } // namespace
 
-cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st, const SideStream* side) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
-    return nativeIO(pos, vel, force) ? launchPart2Formats<true>(S, dt, pos, vel, force, true, st)
-                                     : launchPart2Formats<false>(S, dt, pos, vel, force, true, st);
+    return nativeIO(pos, vel, force) ? launchPart2Formats<true>(S, dt, pos, vel, force, true, st, side)
+                                     : launchPart2Formats<false>(S, dt, pos, vel, force, true, st, side);
 }
 
 cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
@@ -1269,10 +1308,9 @@ cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, Ato
         // free atoms' small CTAs run in the registers the body kernels leave unused and in their tails (disjoint atoms,
         // no data dependence); the caller's stream continues when both are done.
         const bool native = nativeIO(pos, vel, force);
-        const bool overlap = side != nullptr && side->stream != nullptr && S.numFree > 0 && S.numTiles > 0 && S.splitPart1;
+        const bool overlap = sideUsable(S, side);
         if (overlap) {
-            cudaError_t e = cudaEventRecord(side->fork, st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+            cudaError_t e = sideFork(side, st);
             if (e != cudaSuccess) return e;
         }
         else if (native) launchFree<3, true>(S, dt, pos, vel, force, st);
@@ -1281,15 +1319,12 @@ cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, Ato
         cudaError_t e = native ? launchPart2Formats<true>(S, dt, pos, vel, force, false, st) : launchPart2Formats<false>(S, dt, pos, vel, force, false, st);
         if (e != cudaSuccess) return e;
         if (overlap) {
-            const int blocks = (S.numFree + kSideFreeThreads - 1)/kSideFreeThreads;
-            if (native) freeAtomsKernel<3, true><<<blocks, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
-            else freeAtomsKernel<3, false><<<blocks, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
-            e = cudaEventRecord(side->join, side->stream);
+            e = native ? sideFree<3, true>(S, dt, pos, vel, force, side) : sideFree<3, false>(S, dt, pos, vel, force, side);
             if (e != cudaSuccess) return e;
         }
         e = native ? launchPart1Formats<true>(S, dt, pos, vel, force, false, st) : launchPart1Formats<false>(S, dt, pos, vel, force, false, st);
         if (e != cudaSuccess) return e;
-        return overlap ? cudaStreamWaitEvent(st, side->join, 0) : cudaSuccess;
+        return overlap ? sideJoin(side, st) : cudaSuccess;
     }
     const bool small = S.maxBodySize <= kSmallBody;
     if (S.rotationMode == 0) return small ? launchFused<true, true>(S, dt, pos, vel, force, st) : launchFused<true, false>(S, dt, pos, vel, force, st);
