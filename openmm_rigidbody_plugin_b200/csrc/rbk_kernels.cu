@@ -1,13 +1,15 @@
 // rbk_kernels.cu - hand-written CUDA kernels (sm_100a) of the RigidBodyIntegrator step.
 //
 // Work decomposition (DESIGN.md "Kernels"): bodies are cut into TILES of <=128 consecutive bodies
-// (<= ~1024 atoms); one 128-thread CTA owns a tile and alternates between two thread mappings
+// (<= 512 atoms, <= 256 for large-body systems); a CTA owns a tile and alternates between two thread mappings
 //   thread-per-BODY : coalesced SoA loads of the body state, half kick / rotation / second kick
 //   thread-per-ATOM : coalesced loads of body-frame coordinates + atom forces, position / velocity
-//                     reconstruction, warp-shuffle segmented reduction of force and torque
+//                     reconstruction, segmented reduction of force and torque
 // exchanging per-body quantities (q, r, v_cm, omega) through shared memory, so the rotation update
-// and the atom scatter are ONE kernel and nothing per-body is re-read from HBM.  CTAs past the last
-// tile integrate the free atoms (velocity Verlet).  No atomics on the data path (the persistent kernels' tile counter only
+// and the atom scatter are ONE kernel and nothing per-body is re-read from HBM.  The reduction is bucketed by body
+// size: bodies of <= 8 atoms are summed by their own thread (step-fused kernel), mixed small systems by a warp-shuffle
+// segmented scan (part2Kernel), systems of large bodies by a lane group per body (part2LargeKernel).  Free atoms
+// (velocity Verlet) have their own kernel.  No atomics on the data path (the persistent kernels' tile counter only
 // decides which CTA takes a tile): results are bit-reproducible.
 //
 // Reference behaviour reproduced: RigidBodySystem::integratePart1/2, computeKineticEnergies
@@ -372,11 +374,12 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
 //
 // The bucket for big bodies of the size-bucketed reduction: with tens of atoms per body a shuffle scan spends
 // 5 levels x 6 doubles of SHFL/select/add on every 32 atoms (ncu on config 4: 28 % of the executed instructions,
-// issue-bound at 3.4 TB/s).  Here a tile's forces and space-frame arms delta = A^T(q) d are staged in shared memory by
-// the atoms' threads (coalesced loads, kLargePerThread atoms in flight per thread), and then ONE THREAD PER
-// (body, component) walks its body's atoms sequentially - the reference's own summation order
-// (RigidBody::forceAndTorque, openmmapi/src/RigidBody.cpp:174-183), no shuffles, no atomics, deterministic.  The arms
-// stay in shared memory for the velocity phase, so the body-frame coordinates are read once and rotated once.
+// issue-bound at 3.4 TB/s).  Here a tile's forces and body-frame coordinates are staged in shared memory; the atoms'
+// threads turn the coordinates into space-frame arms delta = A^T(q) d in place, and then a GROUP OF LANES PER BODY
+// (16 or 8) walks the body's atoms - lane g takes atoms g, g+lanes, ... in order (within a lane the reference's own
+// summation order, RigidBody::forceAndTorque, openmmapi/src/RigidBody.cpp:174-183) - and a fixed butterfly over the
+// group finishes the sums: a few shuffles per BODY instead of per 32 atoms, no atomics, deterministic.  The arms stay
+// in shared memory for the velocity phase, so the body-frame coordinates are read once and rotated once.
 // A body larger than a tile is alone in its tile and is reduced by the whole CTA (strided partial sums, fixed tree).
 // ------------------------------------------------------------------------------------------------
 // Persistent CTAs (one wave) walk the tiles round-robin behind a three-deep cp.async pipeline: while tile i is processed,
@@ -1279,14 +1282,12 @@ cudaError_t launchPart2Formats(const DeviceSystem& S, double dt, AtomView pos, A
         if (e != cudaSuccess) return e;
     }
     else if (freeAtoms) launchFree<2, NATIVE>(S, dt, pos, vel, force, st);
-#ifndef RBK_P2_OLD
     if (S.numTiles > 0 && S.splitPart1) {
         cudaError_t e = launchPart2Large<NATIVE>(S, dt, pos, vel, force, st);
         if (e != cudaSuccess || !overlap) return e;
         e = sideFree<2, NATIVE>(S, dt, pos, vel, force, side);
         return e != cudaSuccess ? e : sideJoin(side, st);
     }
-#endif
     if (S.numTiles > 0) part2Kernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
