@@ -81,3 +81,64 @@ def test_bit_reproducible_large_bodies():
     a = _run_pair(sysd, 0, "vec3", True, fused=True)
     b = _run_pair(sysd, 0, "vec3", True, fused=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def _raw_system(seed, n_bodies=600, n_free=500):
+    """DeviceRigidBodySystem + device arrays of a large-body system with interleaved free atoms (non-identity atom map)."""
+    import torch
+    from openmm_rigidbody_plugin_b200 import DeviceRigidBodySystem
+    sysd = common.synth.mixed_system(n_bodies, n_free, seed=seed)
+    dev = torch.device("cuda:0")
+    system = DeviceRigidBodySystem(sysd["bodyIndices"], sysd["masses"], 0)
+    system.update(sysd["R"], sysd["V"], sysd["F"], True, True)
+    system.upload()
+    pos, vel = (torch.from_numpy(sysd[k].copy()).to(dev) for k in ("R", "V"))
+    forces = (torch.from_numpy(sysd["F"].copy()).to(dev), torch.from_numpy(-sysd["F"]).to(dev))
+    return system, pos, vel, forces
+
+
+def test_side_stream_keeps_stream_order_and_can_be_captured():
+    """The free atoms of a large-body step run on a second stream owned by the handle, forked from / joined to the
+    caller's stream with events (include/rbk.h, rbk_part2_part1).  (1) On a non-default stream, work queued right
+    behind the call must see the call's complete result.  (2) The fork/join pattern must be legal under stream
+    capture: the same steps replayed from a CUDA graph give bit-identical arrays."""
+    import torch
+    dt, steps = 0.001, 6
+
+    def plain(stream):
+        system, pos, vel, F = _raw_system(411)
+        snap = []
+        with torch.cuda.stream(stream):
+            system.part1(dt, pos, vel, F[0])
+            for i in range(steps):
+                system.part2_part1(dt, pos, vel, F[(i + 1) & 1])
+                snap.append((pos.clone(), vel.clone()))          # queued on the same stream, no host sync in between
+            system.part2(dt, pos, vel, F[(steps + 1) & 1])
+        stream.synchronize()
+        out = [(p.cpu().numpy(), v.cpu().numpy()) for p, v in snap] + [(pos.cpu().numpy(), vel.cpu().numpy())]
+        system.close()
+        return out
+
+    ref = plain(torch.cuda.current_stream())
+    other = plain(torch.cuda.Stream())
+    for (p0, v0), (p1, v1) in zip(ref, other):
+        assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+
+    # CUDA graph: two plain fused steps first (they create the handle's side stream and set kernel attributes - not
+    # things to do while capturing), then capture two fused steps and replay them twice: six fused steps in all
+    system, pos, vel, F = _raw_system(411)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        system.part1(dt, pos, vel, F[0])
+        system.part2_part1(dt, pos, vel, F[1])
+        system.part2_part1(dt, pos, vel, F[0])
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        system.part2_part1(dt, pos, vel, F[1])
+        system.part2_part1(dt, pos, vel, F[0])
+    for _ in range((steps - 2) // 2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(pos.cpu().numpy(), ref[steps - 1][0]) and np.array_equal(vel.cpu().numpy(), ref[steps - 1][1])
+    system.close()
