@@ -52,7 +52,12 @@ def parse_args():
     ap.add_argument("--molecules", type=int, default=1_000_000)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--workload", default="water", choices=["water", "mixed"])
-    ap.add_argument("--layout", default="vec3", choices=["vec3", "soa"])
+    ap.add_argument("--layout", default="vec3", choices=["vec3", "soa", "openmm-mixed", "openmm-double"],
+                    help="caller-owned atom arrays: fp64 Vec3 / SoA planes, or the OpenMM-CUDA boundary formats")
+    ap.add_argument("--shuffle", action="store_true", help="atoms stored in a random permutation (rbk_set_atom_location)")
+    ap.add_argument("--forces", default="alternating", choices=["alternating", "constant"],
+                    help="fixed synthetic forces: sign flipping every step (default) or literally constant (SURVEY 8d)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the CPU-oracle subsample check after the timed region")
     ap.add_argument("--no-fuse", action="store_true", help="step with separate part1/part2 launches only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -63,7 +68,7 @@ def parse_args():
 def make_workload(args, seed):
     if args.workload == "water":
         sysd = synth.water_box(args.molecules, seed=seed)
-        name = f"{args.molecules} rigid TIP3P waters ({3*args.molecules} atoms), mode {args.mode}, integrator-only, fixed synthetic forces (sign alternating per step)"
+        name = f"{args.molecules} rigid TIP3P waters ({3*args.molecules} atoms), mode {args.mode}, integrator-only, fixed synthetic forces ({'sign alternating per step' if args.forces == 'alternating' else 'constant'})"
     else:
         nb = max(args.molecules // 5, 1)
         sysd = synth.mixed_system(nb, int(2.5 * nb), seed=seed)
@@ -74,7 +79,7 @@ def make_workload(args, seed):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own arithmetic on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(sysd, mode, n_bodies_sample, steps, warmup, threads):
+def cpu_reference(sysd, mode, n_bodies_sample, steps, warmup, threads, alternate=True):
     """Time `steps` passes of the reference CPU stepper over the first n_bodies_sample molecules of the
     workload, bodies split into `threads` disjoint slices (the reference itself is single-threaded:
     plain loops in RigidBodySystem.cpp:170-204; bodies are independent, so slicing is exact)."""
@@ -95,7 +100,7 @@ def cpu_reference(sysd, mode, n_bodies_sample, steps, warmup, threads):
         sub = {k: np.ascontiguousarray(sysd[k][sel]) for k in ("masses", "R", "V", "F", "charges", "bodyIndices")}
         s = checkers.CpuStepper(kind, sub["bodyIndices"], sub["masses"], mode)
         common.init_like_reference(s, sub)
-        s.set_alternate(True)                  # same workload as the GPU arm: sign of F flips every step
+        s.set_alternate(alternate)             # same workload as the GPU arm (sign of F flips every step unless --forces constant)
         steppers.append(s)
 
     def run(n):
@@ -128,7 +133,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     # bounded sample: ~0.1 s of work per step per core
     sample = int(min(args.molecules, max(2000, 40000 * cores // (10 if args.mode >= 10 else 1) // 4)))
-    res = cpu_reference(sysd, args.mode, sample, args.steps, args.warmup, cores)
+    res = cpu_reference(sysd, args.mode, sample, args.steps, args.warmup, cores, args.forces == "alternating")
     value = res["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -213,6 +218,136 @@ def ncu_traffic(kernel_key):
         return None
 
 
+class AtomArrays:
+    """The caller-owned device arrays of one replica in one of the layouts librbk accepts, with the step calls that go
+    with it.  vec3 / soa: plain fp64 (RBK_LAYOUT_VEC3 = the Reference platform's std::vector<Vec3>, RBK_LAYOUT_SOA);
+    openmm-mixed / openmm-double: the OpenMM-CUDA boundary formats (posq float4 + posqCorrection | double4, velm double4,
+    fixed-point long long force planes).  shuffle: atoms stored in a random permutation handed to rbk_set_atom_location
+    (the CUDA platform's atom reordering)."""
+
+    def __init__(self, system, sysd, layout, shuffle, dev, alternate):
+        import torch
+        from openmm_rigidbody_plugin_b200._lib import RBK_OPENMM_DOUBLE, RBK_OPENMM_MIXED
+        self.t, self.sys, self.layout, self.dev = torch, system, layout, dev
+        n = self.n = sysd["masses"].shape[0]
+        self.order = None
+        if shuffle:
+            self.order = np.random.Generator(np.random.Philox(key=12345)).permutation(n)     # atom i lives at slot order[i]
+            system.set_atom_location(self.order[system.atom_index()].astype(np.int32))
+        self.openmm = layout.startswith("openmm")
+        F = sysd["F"]
+        if self.openmm:
+            self.precision = RBK_OPENMM_MIXED if layout == "openmm-mixed" else RBK_OPENMM_DOUBLE
+            self.padded = ((n + 31) // 32) * 32
+            Fq = np.round(F * 4294967296.0).astype(np.int64)         # exact: run_b200_arm quantised sysd["F"] already
+            pos4, vel4 = np.zeros((self.padded, 4)), np.zeros((self.padded, 4))
+            sl = self.order if self.order is not None else np.arange(n)
+            pos4[sl, :3], pos4[sl, 3] = sysd["R"], sysd["charges"]
+            vel4[sl, :3], vel4[sl, 3] = sysd["V"], 1.0 / sysd["masses"]
+            p64 = torch.from_numpy(pos4).to(dev)
+            if self.precision == RBK_OPENMM_MIXED:
+                self.posq = p64.float().contiguous()
+                self.corr = (p64 - self.posq.double()).float().contiguous()
+            else:
+                self.posq, self.corr = p64.contiguous(), None
+            self.velm = torch.from_numpy(vel4).to(dev).contiguous()
+            planes = np.zeros((3, self.padded), np.int64)
+            planes[:, sl] = Fq.T
+            f0 = torch.from_numpy(planes).to(dev).contiguous()
+            self.forces = (f0, (-f0).contiguous()) if alternate else (f0, f0)
+        else:
+            self.pos, self.vel = self._dev(sysd["R"]), self._dev(sysd["V"])
+            f0 = self._dev(F)
+            self.forces = (f0, self._dev(-F)) if alternate else (f0, f0)
+
+    def _dev(self, a):
+        if self.order is not None:
+            b = np.empty_like(a)
+            b[self.order] = a
+            a = b
+        x = self.t.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        return x.t().contiguous() if self.layout == "soa" else x
+
+    def part1(self, dt, k):
+        if self.openmm:
+            self.sys.part1_openmm(dt, self.posq, self.corr, self.velm, self.forces[k], self.padded, self.precision)
+        else:
+            self.sys.part1(dt, self.pos, self.vel, self.forces[k])
+
+    def part2(self, dt, k):
+        if self.openmm:
+            self.sys.part2_openmm(dt, self.posq, self.corr, self.velm, self.forces[k], self.padded, self.precision)
+        else:
+            self.sys.part2(dt, self.pos, self.vel, self.forces[k])
+
+    def part2_part1(self, dt, k):
+        if self.openmm:
+            self.sys.part2_part1_openmm(dt, self.posq, self.corr, self.velm, self.forces[k], self.padded, self.precision)
+        else:
+            self.sys.part2_part1(dt, self.pos, self.vel, self.forces[k])
+
+    def kinetic(self):
+        return self.sys.kinetic_openmm(self.velm, self.precision) if self.openmm else self.sys.kinetic(self.vel)
+
+    def rows(self, atoms):
+        """positions and velocities (fp64, host) of the given atoms (original numbering)"""
+        t = self.t
+        idx = t.from_numpy(np.ascontiguousarray(self.order[atoms] if self.order is not None else atoms)).to(self.dev)
+        if self.openmm:
+            R = self.posq[idx, :3].double()
+            if self.corr is not None:
+                R = R + self.corr[idx, :3].double()
+            V = self.velm[idx, :3]
+        elif self.layout == "soa":
+            R, V = self.pos[:, idx].t(), self.vel[:, idx].t()
+        else:
+            R, V = self.pos[idx], self.vel[idx]
+        return R.cpu().numpy(), V.cpu().numpy()
+
+    # bytes moved per atom by the position write / velocity write / force read in this layout (SURVEY.md section 8d)
+    def atom_io_bytes(self):
+        if not self.openmm:
+            return 24, 24, 24
+        return (32 if self.corr is not None else 32), 32, 24
+
+
+def parity_subsample(sysd, arrays, mode, total_steps, alternate, n_bodies=2000, n_free=2000):
+    """The timed kernels did the work: re-run a random subsample of the workload (bodies and free atoms are independent
+    under prescribed forces) on the CPU oracle for exactly the number of steps the GPU arrays have seen and compare."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    from oracle import checkers
+    body = sysd["bodyIndices"]
+    rng = np.random.Generator(np.random.Philox(key=4242))
+    labels = np.unique(body[body > 0])
+    pick = rng.choice(labels, min(n_bodies, labels.shape[0]), replace=False) if labels.shape[0] else labels
+    free = np.nonzero(body <= 0)[0]
+    mask = np.isin(body, pick)
+    if free.shape[0]:
+        mask[rng.choice(free, min(n_free, free.shape[0]), replace=False)] = True
+    atoms = np.nonzero(mask)[0]
+    sub = {k: np.ascontiguousarray(sysd[k][atoms]) for k in ("masses", "R", "V", "F", "charges", "bodyIndices")}
+    o = checkers.CpuStepper("oracle", sub["bodyIndices"], sub["masses"], mode)
+    common.init_like_reference(o, sub)
+    o.set_alternate(alternate)
+    o.step(DT, total_steps)
+    Ro, Vo, _ = o.get_state()
+    Rg, Vg = arrays.rows(atoms)
+    o.close()
+    return {"max_rel_R": common.rel_inf(Rg, Ro), "max_rel_V": common.rel_inf(Vg, Vo), "steps": total_steps,
+            "bodies": int(pick.shape[0]), "atoms": int(atoms.shape[0]),
+            "how": "random subsample re-run on the CPU oracle (oracle/rb_oracle.c) for every step the device arrays have seen; "
+                   "||gpu - cpu||_inf / ||cpu||_inf"}
+
+
+def committed_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -230,33 +365,27 @@ def run_b200_arm(args):
 
     # one independent replica per GPU, distinct seed per replica (BASELINE.json: replicas only)
     sysd, name = make_workload(args, seed=replicas.replica_seed(20240001, rank))
+    alternate = args.forces == "alternating"
     n = sysd["masses"].shape[0]
+    if args.layout.startswith("openmm"):
+        # OpenMM's force arrays are fixed point (scale 2^32): quantise once so that the body build, the kernels and the CPU
+        # check all see the same numbers
+        sysd = dict(sysd, F=np.round(sysd["F"] * 4294967296.0) / 4294967296.0)
     system = DeviceRigidBodySystem(sysd["bodyIndices"], sysd["masses"], args.mode)
     system.update(sysd["R"], np.zeros((n, 3)), sysd["F"], True, True)
     system.update(V=sysd["V"], geometry=False, velocities=True)
     system.upload()
     c = system.counts()
     nB, nF, nA = c["numBodies"], c["numFree"], c["numBodyAtoms"]
-
-    def dev_array(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        return t.t().contiguous() if args.layout == "soa" else t
-
-    pos, vel = dev_array(sysd["R"]), dev_array(sysd["V"])
-    # Fixed synthetic forces whose SIGN alternates from step to step (two resident buffers, no extra
-    # kernel): constant forces would spin the bodies up without bound (25x thermal angular momentum
-    # after 100 steps), alternating ones keep the system at its 300 K state for any number of steps.
-    forces = (dev_array(sysd["F"]), dev_array(-sysd["F"]))
+    A = AtomArrays(system, sysd, args.layout, args.shuffle, dev, alternate)
     stream = torch.cuda.current_stream()
     cur = [0]                 # index of the force buffer of the most recent force "evaluation"
+    done = [0]                # integrator steps the device arrays have seen
 
-    def step():
-        # Part 1 kicks with the forces of the previous evaluation, Part 2 with the new ones - the order in which
-        # the reference's execute() sees them (ReferenceRigidBodyKernels.cpp:97-102)
-        system.part1(DT, pos, vel, forces[cur[0]])
-        cur[0] ^= 1
-        system.part2(DT, pos, vel, forces[cur[0]])
-
+    # Forces: fixed synthetic arrays.  --forces alternating (default): the SIGN flips from step to step (two resident
+    # buffers, no extra kernel) - constant forces spin the bodies up without bound (25x thermal angular momentum after
+    # 100 steps), alternating ones keep the system at its 300 K state for any number of steps.  --forces constant: the
+    # literal contract workload of SURVEY.md section 8(d).
     def barrier():
         torch.cuda.synchronize()
         replicas.barrier(dist if world > 1 else None)
@@ -264,20 +393,25 @@ def run_b200_arm(args):
 
     def run_steps(k):
         """k integrator steps the way RigidBodyIntegrator::step(k) runs on this library: part1, then (k-1) times
-        [new forces, part2+part1 in one pass (rbk_part2_part1)], then new forces, part2.  --no-fuse: k x [part1, part2]."""
+        [new forces, part2+part1 in one pass (rbk_part2_part1)], then new forces, part2.  --no-fuse: k x [part1, part2].
+        Part 1 kicks with the forces of the previous evaluation, Part 2 with the new ones - the order in which the
+        reference's execute() sees them (ReferenceRigidBodyKernels.cpp:97-102)."""
+        done[0] += k
         if args.no_fuse:
             for _ in range(k):
-                step()
+                A.part1(DT, cur[0])
+                cur[0] ^= 1
+                A.part2(DT, cur[0])
             return 2 * k
-        system.part1(DT, pos, vel, forces[cur[0]])
+        A.part1(DT, cur[0])
         for _ in range(k - 1):
             cur[0] ^= 1
-            system.part2_part1(DT, pos, vel, forces[cur[0]])
+            A.part2_part1(DT, cur[0])
         cur[0] ^= 1
-        system.part2(DT, pos, vel, forces[cur[0]])
+        A.part2(DT, cur[0])
         return k + 1
 
-    ke_start = system.kinetic(vel)
+    ke_start = A.kinetic()
     clocks = ClockSampler(local)
     clocks.start()
     run_steps(max(args.warmup, 3))
@@ -294,92 +428,132 @@ def run_b200_arm(args):
     torch.cuda.synchronize()
     for i in range(args.steps):
         ev[3*i].record(stream)
-        system.part1(DT, pos, vel, forces[cur[0]])
+        A.part1(DT, cur[0])
         ev[3*i+1].record(stream)
         cur[0] ^= 1
-        system.part2(DT, pos, vel, forces[cur[0]])
+        A.part2(DT, cur[0])
         ev[3*i+2].record(stream)
+    done[0] += args.steps
     torch.cuda.synchronize()
     t1 = float(np.mean([ev[3*i].elapsed_time(ev[3*i+1]) for i in range(args.steps)]))
     t2 = float(np.mean([ev[3*i+1].elapsed_time(ev[3*i+2]) for i in range(args.steps)]))
-    fused_ok = (not args.no_fuse) and nB > 0 and nA <= 8 * nB
+    large = nB > 0 and nA > 8 * nB
+    fused_ok = (not args.no_fuse) and nB > 0 and not large
     tf = None
-    if fused_ok:          # event-time the one-pass kernel (part 2 of step k + part 1 of step k+1 = one step of work)
+    if not args.no_fuse:  # event-time the one-pass call (part 2 of step k + part 1 of step k+1 = one step of work)
         fe = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        system.part1(DT, pos, vel, forces[cur[0]])
+        A.part1(DT, cur[0])
         for i in range(args.steps):
             fe[i].record(stream)
             cur[0] ^= 1
-            system.part2_part1(DT, pos, vel, forces[cur[0]])
+            A.part2_part1(DT, cur[0])
         fe[args.steps].record(stream)
         cur[0] ^= 1
-        system.part2(DT, pos, vel, forces[cur[0]])
+        A.part2(DT, cur[0])
+        done[0] += args.steps + 1
         torch.cuda.synchronize()
         tf = float(np.mean([fe[i].elapsed_time(fe[i+1]) for i in range(args.steps)]))
     clk = clocks.stop()
-    ke = system.kinetic(vel)
+    ke = A.kinetic()
     if not np.isfinite(ke).all():
         raise SystemExit("bench.py: non-finite kinetic energy after the timed region")
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_subsample(sysd, A, args.mode, done[0], alternate)
+        bar = 1e-6                                        # BASELINE.json's bar for ONE step, held after every step run here
+        if not (parity["max_rel_R"] <= bar and parity["max_rel_V"] <= bar):
+            raise SystemExit(f"bench.py: the timed kernels disagree with the CPU oracle: {parity}")
 
     value = world * nB * args.steps / (ms * 1e-3)
     # kernels launched inside the timed region (librbk's launch structure, rbk_kernels.cu launchPart1 / launchPart2 /
     # launchPart2Part1): free atoms have their own launch; large bodies split part 1 into rotation + position kernels
-    large, fr = nB > 0 and nA > 8 * nB, 1 if nF > 0 else 0
+    fr = 1 if nF > 0 else 0
     per_p1, per_p2 = fr + (2 if large else 1 if nB else 0), fr + (1 if nB else 0)
     per_pp = fr + (3 if large else 1 if nB else 0)
     gpu_launches = args.steps * (per_p1 + per_p2) if args.no_fuse else per_p1 + (args.steps - 1) * per_pp + per_p2
-    bytes1 = P1_BODY * nB + P1_ATOM * nA + FREE_P1 * nF
-    bytes2 = P2_BODY * nB + P2_ATOM * nA + FREE_P2 * nF
+
+    # ---- roofline.  Two byte counts per launch, both stated:
+    #   compulsory  what the kernel(s) ACTUALLY timed must move (this layout, this launch structure) - `frac` uses it
+    #   work-equivalent  SURVEY.md section 8(d)'s model of the two-kernel formulation (560 + 128 n per body-step, 288 per
+    #                free atom-step) - the contract's per-unit figure, kept under work_equiv_*; the one-pass kernel moves
+    #                fewer bytes than that model, so work_equiv_frac can exceed 1 and is NOT a bandwidth
+    wpos, wvel, rfor = A.atom_io_bytes()
+    identity = A.order is None and not (nF > 0 and nB > 0 and args.workload == "mixed")
+    loc4 = 0 if identity else 4                      # atomLoc look-up when the plugin-order -> array map is not the identity
+    # per body: state planes read + written (8 B each) + 4 B prefix offset; per atom: body-frame coordinates 24, body byte 1,
+    # [slot 4], force, velocity, position in this layout; per free atom: v, f, x, 1/m (+ savedPos) in, v, x (+ savedPos) out
+    p1_bytes = (192 + 4 + 112) * nB + (24 + 1 + loc4 + wpos) * nA + (loc4 + 2 * wvel + rfor + 2 * wpos + 8 + 24) * nF
+    p2_bytes = (120 + 4 + 104) * nB + (24 + 1 + loc4 + rfor + wvel) * nA + (loc4 + 2 * wvel + rfor + wpos + 24 + 8) * nF
+    free_pp = (loc4 + 2 * wvel + rfor + 2 * wpos + 24 + 8 + 24) * nF
+    if large:
+        # one rbk_part2_part1 call = part2LargeKernel (state in 120 + 4, out 104; per atom d, byte, slot, f in, v out) +
+        # rotation kernel (in 192, out 112) + atomPositionKernel (r, q in 56; per atom d, byte, slot in, x out) + free atoms
+        pp_bytes = (124 + 104 + 192 + 112 + 56) * nB + (2 * (24 + 1 + loc4) + rfor + wvel + wpos) * nA + free_pp
+    else:
+        # the one-pass kernel: r p q pi 1/m 1/I in (144 + 4), r p q pi out (112) [+ F tau out (48) when the stores are kept]
+        ft = 0 if system_lazy_ft() else 48
+        pp_bytes = (148 + 112 + ft) * nB + (24 + 1 + loc4 + rfor + wvel + wpos) * nA + free_pp
+    work1 = P1_BODY * nB + P1_ATOM * nA + FREE_P1 * nF
+    work2 = P2_BODY * nB + P2_ATOM * nA + FREE_P2 * nF
     peak, peak_src = measured_peak()
-    dom = ("part1", bytes1, t1) if t1 >= t2 else ("part2", bytes2, t2)
     if tf is not None:
-        dom = ("part2Part1", bytes1 + bytes2, tf)
+        dom = ("part2Part1", pp_bytes, tf)
+    else:
+        dom = ("part1", p1_bytes, t1) if t1 >= t2 else ("part2", p2_bytes, t2)
     ach = dom[1] / (dom[2] * 1e-3) / 1e9
-    step_ach = (bytes1 + bytes2) / ((ms / args.steps) * 1e-3) / 1e9
+    kernel_name = {"part2Part1": "rbk::part2Part1Kernel" if not large else "rbk_part2_part1 call = part2LargeKernel + part1Kernel (rotation) + atomPositionKernel + freeAtomsKernel<3>",
+                   "part1": "rbk_part1 call", "part2": "rbk_part2 call"}[dom[0]]
+    traffic = ncu_traffic(f"{dom[0]}_mode{args.mode}_{args.workload}{args.molecules}_{args.layout}{'_shuffle' if args.shuffle else ''}")
+    work_ach = (work1 + work2) / (dom[2] * 1e-3) / 1e9 if tf is not None else None
+    fp64 = committed_json("fp64_peak.json")
     roofline = {
-        "bound": "hbm", "kernel": f"rbk::{'part2Large' if large and dom[0] == 'part2' else dom[0]}Kernel" + (" (+ freeAtomsKernel of the same call)" if fr and tf is None else ""), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": ncu_traffic(f"{dom[0]}_mode{args.mode}_{args.workload}{args.molecules}"),
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[2],
-        "kernels": {"part1": {"ms": t1, "bytes": bytes1, "GBps": bytes1 / (t1 * 1e-3) / 1e9},
-                    "part2": {"ms": t2, "bytes": bytes2, "GBps": bytes2 / (t2 * 1e-3) / 1e9}},
-        "step": {"achieved": step_ach, "frac": step_ach / peak, "bytes": bytes1 + bytes2,
+        "bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[2],
+        "bytes_model": "compulsory bytes of the launch(es) actually timed: per body state in + out, per atom body-frame coordinates, "
+                       "body byte, force, velocity, position in this layout; DESIGN.md section 4 lists them per kernel",
+        "kernels": {"part1": {"ms": t1, "bytes": p1_bytes, "GBps": p1_bytes / (t1 * 1e-3) / 1e9},
+                    "part2": {"ms": t2, "bytes": p2_bytes, "GBps": p2_bytes / (t2 * 1e-3) / 1e9}},
+        "work_equiv": {"bytes_per_step": work1 + work2, "achieved": work_ach, "frac": None if work_ach is None else work_ach / peak,
+                       "note": "SURVEY.md 8(d) two-kernel byte model (560 + 128 n per body-step) over the one-pass launch time: a work rate, "
+                               "not a bandwidth (can exceed 1)"},
+        "step": {"ms": ms / args.steps, "compulsory_GBps": (pp_bytes if tf is not None else p1_bytes + p2_bytes) / ((ms / args.steps) * 1e-3) / 1e9,
                  "note": "whole step from the 2-event timed region (all launches, incl. the opening part1 / closing part2)"},
+        "secondary_bound_fp64": fp64,
     }
     if tf is not None:
-        roofline["kernels"]["part2Part1"] = {"ms": tf, "bytes": bytes1 + bytes2, "GBps": (bytes1 + bytes2) / (tf * 1e-3) / 1e9}
-        # what the one-pass kernel itself has to move: state read once (r p q pi 1/m 1/I), written once (r p q pi F tau);
-        # per atom: force + coordinates + body byte in, velocity + position out
-        fused_bytes = (144 + 160) * nB + (49 + 48) * nA + 288 * nF
-        roofline["one_pass_compulsory_bytes"] = fused_bytes
-        roofline["note"] = ("achieved/frac use SURVEY.md's algorithmic bytes of the two-kernel formulation (560+128n per body-step); the "
-                            "one-pass kernel moves fewer compulsory bytes (state resident across the step boundary), so frac can exceed "
-                            "what a two-kernel step could reach; frac_of_one_pass_bytes = " + f"{fused_bytes / (tf * 1e-3) / 1e9 / peak:.3f}")
+        roofline["kernels"]["part2Part1"] = {"ms": tf, "bytes": pp_bytes, "GBps": pp_bytes / (tf * 1e-3) / 1e9}
+    if traffic:
+        roofline["traffic_frac"] = traffic / (dom[2] * 1e-3) / 1e9 / peak
 
-    # ---- e2e: host-buffer call, pinned host R/V/F, copies inside the timed region
+    # ---- e2e: the host-buffer call (what a Reference-platform RigidBodyIntegrator::step drives): pinned host R/V/F; every
+    # step that step's forces go host -> device and the new positions device -> host inside the timed region; velocities
+    # come back once, after the last step (nothing on the host reads them in between - rbk.h, rbk_execute_host)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not A.openmm and A.order is None and args.layout == "vec3":
         hR = torch.from_numpy(sysd["R"].copy()).pin_memory()
         hV = torch.from_numpy(sysd["V"].copy()).pin_memory()
-        hF = (torch.from_numpy(sysd["F"].copy()).pin_memory(), torch.from_numpy(-sysd["F"]).pin_memory())
+        hF = (torch.from_numpy(sysd["F"].copy()).pin_memory(), torch.from_numpy((-sysd["F"]) if alternate else sysd["F"].copy()).pin_memory())
         system.upload()                                   # reset body state + device mirrors
         k2 = max(3, min(args.steps, 20))
-        for i in range(4):                                # warm-up (first call also uploads the mirrors)
-            system.execute_host(DT, 1, hR, hV, hF[i & 1])
+        system.execute_host(DT, 1, hR, hV, hF[0])         # warm-up (the first call also uploads the mirrors)
+        for i in range(1, 4):
+            system.execute_host(DT, 1, hR, None, hF[i & 1])
         barrier()
         t0 = time.perf_counter()
         for i in range(k2):                               # one call per step, that step's forces from the host
-            system.execute_host(DT, 1, hR, hV, hF[i & 1])
+            system.execute_host(DT, 1, hR, hV if i == k2 - 1 else None, hF[i & 1])
         torch.cuda.synchronize()
         el = replicas.max_over_ranks(time.perf_counter() - t0, dist if world > 1 else None, dev)
-        e2e = {"value": world * nB * k2 / el, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 48 * n,
+        e2e = {"value": world * nB * k2 / el, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n + 24 * n // k2,
                "steps": k2, "ms_per_step": 1e3 * el / k2,
-               "call": "one rbk_execute_host per step with that step's forces in pinned host memory: forces H2D (copy stream) under part1 + positions D2H, part2, velocities D2H, sync"}
+               "call": "one rbk_execute_host per step with that step's forces in pinned host memory: forces H2D (copy stream) under part1 + "
+                       "positions D2H, part2, sync; velocities D2H once, after the last step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sample = int(min(nB, max(2000, 25000 * cores // (4 if args.mode >= 10 else 1))))
-        res = cpu_reference(sysd, args.mode, sample, 40, 2, cores)
+        res = cpu_reference(sysd, args.mode, sample, 40, 2, cores, alternate)
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -388,16 +562,21 @@ def run_b200_arm(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": name, "per_gpu": "one independent replica per GPU (replicas only, no collective)",
-                       "layout": args.layout, "dt_ps": DT, "bodies": nB, "body_atoms": nA, "free_atoms": nF,
+                       "layout": args.layout, "shuffle": bool(args.shuffle), "forces": args.forces, "dt_ps": DT, "bodies": nB, "body_atoms": nA, "free_atoms": nF,
                        "l2": "no flush needed: the per-step working set (state + atoms, >500 MB at 1M waters) exceeds the 126 MB L2"},
             "ns_per_day": (args.steps / (ms * 1e-3)) * DT * 1e-3 * 86400.0,
             "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+            "parity_subsample": parity,
             "kinetic_energy_kJmol": {"start": [float(ke_start[0]), float(ke_start[1])], "end": [float(ke[0]), float(ke[1])],
-                                     "note": "translational, rotational; the workload stays at its initial ~300 K state"},
+                                     "note": "translational, rotational"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def system_lazy_ft():
+    return os.environ.get("RBK_EAGER_FORCE_TORQUE", "0")[:1] != "1"
 
 
 def main():

@@ -110,8 +110,10 @@ int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const 
  * happens between the two in RigidBodyIntegrator::step (openmmapi/src/RigidBodyIntegrator.cpp:96-101: execute, execute,
  * ...; the force evaluation sits between Part 1 and Part 2 of the SAME step).  step(n) becomes
  *     part1, forces, [part2_part1, forces] x (n-1), part2.
- * Bit-identical to calling rbk_part2 then rbk_part1 with the same arguments; the body state makes one round trip
- * through HBM instead of two and the body-frame coordinates are read once.  On return `vel` holds the velocities at the
+ * Positions, velocities and r, p, q, pi are bit-identical to calling rbk_part2 then rbk_part1 with the same arguments
+ * (water-size bodies: up to the summation order of a body's atom forces); the body state makes one round trip through
+ * HBM instead of two and the body-frame coordinates are read once.  The stored body force / torque are NOT refreshed by
+ * this call (the next rbk_part2 or rbk_part2_part1 recomputes them before anything reads them).  On return `vel` holds the velocities at the
  * end of step k and `pos` the positions after Part 1 of step k+1 (exactly the state the reference is in when it
  * evaluates forces).  Stream semantics: everything is ordered after the work already queued on `stream`, and `stream`
  * continues only when the whole call's work is done; for systems of large bodies WITH free atoms the free atoms are
@@ -129,6 +131,7 @@ int rbk_kinetic(rbk_system* sys, const double* vel, int layout, long long stride
  * torque is the quaternion-frame 4-vector C(q)tau as the reference stores it (RigidBody.h:40). */
 int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, double* pi,
                         double* force, double* torque, void* stream);
+/* (force / torque: RBK_ESTATE between rbk_part2_part1 and the closing rbk_part2 - interior steps keep them in registers) */
 
 /* ---- host-buffer step (the reference-facing call measured as `e2e`) ------------------------ */
 
@@ -139,8 +142,13 @@ typedef void (*rbk_force_fn)(const double* R, double* F, int numAtoms, void* use
  * with HOST buffers, `steps` times: Part 1 on the device, positions copied to R, forces obtained
  * from `forces` (NULL = keep F as is) and copied to the device, Part 2, velocities copied to V.
  * R,V,F: host arrays in RBK_LAYOUT_VEC3 (pinned memory makes the copies asynchronous); on the first
- * call R,V,F are uploaded in full.  Uses device mirrors owned by the handle.  With forces == NULL the
- * upload of F (known before the call) runs on a copy stream underneath Part 1 and the download of R. */
+ * call R,V,F are uploaded in full.  Uses device mirrors owned by the handle.
+ *   forces != NULL: per step Part 1, R to the host, forces(R, F), F to the device, then Part 2 - for steps > 1 fused with
+ *                   the next step's Part 1 (rbk_part2_part1).  F at entry = the forces at the current positions.
+ *   forces == NULL: F = the forces at the NEW positions, known up front and used for every step of the call; its upload
+ *                   runs on a copy stream underneath Part 1 and the download of R; R is downloaded after the last Part 1.
+ * V is written once, after the last step of the call (nothing on the host reads velocities between the steps of
+ * RigidBodyIntegrator::step(n)); V == NULL leaves the velocities on the device until a later call passes V. */
 int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V, double* F,
                      rbk_force_fn forces, void* user, void* stream);
 
@@ -177,6 +185,16 @@ int rbk_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
 int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
                      int paddedNumAtoms, int precision, void* stream);
 int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double* out, void* stream);
+/* rbk_part2_part1 on the OpenMM formats: Part 2 of step k + Part 1 of step k+1 in one pass, for callers that have nothing
+ * between two execute() calls (CudaIntegrateRigidBodyStepKernel::execute, CudaRigidBodyKernels.cpp:377-444, when
+ * context.updateContextState() is a no-op; cu.reorderAtoms() moves to the point after this call - the old forces are not
+ * needed any more once both half kicks are done). */
+int rbk_part2_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
+                           int paddedNumAtoms, int precision, void* stream);
+/* CudaIntegrateRigidBodyStepKernel::ReorderListener::execute (CudaRigidBodyKernels.cpp:78-108), on the device: move the
+ * force of every atom the integrator owns from its old index to its new one (the next Part 1 kicks the free atoms with
+ * them; force == NULL skips this) and install `location` like rbk_set_atom_location. */
+int rbk_reorder_openmm(rbk_system* sys, const int* location, long long* force, int paddedNumAtoms, void* stream);
 
 /* Free-atom constraint hooks of the CUDA flow (CudaRigidBodyKernels.cpp:405-421; kernels freeAtomsDelta and the
  * free-atom loop of integrateRigidBodyPart1, rigidbodyintegrator.cu:276-285, 303-312):

@@ -39,6 +39,8 @@ SIGNATURES = {
     "rbk_kinetic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, _dp, C.c_void_p]),
     "rbk_part1_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rbk_part2_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rbk_part2_part1_openmm": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rbk_reorder_openmm": (C.c_int, [C.c_void_p, _ip, C.c_void_p, C.c_int, C.c_void_p]),
     "rbk_kinetic_openmm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_void_p]),
     "rbk_kinetic_host": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.c_void_p]),
     "rbk_download_bodies": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_void_p]),

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -58,11 +59,14 @@ struct rbk_system {
     int* dTileCounter = nullptr;
     rbk::TileMaps tileMaps{};        // TMA descriptors of the one-warp-tile pipeline (valid when dev.tileMaps != NULL)
     int* dAtomLoc = nullptr;
+    long long* dForcePacked = nullptr;   // scratch of rbk_reorder_openmm
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
     double* dAtomMass = nullptr;     // body atoms, plugin order (GPU-side body build)
     int* dDofSum = nullptr;
     bool hostStale = false;          // device build used: the host copy of the bodies is not current
+    bool deviceAhead = false;        // a step has run since the last upload: r, q, p, pi, F, tau live on the device only
+    bool forceTorqueStale = false;   // last step call was rbk_part2_part1: the F / tau planes are one step old
     double* dKinPartial = nullptr;
     unsigned* dKinCounter = nullptr;
     double* dKinOut = nullptr;
@@ -78,11 +82,12 @@ struct rbk_system {
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaEvent_t evStart = nullptr, evForces = nullptr, evPart1 = nullptr, evPositions = nullptr;
     bool mirrorsLoaded = false;
+    bool hostVelStale = false;       // the last rbk_execute_host call left the velocities on the device (V == NULL)
     std::vector<double> staging, oldPositions;
 
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter);
-        cudaFree(dAtomLoc); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
+        cudaFree(dAtomLoc); cudaFree(dForcePacked); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (side.stream) cudaStreamDestroy(side.stream);
         if (side.fork) cudaEventDestroy(side.fork);
@@ -178,6 +183,9 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.numBodyTiles = (int) bodyMeta.size();
     d.splitPart1 = nB > 0 && (long long) nA > (long long) rbk::kSplitAtomsPerBody*nB;
     d.fusable = !d.splitPart1;
+    // interior steps of step(n) keep F and tau in registers; RBK_EAGER_FORCE_TORQUE=1 restores the stores (A/B measurements)
+    const char* eager = std::getenv("RBK_EAGER_FORCE_TORQUE");
+    d.lazyForceTorque = !(eager && eager[0] == '1');
     for (const int4& t : meta) if (t.w > rbk::kTileAtoms) d.fusable = 0;
     // one-warp tiles for the step-fused kernel: bodies of <= 4 atoms (water) - then the atom tiles above are exactly the
     // consecutive groups of 128 bodies and these are their 32-body quarters (localBody & 31 = index in the quarter)
@@ -331,14 +339,65 @@ int rbk_get_atom_index(const rbk_system* sys, int* out) {
     return RBK_OK;
 }
 
+namespace {
+// Device body state -> host model (everything a later rbk_upload writes back: r p q pi F tau 1/m 1/I I and the body-frame
+// coordinates).  Needed before a velocities-only rebuild on a system that has been stepped or built on the device: the
+// host copy still holds the configuration of the last setPositions, and rebuilding pi with that q and uploading it would
+// rewind every body (RigidBodyIntegrator::stateChanged(Velocities) after step(), openmmapi/src/RigidBodyIntegrator.cpp:63-74).
+int pullHostModel(rbk_system* sys) {
+    HostModel& h = sys->host;
+    const DeviceSystem& d = sys->dev;
+    const size_t ld = d.bodyStride, as = d.atomStride;
+    RBK_CUDA(cudaDeviceSynchronize());                 // no stream argument here: whatever was queued must be done
+    std::vector<double>& buf = sys->staging;
+    buf.resize(std::max(buf.size(), std::max(ld*rbk::NPLANES, as*3)));
+    RBK_CUDA(cudaMemcpy(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < h.numBodies; b++) {
+        HostBody& B = h.body[b];
+        for (int c = 0; c < 3; c++) {
+            B.rcm[c] = buf[(rbk::PL_R + c)*ld + b];
+            B.pcm[c] = buf[(rbk::PL_P + c)*ld + b];
+            B.force[c] = buf[(rbk::PL_F + c)*ld + b];
+            B.tau[c] = buf[(rbk::PL_TAU + c)*ld + b];
+            B.I[c] = buf[(rbk::PL_I + c)*ld + b];
+            B.invI[c] = buf[(rbk::PL_INVI + c)*ld + b];
+        }
+        for (int c = 0; c < 4; c++) {
+            B.q[c] = buf[(rbk::PL_Q + c)*ld + b];
+            B.pi[c] = buf[(rbk::PL_PI + c)*ld + b];
+        }
+        B.invMass = buf[rbk::PL_INVM*ld + b];
+        B.mass = 1.0/B.invMass;
+        const double* q = B.q;                          // C(q) tau, the form the reference stores (RigidBody.h:40)
+        B.torque[0] = -q[1]*B.tau[0] - q[2]*B.tau[1] - q[3]*B.tau[2];
+        B.torque[1] =  q[0]*B.tau[0] + q[3]*B.tau[1] - q[2]*B.tau[2];
+        B.torque[2] = -q[3]*B.tau[0] + q[0]*B.tau[1] + q[1]*B.tau[2];
+        B.torque[3] =  q[2]*B.tau[0] - q[1]*B.tau[1] + q[0]*B.tau[2];
+    }
+    if (sys->hostStale) {                               // geometry was built on the device: the coordinates too
+        RBK_CUDA(cudaMemcpy(buf.data(), sys->dDxyz, as*3*sizeof(double), cudaMemcpyDeviceToHost));
+        for (int a = 0; a < h.numBodyAtoms; a++)
+            for (int c = 0; c < 3; c++) h.d[3*(size_t) a + c] = buf[c*as + a];
+    }
+    sys->hostStale = false;
+    sys->deviceAhead = false;
+    return RBK_OK;
+}
+} // namespace
+
 int rbk_update(rbk_system* sys, const double* R, const double* V, const double* F, int geometry, int velocities) {
     if (!sys) return fail(RBK_EINVAL, "rbk_update: NULL system");
     if (geometry && (!R || !F)) return fail(RBK_EINVAL, "rbk_update: geometry needs positions and forces");
     if (velocities && !V) return fail(RBK_EINVAL, "rbk_update: velocities needed");
-    if (velocities && !geometry && sys->host.numBodies > 0 && sys->host.body[0].mass == 0.0)
+    if (velocities && !geometry && sys->host.numBodies > 0 && sys->host.body[0].mass == 0.0 && !sys->hostStale)
         return fail(RBK_ESTATE, "rbk_update: velocities before any geometry build");
+    if (!geometry && sys->uploaded && (sys->deviceAhead || sys->hostStale)) {
+        if (sys->forceTorqueStale)
+            return fail(RBK_ESTATE, "rbk_update: velocities cannot be rebuilt between rbk_part2_part1 and the closing rbk_part2");
+        if (int rc = pullHostModel(sys)) return rc;
+    }
     sys->host.update(R, V, F, geometry != 0, velocities != 0);
-    sys->hostStale = false;
+    if (geometry) sys->hostStale = false;
     return RBK_OK;
 }
 
@@ -378,6 +437,8 @@ int rbk_get_body_fixed(const rbk_system* sys, double* d) {
 
 int rbk_upload(rbk_system* sys, void* stream) {
     if (!sys) return fail(RBK_EINVAL, "rbk_upload: NULL system");
+    if (sys->hostStale)
+        return fail(RBK_ESTATE, "rbk_upload: the bodies were built on the device (rbk_update_device); the host copy is not current");
     cudaStream_t st = (cudaStream_t) stream;
     if (!sys->allocated) {
         int rc = allocateDevice(sys, st);
@@ -416,6 +477,8 @@ int rbk_upload(rbk_system* sys, void* stream) {
     RBK_CUDA(cudaStreamSynchronize(st));
     sys->uploaded = true;
     sys->mirrorsLoaded = false;
+    sys->deviceAhead = false;
+    sys->forceTorqueStale = false;
     return RBK_OK;
 }
 
@@ -480,6 +543,7 @@ const rbk::SideStream* sideStream(rbk_system* sys) {
 
 // Part 1 / Part 2 with the refined-energy passes around them when the diagnostics are on (rbk_refined.cu)
 cudaError_t stepPart1(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView f, const AtomView* delta, cudaStream_t st) {
+    sys->deviceAhead = true;
     if (sys->refinedMode != RBK_REFINED_OFF) {
         cudaError_t e = rbk::launchRefinedBodies(sys->dev, sys->refined, dt, 1, st);
         if (e == cudaSuccess && sys->refinedMode == RBK_REFINED_ALL && !delta)
@@ -490,11 +554,25 @@ cudaError_t stepPart1(rbk_system* sys, double dt, AtomView p, AtomView v, AtomVi
 }
 
 cudaError_t stepPart2(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView f, cudaStream_t st) {
+    sys->deviceAhead = true;
+    sys->forceTorqueStale = false;
     cudaError_t e = rbk::launchPart2(sys->dev, dt, p, v, f, st, sideStream(sys));
     if (e != cudaSuccess || sys->refinedMode == RBK_REFINED_OFF) return e;
     e = rbk::launchRefinedBodies(sys->dev, sys->refined, dt, 2, st);
     if (e == cudaSuccess && sys->refinedMode == RBK_REFINED_ALL) e = rbk::launchRefinedFree(sys->dev, sys->refined, dt, 2, v, f, st);
     return e;
+}
+
+int stepPart2Part1(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView f, cudaStream_t st) {
+    if (sys->refinedMode != RBK_REFINED_OFF) {          // the diagnostics sit between the two halves: no one-pass kernel
+        RBK_CUDA(stepPart2(sys, dt, p, v, f, st));
+        RBK_CUDA(stepPart1(sys, dt, p, v, f, nullptr, st));
+        return RBK_OK;
+    }
+    sys->deviceAhead = true;
+    RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, st, sideStream(sys)));
+    sys->forceTorqueStale = !rbk::part2Part1LeavesForceTorque(sys->dev);
+    return RBK_OK;
 }
 
 int reduceOut(rbk_system* sys, double* out, int count, cudaStream_t st) {
@@ -579,13 +657,7 @@ int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const 
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2_part1: body system not uploaded");
     AtomView p, v, f;
     if (viewOf(pos, layout, stride, p) || viewOf(vel, layout, stride, v) || viewOf(force, layout, stride, f)) return RBK_EINVAL;
-    if (sys->refinedMode != RBK_REFINED_OFF) {          // the diagnostics sit between the two halves: no one-pass kernel
-        RBK_CUDA(stepPart2(sys, dt, p, v, f, (cudaStream_t) stream));
-        RBK_CUDA(stepPart1(sys, dt, p, v, f, nullptr, (cudaStream_t) stream));
-        return RBK_OK;
-    }
-    RBK_CUDA(rbk::launchPart2Part1(sys->dev, dt, p, v, f, (cudaStream_t) stream, sideStream(sys)));
-    return RBK_OK;
+    return stepPart2Part1(sys, dt, p, v, f, (cudaStream_t) stream);
 }
 
 int rbk_kinetic(rbk_system* sys, const double* vel, int layout, long long stride, double* out, void* stream) {
@@ -637,6 +709,54 @@ int rbk_part2_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrectio
     AtomView p, v, f;
     if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
     RBK_CUDA(stepPart2(sys, dt, p, v, f, (cudaStream_t) stream));
+    return RBK_OK;
+}
+
+int rbk_part2_part1_openmm(rbk_system* sys, double dt, void* posq, void* posqCorrection, void* velm, const long long* force,
+                           int paddedNumAtoms, int precision, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_part2_part1_openmm: NULL system");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_part2_part1_openmm: body system not uploaded");
+    AtomView p, v, f;
+    if (openmmViews(posq, posqCorrection, velm, force, paddedNumAtoms, precision, p, v, f)) return RBK_EINVAL;
+    return stepPart2Part1(sys, dt, p, v, f, (cudaStream_t) stream);
+}
+
+namespace {
+// forces of the atoms the integrator owns: planes (stride) -> packed [3][n] in plugin order, and back through a new map
+__global__ void gatherForcesKernel(const long long* __restrict__ force, long long stride, const int* __restrict__ loc, int n,
+                                   long long* __restrict__ packed) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long a = loc ? loc[i] : i;
+#pragma unroll
+    for (int c = 0; c < 3; c++) packed[(size_t) c*n + i] = force[a + c*stride];
+}
+__global__ void scatterForcesKernel(long long* __restrict__ force, long long stride, const int* __restrict__ loc, int n,
+                                    const long long* __restrict__ packed) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long a = loc ? loc[i] : i;
+#pragma unroll
+    for (int c = 0; c < 3; c++) force[a + c*stride] = packed[(size_t) c*n + i];
+}
+} // namespace
+
+int rbk_reorder_openmm(rbk_system* sys, const int* location, long long* force, int paddedNumAtoms, void* stream) {
+    if (!sys) return fail(RBK_EINVAL, "rbk_reorder_openmm: NULL system");
+    if (!sys->allocated) return fail(RBK_ESTATE, "rbk_reorder_openmm: call rbk_upload first");
+    cudaStream_t st = (cudaStream_t) stream;
+    const int n = sys->host.numFree + sys->host.numBodyAtoms;
+    if (force && n > 0) {
+        if (paddedNumAtoms <= 0) return fail(RBK_EINVAL, "rbk_reorder_openmm: paddedNumAtoms must be positive");
+        if (!sys->dForcePacked) RBK_CUDA(devAlloc(sys->dForcePacked, (size_t) 3*n));
+        gatherForcesKernel<<<(n + 255)/256, 256, 0, st>>>(force, paddedNumAtoms, sys->dev.atomLoc, n, sys->dForcePacked);
+        RBK_CUDA(cudaGetLastError());
+    }
+    if (int rc = setLocation(sys, location, st)) return rc;
+    if (force && n > 0) {
+        scatterForcesKernel<<<(n + 255)/256, 256, 0, st>>>(force, paddedNumAtoms, sys->dev.atomLoc, n, sys->dForcePacked);
+        RBK_CUDA(cudaGetLastError());
+    }
     return RBK_OK;
 }
 
@@ -718,7 +838,7 @@ int rbk_refined_kinetic_host(rbk_system* sys, double dt, const double* V, double
     if (!sys->mVel) return fail(RBK_ESTATE, "rbk_refined_kinetic_host: no step has been taken with rbk_execute_host");
     cudaStream_t st = (cudaStream_t) stream;
     const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
-    if (sys->host.numFree > 0) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+    if (sys->host.numFree > 0 && !sys->hostVelStale) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
     return rbk_refined_kinetic(sys, dt, sys->mVel, RBK_LAYOUT_VEC3, 0, out, stream);
 }
 
@@ -742,7 +862,8 @@ int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream
         RBK_CUDA(cudaMalloc((void**) &sys->mVel, bytes));
         RBK_CUDA(cudaMalloc((void**) &sys->mForce, bytes));
     }
-    if (sys->host.numFree > 0) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+    // (after an rbk_execute_host call that left the velocities on the device, V == NULL, the mirror is the current copy)
+    if (sys->host.numFree > 0 && !sys->hostVelStale) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
     return rbk_kinetic(sys, sys->mVel, RBK_LAYOUT_VEC3, 0, out, stream);
 }
 
@@ -750,6 +871,8 @@ int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, do
                         double* torque, void* stream) {
     if (!sys) return fail(RBK_EINVAL, "rbk_download_bodies: NULL system");
     if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_download_bodies: body system not uploaded");
+    if ((force || torque) && sys->forceTorqueStale)
+        return fail(RBK_ESTATE, "rbk_download_bodies: force and torque are not kept between rbk_part2_part1 and the closing rbk_part2");
     cudaStream_t st = (cudaStream_t) stream;
     const size_t ld = sys->dev.bodyStride;
     std::vector<double>& buf = sys->staging;
@@ -784,12 +907,9 @@ int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V
     return rbk_execute_host_hooks(sys, dt, steps, R, V, F, forces, nullptr, nullptr, user, stream);
 }
 
-int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, double* V, double* F, rbk_force_fn forces,
-                           rbk_positions_fn constrainPositions, rbk_velocities_fn constrainVelocities, void* user,
-                           void* stream) {
-    if (!sys || !R || !V || !F) return fail(RBK_EINVAL, "rbk_execute_host: NULL argument");
-    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_execute_host: body system not uploaded");
-    cudaStream_t st = (cudaStream_t) stream;
+namespace {
+int executeHost(rbk_system* sys, double dt, int steps, double* R, double* V, double* F, rbk_force_fn forces,
+                rbk_positions_fn constrainPositions, rbk_velocities_fn constrainVelocities, void* user, cudaStream_t st) {
     const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
     if (!sys->mPos) {
         RBK_CUDA(cudaMalloc((void**) &sys->mPos, bytes));
@@ -803,22 +923,37 @@ int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, dou
         for (cudaEvent_t* e : {&sys->evStart, &sys->evForces, &sys->evPart1, &sys->evPositions})
             RBK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
+    const bool hostFlow = forces || constrainPositions;       // something on the host needs R between Part 1 and Part 2
     if (!sys->mirrorsLoaded) {
+        if (!V) return fail(RBK_EINVAL, "rbk_execute_host: the first call after an upload needs V (the device mirror is empty)");
         RBK_CUDA(cudaMemcpyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
         RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
         RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
         sys->mirrorsLoaded = true;
+        sys->hostVelStale = false;
     }
+    else if (hostFlow)
+        // F holds the forces at the current positions and the caller may have re-evaluated them since the last call
+        // (updateParametersInContext, setParameter): the reference reads data.forces every step
+        // (ReferenceRigidBodyKernels.cpp:96), so Part 1's half kick must not use a stale mirror
+        RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
     const AtomView p{sys->mPos, 3, 1, rbk::FMT_F64, nullptr}, v{sys->mVel, 3, 1, rbk::FMT_F64, nullptr};
+    // step(n) = part1, forces, [part2+part1 in one pass, forces] x (n-1), part2 whenever nothing sits between Part 2 of
+    // one step and Part 1 of the next (no velocity hook, no diagnostics): rbk_part2_part1
+    const bool fuse = steps > 1 && !constrainVelocities && sys->refinedMode == RBK_REFINED_OFF;
     for (int i = 0; i < steps; i++) {
-        const AtomView fOld{sys->mForce, 3, 1, rbk::FMT_F64, nullptr}, fNew{sys->mForce2, 3, 1, rbk::FMT_F64, nullptr};
-        if (forces || constrainPositions) {
+        const bool last = i == steps - 1;
+        // new forces land in the second mirror while Part 1 still reads the old ones; without a host force evaluation the
+        // call's F is uploaded once (step 0) and serves every later step of the call
+        const bool newForces = hostFlow || i == 0;
+        const AtomView fOld{sys->mForce, 3, 1, rbk::FMT_F64, nullptr}, fNew{newForces ? sys->mForce2 : sys->mForce, 3, 1, rbk::FMT_F64, nullptr};
+        if (hostFlow) {
             // forces depend on the new positions: Part 1 -> positions to the host -> hooks -> forces to the device
             if (constrainPositions) {
                 sys->oldPositions.resize((size_t) sys->host.numAtoms*3);
                 std::memcpy(sys->oldPositions.data(), R, bytes);
             }
-            RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
+            if (i == 0 || !fuse) RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
             RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
             RBK_CUDA(cudaStreamSynchronize(st));
             if (constrainPositions && constrainPositions(sys->oldPositions.data(), R, sys->host.numAtoms, user))
@@ -826,32 +961,79 @@ int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, dou
             if (forces) forces(R, F, sys->host.numAtoms, user);
             RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, st));
         }
-        else {
-            // F is this step's input, known up front: its upload (H2D engine) runs under Part 1 and under the download
-            // of the positions (D2H engine); Part 2 waits for the forces only
+        else if (i == 0) {
+            // F is this call's input, known up front and the same for all of its steps: the upload (H2D engine) runs under
+            // Part 1 - and, in a one-step call, under the download of the positions (D2H engine); Part 2 waits for it only
             RBK_CUDA(cudaEventRecord(sys->evStart, st));
             RBK_CUDA(cudaStreamWaitEvent(sys->h2dStream, sys->evStart, 0));
             RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, sys->h2dStream));
             RBK_CUDA(cudaEventRecord(sys->evForces, sys->h2dStream));
             RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
-            RBK_CUDA(cudaEventRecord(sys->evPart1, st));
-            RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
-            RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
-            RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
+            if (last) {
+                RBK_CUDA(cudaEventRecord(sys->evPart1, st));
+                RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
+                RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
+                RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
+            }
             RBK_CUDA(cudaStreamWaitEvent(st, sys->evForces, 0));
         }
-        RBK_CUDA(stepPart2(sys, dt, p, v, fNew, st));
-        RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
-        if (!forces && !constrainPositions) RBK_CUDA(cudaStreamWaitEvent(st, sys->evPositions, 0));     // R is complete when `st` is
+        else if (!fuse) RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
+        if (fuse && !last) {
+            if (int rc = stepPart2Part1(sys, dt, p, v, fNew, st)) return rc;
+            if (!hostFlow && i == steps - 2) {                // positions are final after the last Part 1
+                RBK_CUDA(cudaEventRecord(sys->evPart1, st));
+                RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
+                RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
+                RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
+            }
+        }
+        else {
+            if (!hostFlow && !fuse && last && steps > 1) {
+                RBK_CUDA(cudaEventRecord(sys->evPart1, st));
+                RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
+                RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
+                RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
+            }
+            RBK_CUDA(stepPart2(sys, dt, p, v, fNew, st));
+        }
         if (constrainVelocities) {
+            RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
             RBK_CUDA(cudaStreamSynchronize(st));
             if (constrainVelocities(R, V, sys->host.numAtoms, user))
                 RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
         }
-        std::swap(sys->mForce, sys->mForce2);
+        if (newForces) std::swap(sys->mForce, sys->mForce2);             // mForce = the forces of the latest evaluation
     }
+    // velocities leave the device once per call (nothing on the host reads them between the steps of a call unless a
+    // velocity hook is installed), and not at all when the caller passes V = NULL
+    if (V && !constrainVelocities) RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
+    sys->hostVelStale = V == nullptr;
+    if (!hostFlow) RBK_CUDA(cudaStreamWaitEvent(st, sys->evPositions, 0));     // R is complete when `st` is
     RBK_CUDA(cudaStreamSynchronize(st));
     return RBK_OK;
+}
+} // namespace
+
+int rbk_execute_host_hooks(rbk_system* sys, double dt, int steps, double* R, double* V, double* F, rbk_force_fn forces,
+                           rbk_positions_fn constrainPositions, rbk_velocities_fn constrainVelocities, void* user,
+                           void* stream) {
+    if (!sys || !R || !F) return fail(RBK_EINVAL, "rbk_execute_host: NULL argument");
+    if (!V && constrainVelocities) return fail(RBK_EINVAL, "rbk_execute_host: a velocity hook needs V");
+    if (!sys->uploaded) return fail(RBK_ESTATE, "rbk_execute_host: body system not uploaded");
+    if (steps <= 0) return RBK_OK;
+    cudaStream_t st = (cudaStream_t) stream;
+    const int rc = executeHost(sys, dt, steps, R, V, F, forces, constrainPositions, constrainVelocities, user, st);
+    if (rc != RBK_OK) {
+        // leave nothing in flight that still reads or writes the caller's buffers; the mirrors are reloaded next time
+        const std::string message = g_error;
+        cudaStreamSynchronize(st);
+        if (sys->h2dStream) cudaStreamSynchronize(sys->h2dStream);
+        if (sys->d2hStream) cudaStreamSynchronize(sys->d2hStream);
+        cudaGetLastError();
+        sys->mirrorsLoaded = false;
+        g_error = message;
+    }
+    return rc;
 }
 
 } // extern "C"

@@ -43,6 +43,7 @@ struct DeviceSystem {
     int numBodies, numFree, numBodyAtoms, numTiles, numBodyTiles, numFreeBlocks;
     int rotationMode, maxBodySize, numSMs, splitPart1;
     int fusable;                 // every atom tile fits the shared-memory staging of the step-fused kernel
+    int lazyForceTorque;         // rbk_part2_part1 keeps F and tau in registers (nothing reads the planes before the next Part 2)
     int numWarpTiles;            // > 0: bodies have <= 4 atoms and the step-fused kernel runs one warp per 32-body tile
     int stageBodies;             // large-body systems: most bodies in any atom tile of <= kLargeBodyTileAtoms atoms (multiple of 4)
     size_t bodyStride, atomStride, freeStride;
@@ -122,6 +123,8 @@ cudaError_t launchRefinedKinetic(const DeviceSystem& S, const RefinedState& X, d
                                  unsigned* counter, double* out, cudaStream_t st);
 cudaError_t launchPotentialRefinement(const DeviceSystem& S, const RefinedState& X, double dt, AtomView force, double* partial,
                                       unsigned* counter, double* out, cudaStream_t st);
+// false when launchPart2Part1 skips the F / tau stores of its bodies (S.lazyForceTorque and the one-pass kernel is used)
+bool part2Part1LeavesForceTorque(const DeviceSystem& S);
 int part1LaunchesPerStep(const DeviceSystem& S);   // 1 (fused) or 2 (rotation kernel + atom kernel)
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out, cudaStream_t st);
 

@@ -322,10 +322,13 @@ void HostModel::buildGeometry(HostBody& b, const double* R, const double* F) {
     qC(b.q, t, b.torque);
 }
 
-// ---- RigidBody::buildDynamics (RigidBody.cpp:123-142); pcm accumulates exactly as the reference's does
+// ---- RigidBody::buildDynamics (RigidBody.cpp:123-142).  p = sum m v is SET here, like the GPU-side build
+// (rbk_build.cu).  The reference adds into its previous pcm (RigidBody.cpp:126-130: no reset), which doubles the
+// momentum when velocities are set twice; in its own start-up protocol (setPositions with V = 0, then
+// setVelocities) pcm is zero before the only call that matters, so the two agree wherever the reference is right.
 void HostModel::buildDynamics(HostBody& b, const double* V) {
     const int* atom = atomIndex.data() + numFree + b.loc;
-    V3 p = ld(b.pcm);
+    V3 p{0.0, 0.0, 0.0};
     for (int j = 0; j < b.N; j++) p = p + ld(V + 3*(size_t) atom[j])*mass[atom[j]];
     st(b.pcm, p);
     V3 vcm = divide(p, b.mass);

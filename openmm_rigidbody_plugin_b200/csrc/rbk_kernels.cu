@@ -20,6 +20,7 @@
 #include "rbk_step.cuh"
 
 #include <cstddef>
+#include <mutex>
 
 namespace rbk {
 namespace {
@@ -75,6 +76,45 @@ __device__ __forceinline__ void cpAsync16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Per-device launch configuration of one kernel instantiation (dynamic shared memory attribute, resident CTAs per SM).
+// Handles on different host threads may launch concurrently: the cache is guarded by a mutex (taken once per launch,
+// uncontended in the single-threaded case).
+struct LaunchCache {
+    std::mutex lock;
+    size_t attribute[kMaxDevices] = {};             // largest dynamic shared memory size the kernel was configured for
+    size_t occupancyFor[kMaxDevices] = {};          // the size perSM was computed for
+    int perSM[kMaxDevices] = {};
+    // returns resident CTAs per SM (>= 1) for `kernel` with `smem` bytes of dynamic shared memory, or an error
+    template <class Kernel> cudaError_t get(Kernel kernel, int threads, size_t smem, int& blocks) {
+        int device = 0;
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return e;
+        const bool cached = device >= 0 && device < kMaxDevices;
+        std::lock_guard<std::mutex> guard(lock);
+        if (!cached || attribute[device] < smem) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess) return e;
+            if (cached) attribute[device] = smem;
+        }
+        if (!cached || perSM[device] == 0 || occupancyFor[device] != smem) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, threads, smem);
+            if (e != cudaSuccess) return e;
+            if (blocks < 1) blocks = 1;
+            if (cached) { occupancyFor[device] = smem; perSM[device] = blocks; }
+            return cudaSuccess;
+        }
+        blocks = perSM[device];
+        return cudaSuccess;
+    }
+};
+
+// A persistent launch that fails leaves the tile counter wherever the CTAs that did run put it: re-arm it.
+inline cudaError_t launchResult(const DeviceSystem& S, cudaStream_t st) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) cudaMemsetAsync(S.tileCounter, 0, sizeof(int), st);
+    return e;
+}
 
 // smem plane k of a part1Kernel stage (r p q pi | F tau | 1/m | 1/I) <-> global state plane
 __device__ __forceinline__ int globalPlane(int k) {
@@ -645,23 +685,10 @@ __global__ void RBK_P2L_REGCAP part2LargeKernel(const DeviceSystem S, const doub
 template <bool NATIVE>
 cudaError_t launchPart2Large(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     const size_t smem = (size_t) part2LargeLayout(S.stageBodies).total;
-    static size_t configured[kMaxDevices] = {};                // the attribute is per device; grows with the largest system seen
-    static int perSM[kMaxDevices] = {};
-    int device = 0;
-    cudaGetDevice(&device);
-    const bool cached = device >= 0 && device < kMaxDevices;
-    if (!cached || configured[device] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(part2LargeKernel<NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return e;
-        if (cached) { configured[device] = smem; perSM[device] = 0; }
-    }
-    int blocks = cached ? perSM[device] : 0;
-    if (blocks == 0) {                                           // persistent CTAs: one full wave, whatever fits
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2LargeKernel<NATIVE>, kP2LThreads, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks < 1) blocks = 1;
-        if (cached) perSM[device] = blocks;
-    }
+    static LaunchCache cache;                                  // persistent CTAs: one full wave, whatever fits
+    int blocks = 0;
+    cudaError_t e = cache.get(part2LargeKernel<NATIVE>, kP2LThreads, smem, blocks);
+    if (e != cudaSuccess) return e;
     const int resident = S.numSMs*blocks;
     part2LargeKernel<NATIVE><<<S.numTiles < resident ? S.numTiles : resident, kP2LThreads, smem, st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
@@ -692,16 +719,27 @@ struct alignas(128) FusedStage {                    // 128-byte alignment: desti
     int loc[BODIES + 4];
     unsigned char localBody[ATOMS + 32];
 };
-template <int BODIES, int ATOMS, int STAGES>
+// GATHER (reordered atoms and / or the OpenMM boundary formats): the atoms' array slots travel two tiles ahead of the data in
+// a three-entry ring, so that the per-thread force requests never wait for an atomLoc look-up; the descriptor ring is one
+// entry deeper for it.
+template <int BODIES, int ATOMS, int STAGES, bool GATHER>
 struct FusedSmem {
     FusedStage<BODIES, ATOMS> stage[STAGES];
     unsigned long long bar[2];                      // one mbarrier per stage (bulk-copy completion)
     double acc[6][BODIES];
     double head[BODIES/32][6];
     int headKey[BODIES/32];
-    int4 meta[3];
-    int tileIdx[3];                                 // tile numbers of the current, next and next-but-one tile (ring)
+    int4 meta[GATHER ? 4 : 3];
+    int tileIdx[GATHER ? 4 : 3];                    // tile numbers of the current, next and next-but-one (GATHER: + one more) tile (ring)
+    int slot[GATHER ? 3 : 1][GATHER ? ATOMS : 4];   // GATHER: array slots of the atoms of the current, next and next-but-one tile (ring)
 };
+
+// An atom force as staged in shared memory (raw 8-byte word) -> double: fp64 arrays as they are, OpenMM's fixed-point
+// long long planes scaled by 2^-32 (platforms/cuda/src/kernels/rigidbodyintegrator.cu:341,369).
+template <bool NATIVE> __device__ __forceinline__ double stagedForce(const AtomView& force, double raw) {
+    if (NATIVE || force.fmt == FMT_F64) return raw;
+    return (1.0/4294967296.0)*(double) __double_as_longlong(raw);
+}
 
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier completion: one elected thread moves a whole plane
 // segment with one instruction instead of every thread issuing an 8-byte cp.async per element.
@@ -742,14 +780,21 @@ __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k 
 // smaller footprint lets four CTAs share an SM, which hide each other's load latency (NO-SQUISH: 112 registers).
 // P1ONLY: Part 1 alone through the same pipeline (the step's opening launch and callers that evaluate forces between
 // two launches): no forces are staged, the stored F and tau planes take their place in the stage, Part 2's phases drop out.
-template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY>
+// GATHER: the instantiation for everything that is not "fp64 arrays in plugin order" - reordered atoms (atomLoc) and the
+// OpenMM-CUDA boundary formats (float4 posq + correction, mixed4 velm, fixed-point force planes): the state planes, body-frame
+// coordinates, offsets and body bytes still arrive by TMA (they are the handle's own, in body order), the forces by
+// per-thread 8-byte cp.async through the slot ring (raw words, converted where they are consumed); positions and velocities
+// leave through the format-aware stores.  storeFT = false: interior step of step(n) - nothing reads F and tau before the
+// next Part 2 rewrites them, so they stay in registers (48 B per body-step less).
+template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER>
 __global__ void __launch_bounds__(BODIES, (STAGES == 2 ? 256 : 512)/BODIES)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force,
-                 const __grid_constant__ TileMaps maps, const bool useMaps) {
+                 const __grid_constant__ TileMaps maps, const bool useMaps, const bool storeFT) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     typedef FusedStage<BODIES, ATOMS> Stage;
-    FusedSmem<BODIES, ATOMS, STAGES>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS, STAGES>*>(smemRaw);
+    FusedSmem<BODIES, ATOMS, STAGES, GATHER>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS, STAGES, GATHER>*>(smemRaw);
     constexpr int kBlock = BODIES, kWarps = BODIES/32;          // shadow the file-level constants inside this kernel
+    constexpr int RING = GATHER ? 4 : 3;
     const int4* const tileMeta = BODIES == 32 ? S.warpTileMeta : S.tileMeta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
@@ -760,13 +805,30 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     // tile's forces are one contiguous Vec3 range (water tiles always are); otherwise per-thread cp.async.
     const bool contiguousForces = S.atomLoc == nullptr && force.sa == 3 && force.sc == 1 && (reinterpret_cast<size_t>(force.p) & 15) == 0;
     auto bulkOK = [&](int4 m) {
-        return (P1ONLY || (contiguousForces && ((S.numFree + m.z) & 1) == 0)) && (m.x & 3) == 0 && (m.y & 3) == 0 &&
+        return (P1ONLY || GATHER || (contiguousForces && ((S.numFree + m.z) & 1) == 0)) && (m.x & 3) == 0 && (m.y & 3) == 0 &&
                (m.z & 1) == 0 && (m.w & 1) == 0;
     };
     auto tensorOK = [&](int4 m) {
-        return BODIES == 32 && useMaps && (P1ONLY || (contiguousForces && ((S.numFree + m.z) & 1) == 0 && (m.w & 1) == 0));
+        return BODIES == 32 && useMaps && (P1ONLY || GATHER || (contiguousForces && ((S.numFree + m.z) & 1) == 0 && (m.w & 1) == 0));
     };
-    auto request = [&](int4 m, int st) {
+    // GATHER: array slots of a tile's atoms into ring entry `ring` (two tiles ahead of the data)
+    auto requestSlots = [&](int4 m, int ring) {
+        int* dst = sm.slot[GATHER ? ring : 0];
+        if (S.atomLoc != nullptr)
+            for (int j = tid; j < m.w; j += kBlock) cpAsync4(dst + j, S.atomLoc + S.numFree + m.z + j);
+        else
+            for (int j = tid; j < m.w; j += kBlock) dst[j] = S.numFree + m.z + j;
+    };
+    // GATHER: the tile's forces, one raw 8-byte word per component (double or fixed-point long long), through the slots
+    auto requestForces = [&](int4 m, Stage& T, const int* slots) {
+        for (int j = tid; j < m.w; j += kBlock) {
+            const double* fp = force.p + (long long) slots[j]*force.sa;
+            cpAsync8(&T.f[3*j], fp);
+            cpAsync8(&T.f[3*j + 1], fp + force.sc);
+            cpAsync8(&T.f[3*j + 2], fp + 2*force.sc);
+        }
+    };
+    auto request = [&](int4 m, int st, const int* slots) {
         Stage& T = sm.stage[st];
         const int lbFirst = m.z & ~15;                         // 16-byte granules of the byte array
         const unsigned lbBytes = (unsigned) (((m.z + m.w - lbFirst) + 15) & ~15);
@@ -777,19 +839,20 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             if (tid == 0) {
                 fenceProxyAsync();
                 constexpr unsigned boxBytes = (P1ONLY ? 24u : 18u)*BODIES*8u + 3u*ATOMS*8u + 4u*BODIES;
-                mbarExpectTx(&sm.bar[st], boxBytes + (P1ONLY ? 0u : 24u*m.w) + lbBytes);
+                mbarExpectTx(&sm.bar[st], boxBytes + (P1ONLY || GATHER ? 0u : 24u*m.w) + lbBytes);
                 tmaLoad2D(&T.body[0][0], P1ONLY ? &maps.state24 : &maps.state18, m.x, 0, &sm.bar[st]);
                 tmaLoad2D(&T.d[0][0], &maps.dxyz, m.z, 0, &sm.bar[st]);
                 bulkCopy(&T.loc[0], S.loc + m.x, 4u*BODIES, &sm.bar[st]);
-                if (!P1ONLY) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
+                if (!P1ONLY && !GATHER) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
                 bulkCopy(&T.localBody[0], S.localBody + lbFirst, lbBytes, &sm.bar[st]);
             }
+            if (GATHER && !P1ONLY) requestForces(m, T, slots);
             return;
         }
         if (bulkOK(m)) {
             if (tid == 0) {
                 fenceProxyAsync();                             // earlier generic-proxy writes to this stage are ordered first
-                mbarExpectTx(&sm.bar[st], (unsigned) ((kFPlanes + (P1ONLY ? 6 : 0))*8*m.y + 4*m.y + (P1ONLY ? 24 : 48)*m.w) + lbBytes);
+                mbarExpectTx(&sm.bar[st], (unsigned) ((kFPlanes + (P1ONLY ? 6 : 0))*8*m.y + 4*m.y + (P1ONLY || GATHER ? 24 : 48)*m.w) + lbBytes);
                 const double* g = S.state + (size_t) m.x;
 #pragma unroll
                 for (int k = 0; k < kFPlanes; k++) bulkCopy(&T.body[k][0], g + fusedGlobalPlane(k)*ld, 8u*m.y, &sm.bar[st]);
@@ -800,9 +863,10 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
 #pragma unroll
                     for (int k = 0; k < 6; k++) bulkCopy(&T.f[k*BODIES], g + ((int) PL_F + k)*ld, 8u*m.y, &sm.bar[st]);
                 }
-                else bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
+                else if (!GATHER) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
                 bulkCopy(&T.localBody[0], S.localBody + lbFirst, lbBytes, &sm.bar[st]);
             }
+            if (GATHER && !P1ONLY) requestForces(m, T, slots);
             return;
         }
         if (tid < m.y) {
@@ -821,7 +885,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             cpAsync8(&T.d[1][j], g + as);
             cpAsync8(&T.d[2][j], g + 2*as);
             if (!P1ONLY) {
-                const double* fp = force.p + atomSlot(S, S.numFree + m.z + j)*force.sa;
+                const double* fp = force.p + (GATHER ? (long long) slots[j] : atomSlot(S, S.numFree + m.z + j))*force.sa;
                 cpAsync8(&T.f[3*j], fp);
                 cpAsync8(&T.f[3*j + 1], fp + force.sc);
                 cpAsync8(&T.f[3*j + 2], fp + 2*force.sc);
@@ -848,6 +912,29 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         if (old == numTiles - 1) *S.tileCounter = 0;
         return G + old;
     };
+    // Requests issued while tile `it` is processed: the data of tile it+1 into stage `st`; then the claim of one more
+    // tile and its descriptor - GATHER: one tile further ahead (it+3), with the array slots of tile it+2 in between.
+    auto advance = [&](int it, int st) {
+        if (sm.tileIdx[(it + 1) % RING] < numTiles) {
+            request(sm.meta[(it + 1) % RING], st, sm.slot[GATHER ? (it + 1) % 3 : 0]);
+            if (!GATHER) {
+                if (tid == 0) {
+                    const int after = claim();
+                    sm.tileIdx[(it + 2) % RING] = after;
+                    if (after < numTiles) cpAsync16(&sm.meta[(it + 2) % RING], tileMeta + after);
+                }
+            }
+            else if (sm.tileIdx[(it + 2) % RING] < numTiles) {
+                requestSlots(sm.meta[(it + 2) % RING], (it + 2) % 3);
+                if (tid == 0) {
+                    const int after = claim();
+                    sm.tileIdx[(it + 3) % RING] = after;
+                    if (after < numTiles) cpAsync16(&sm.meta[(it + 3) % RING], tileMeta + after);
+                }
+            }
+        }
+        cpCommit();
+    };
     const int tile0 = blockIdx.x;
     if (tile0 < numTiles) {
         if (tid == 0) {
@@ -856,17 +943,30 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             sm.tileIdx[1] = tile1;
             sm.meta[0] = tileMeta[tile0];
             if (tile1 < numTiles) sm.meta[1] = tileMeta[tile1];
+            if (GATHER) {
+                const int tile2 = tile1 < numTiles ? claim() : tile1;      // a CTA stops claiming at its first out-of-range claim
+                sm.tileIdx[2] = tile2;
+                if (tile2 < numTiles) sm.meta[2] = tileMeta[tile2];
+            }
             mbarInit(&sm.bar[0], 1);
             mbarInit(&sm.bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        request(sm.meta[0], 0);
+        if (GATHER) {
+            requestSlots(sm.meta[0], 0);
+            if (sm.tileIdx[1] < numTiles) requestSlots(sm.meta[1], 1);
+            cpCommit();
+            cpWait<0>();
+            __syncthreads();
+        }
+        request(sm.meta[0], 0, sm.slot[0]);
         cpCommit();
-        for (int it = 0; sm.tileIdx[it % 3] < numTiles; it++) {
-            const int4 m = sm.meta[it % 3];
+        for (int it = 0; sm.tileIdx[it % RING] < numTiles; it++) {
+            const int4 m = sm.meta[it % RING];
             const int cur = STAGES == 2 ? (it & 1) : 0;
             Stage& T = sm.stage[cur];
+            const int* const slots = sm.slot[GATHER ? it % 3 : 0];
             if (!SMALL && !P1ONLY) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) sm.acc[k][tid] = 0.0;
@@ -874,17 +974,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             }
             arrived(m, cur);                                   // this tile (+ the next tile's descriptor) landed
             __syncthreads();
-            if (STAGES == 2) {
-                if (sm.tileIdx[(it + 1) % 3] < numTiles) {
-                    request(sm.meta[(it + 1) % 3], cur ^ 1);
-                    if (tid == 0) {
-                        const int after = claim();
-                        sm.tileIdx[(it + 2) % 3] = after;
-                        if (after < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + after);
-                    }
-                }
-                cpCommit();
-            }
+            if (STAGES == 2) advance(it, cur ^ 1);
 
             // ---- B: forces and torques -> per-body sums.
             // SMALL (every body has <= kSmallBody atoms, e.g. water): each body's thread sums its own atoms straight
@@ -908,7 +998,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     if (valid) {
                         key = T.localBody[j + shift];
                         const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
-                        const d3 f = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
+                        const d3 f = {stagedForce<NATIVE>(force, T.f[3*j]), stagedForce<NATIVE>(force, T.f[3*j + 1]), stagedForce<NATIVE>(force, T.f[3*j + 2])};
                         const d4 q = {T.body[6][key], T.body[7][key], T.body[8][key], T.body[9][key]};
                         const d3 delta = bodyToSpace(q, d);
                         T.f[3*j] = delta.x; T.f[3*j + 1] = delta.y; T.f[3*j + 2] = delta.z;     // kept for the velocities
@@ -955,7 +1045,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     const int j0 = T.loc[tid] - m.z, j1 = (tid + 1 < m.y ? T.loc[tid + 1] - m.z : m.w);
                     for (int j = j0; j < j1; j++) {
                         const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
-                        const d3 f = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
+                        const d3 f = {stagedForce<NATIVE>(force, T.f[3*j]), stagedForce<NATIVE>(force, T.f[3*j + 1]), stagedForce<NATIVE>(force, T.f[3*j + 2])};
                         const d3 delta = bodyToSpace(q, d);
                         T.f[3*j] = delta.x; T.f[3*j + 1] = delta.y; T.f[3*j + 2] = delta.z;     // kept for the velocities
                         F = F + f;
@@ -990,7 +1080,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 storePlane3(s + PL_P*ld, ld, p);
                 storePlane4(s + PL_Q*ld, ld, q);
                 storePlane4(s + PL_PI*ld, ld, pi);
-                if (!P1ONLY) {
+                if (!P1ONLY && storeFT) {
                     storePlane3(s + PL_F*ld, ld, F);
                     storePlane3(s + PL_TAU*ld, ld, tau);
                 }
@@ -1002,7 +1092,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             // ---- D: thread per atom: velocities at the end of this step, positions of the next
             for (int j = tid; j < m.w; j += kBlock) {
                 const int k = T.localBody[j + shift] & (BODIES - 1);      // index inside the 128-body atom tile -> this tile
-                const long long slot = atomSlot(S, S.numFree + m.z + j);
+                const long long slot = GATHER ? (long long) slots[j] : atomSlot(S, S.numFree + m.z + j);
                 if (!P1ONLY) {
                     const d3 delta = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
                     const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
@@ -1015,17 +1105,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 storeAtom<NATIVE>(pos, slot, atomPosition(r, q, d));
             }
             __syncthreads();
-            if (STAGES == 1) {                                 // the single stage is free again: request the next tile
-                if (sm.tileIdx[(it + 1) % 3] < numTiles) {
-                    request(sm.meta[(it + 1) % 3], 0);
-                    if (tid == 0) {
-                        const int after = claim();
-                        sm.tileIdx[(it + 2) % 3] = after;
-                        if (after < numTiles) cpAsync16(&sm.meta[(it + 2) % 3], tileMeta + after);
-                    }
-                }
-                cpCommit();
-            }
+            if (STAGES == 1) advance(it, 0);                   // the single stage is free again: request the next tile
         }
         cpWait<0>();
     }
@@ -1061,8 +1141,10 @@ __global__ void __launch_bounds__(256) freeAtomsKernel(const DeviceSystem S, con
 constexpr int kSideFreeThreads = RBK_SIDE_FREE_THREADS;                // CTA size of the free-atom launch that shares the SMs with the body kernels
 
 template <int PHASE, bool NATIVE>
-void launchFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    if (S.numFree > 0) freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
+cudaError_t launchFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+    if (S.numFree == 0) return cudaSuccess;
+    freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
+    return cudaGetLastError();
 }
 
 // Free atoms of a large-body launch sequence on the side stream: fork before the body kernels are launched, the free-atom
@@ -1077,7 +1159,8 @@ inline cudaError_t sideFork(const SideStream* side, cudaStream_t st) {
 template <int PHASE, bool NATIVE>
 cudaError_t sideFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, const SideStream* side) {
     freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + kSideFreeThreads - 1)/kSideFreeThreads, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
-    return cudaEventRecord(side->join, side->stream);
+    const cudaError_t e = cudaGetLastError();
+    return e != cudaSuccess ? e : cudaEventRecord(side->join, side->stream);
 }
 inline cudaError_t sideJoin(const SideStream* side, cudaStream_t st) { return cudaStreamWaitEvent(st, side->join, 0); }
 
@@ -1170,73 +1253,65 @@ template <bool EXACT, bool FUSED, bool NATIVE>
 cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st,
                                const SideStream* side = nullptr) {
     const size_t smem = FUSED ? sizeof(Part1Smem) : offsetof(Part1Smem, d);
-    static bool configured[kMaxDevices] = {};                  // the attribute is per device
-    int device = 0;
-    cudaGetDevice(&device);
-    if (device < 0 || device >= kMaxDevices || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(part1Kernel<EXACT, FUSED, NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return e;
-        if (device >= 0 && device < kMaxDevices) configured[device] = true;
-    }
+    static LaunchCache cache;
+    int blocks = 0;
+    cudaError_t e = cache.get(part1Kernel<EXACT, FUSED, NATIVE>, kBlock, smem, blocks);
+    if (e != cudaSuccess) return e;
     // persistent CTAs: one wave that fills every SM
     const bool overlap = !FUSED && freeAtoms && sideUsable(S, side);
-    if (overlap) {
-        cudaError_t e = sideFork(side, st);
-        if (e != cudaSuccess) return e;
-    }
-    else if (freeAtoms) launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
+    if (overlap) e = sideFork(side, st);
+    else if (freeAtoms) e = launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
+    if (e != cudaSuccess) return e;
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
     const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
-    if (tiles > 0) part1Kernel<EXACT, FUSED, NATIVE><<<tiles < resident ? tiles : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
+    if (tiles > 0) {
+        part1Kernel<EXACT, FUSED, NATIVE><<<tiles < resident ? tiles : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
+        e = launchResult(S, st);
+        if (e != cudaSuccess) return e;
+    }
     if (overlap) {
-        cudaError_t e = sideFree<1, NATIVE>(S, dt, pos, vel, force, side);
+        e = sideFree<1, NATIVE>(S, dt, pos, vel, force, side);
         if (e != cudaSuccess) return e;
     }
     if (!FUSED && S.numTiles > 0) atomPositionKernel<NATIVE><<<S.numTiles, kBlock, 0, st>>>(S, pos);
-    if (overlap) return sideJoin(side, st);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return overlap ? sideJoin(side, st) : cudaSuccess;
 }
 
-template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES, bool P1ONLY>
+template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER>
 cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
-                             bool freeAtoms = true) {
-    typedef FusedSmem<BODIES, ATOMS, STAGES> Smem;
-    static bool configured[kMaxDevices] = {};
-    int device = 0;
-    cudaGetDevice(&device);
-    if (device < 0 || device >= kMaxDevices || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
+                             bool freeAtoms = true, bool storeFT = true) {
+    typedef FusedSmem<BODIES, ATOMS, STAGES, GATHER> Smem;
+    constexpr bool NATIVE = !GATHER;
+    auto kernel = part2Part1Kernel<EXACT, SMALL, NATIVE, BODIES, ATOMS, STAGES, P1ONLY, GATHER>;
+    static LaunchCache cache;
+    int blocks = 0;                                            // persistent CTAs: one full wave, whatever fits
+    cudaError_t e = cache.get(kernel, BODIES, sizeof(Smem), blocks);
+    if (e != cudaSuccess) return e;
+    if (freeAtoms) {
+        e = launchFree<P1ONLY ? 1 : 3, NATIVE>(S, dt, pos, vel, force, st);
         if (e != cudaSuccess) return e;
-        if (device >= 0 && device < kMaxDevices) configured[device] = true;
     }
-    if (freeAtoms) launchFree<P1ONLY ? 1 : 3, true>(S, dt, pos, vel, force, st);
     const int tiles = BODIES == 32 ? S.numWarpTiles : S.numTiles;
-    static int perSM[kMaxDevices] = {};                        // persistent CTAs: one full wave, whatever fits
-    int blocks = device >= 0 && device < kMaxDevices ? perSM[device] : 0;
-    if (blocks == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY>, BODIES, sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        if (blocks < 1) blocks = 1;
-        if (device >= 0 && device < kMaxDevices) perSM[device] = blocks;
-    }
     const int resident = S.numSMs*blocks;
-    if (tiles > 0)
-    {
+    if (tiles > 0) {
         static const TileMaps noMaps = {};
         const bool useMaps = BODIES == 32 && S.tileMaps != nullptr;
-        part2Part1Kernel<EXACT, SMALL, true, BODIES, ATOMS, STAGES, P1ONLY><<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(
-            S, dt, pos, vel, force, useMaps ? *S.tileMaps : noMaps, useMaps);
+        kernel<<<tiles < resident ? tiles : resident, BODIES, sizeof(Smem), st>>>(S, dt, pos, vel, force, useMaps ? *S.tileMaps : noMaps,
+                                                                                  useMaps, storeFT);
     }
-    return cudaGetLastError();
+    return launchResult(S, st);
 }
 
-template <bool EXACT, bool SMALL>
-cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
+template <bool EXACT, bool SMALL, bool GATHER>
+cudaError_t launchFused(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st, bool storeFT) {
     // One warp per CTA pays off where a tile's phases are long and uneven (exact rotation: 0.1445 -> 0.137 ms at 1 M
     // waters).  NO-SQUISH (112 registers) instead runs four single-stage CTAs of four warps per SM: mode 10
     // 0.177 -> 0.150 ms, mode 3 0.110 ms; one-warp single-stage CTAs measured 0.147 / 0.118 ms, so the four-warp shape stays.
-    if (EXACT && SMALL && S.numWarpTiles > 0) return launchFusedShape<EXACT, true, 32, kWarpTileAtoms, 2, false>(S, dt, pos, vel, force, st);
-    return launchFusedShape<EXACT, SMALL, kBlock, kTileAtoms, EXACT ? 2 : 1, false>(S, dt, pos, vel, force, st);
+    if (EXACT && SMALL && S.numWarpTiles > 0)
+        return launchFusedShape<EXACT, true, 32, kWarpTileAtoms, 2, false, GATHER>(S, dt, pos, vel, force, st, true, storeFT);
+    return launchFusedShape<EXACT, SMALL, kBlock, kTileAtoms, EXACT ? 2 : 1, false, GATHER>(S, dt, pos, vel, force, st, true, storeFT);
 }
 
 bool nativeIO(const AtomView& a, const AtomView& b, const AtomView& c) {
@@ -1247,9 +1322,12 @@ template <bool NATIVE>
 cudaError_t launchPart1Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st,
                                const SideStream* side = nullptr) {
     const bool exact = S.rotationMode == 0, fused = !S.splitPart1;
-    // exact rotation on water-like bodies, fp64 arrays: Part 1 alone through the TMA-staged one-warp-tile pipeline
-    if (NATIVE && exact && S.numWarpTiles > 0)
-        return launchFusedShape<true, true, 32, kWarpTileAtoms, 2, true>(S, dt, pos, vel, force, st, freeAtoms);
+    // exact rotation on water-like bodies: Part 1 alone through the TMA-staged one-warp-tile pipeline (fp64 arrays in
+    // plugin order: the plain instantiation; reordered atoms / OpenMM formats: the GATHER one)
+    if (exact && S.numWarpTiles > 0) {
+        if (NATIVE && S.atomLoc == nullptr) return launchFusedShape<true, true, 32, kWarpTileAtoms, 2, true, false>(S, dt, pos, vel, force, st, freeAtoms);
+        return launchFusedShape<true, true, 32, kWarpTileAtoms, 2, true, true>(S, dt, pos, vel, force, st, freeAtoms);
+    }
     if (exact) return fused ? launchPart1Variant<true, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<true, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st, side);
     return fused ? launchPart1Variant<false, true, NATIVE>(S, dt, pos, vel, force, freeAtoms, st) : launchPart1Variant<false, false, NATIVE>(S, dt, pos, vel, force, freeAtoms, st, side);
 }
@@ -1281,7 +1359,10 @@ cudaError_t launchPart2Formats(const DeviceSystem& S, double dt, AtomView pos, A
         cudaError_t e = sideFork(side, st);
         if (e != cudaSuccess) return e;
     }
-    else if (freeAtoms) launchFree<2, NATIVE>(S, dt, pos, vel, force, st);
+    else if (freeAtoms) {
+        cudaError_t e = launchFree<2, NATIVE>(S, dt, pos, vel, force, st);
+        if (e != cudaSuccess) return e;
+    }
     if (S.numTiles > 0 && S.splitPart1) {
         cudaError_t e = launchPart2Large<NATIVE>(S, dt, pos, vel, force, st);
         if (e != cudaSuccess || !overlap) return e;
@@ -1302,8 +1383,8 @@ cudaError_t launchPart2(const DeviceSystem& S, double dt, AtomView pos, AtomView
 cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
                              const SideStream* side) {
     if (S.numTiles + S.numFreeBlocks == 0) return cudaSuccess;
-    // the one-pass kernel stages fp64 forces with cp.async; other formats / large bodies take the two kernels
-    if (!S.fusable || !nativeIO(pos, vel, force)) {
+    // large bodies take separate kernels (the one-pass kernel stages a whole tile's atoms in shared memory)
+    if (!S.fusable) {
         // the free atoms still take both halves in ONE launch (same arithmetic, one pass over their data).  Large-body
         // systems: that launch goes to the side stream, AFTER the persistent part2LargeKernel has taken its SMs - the
         // free atoms' small CTAs run in the registers the body kernels leave unused and in their tails (disjoint atoms,
@@ -1314,9 +1395,11 @@ cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, Ato
             cudaError_t e = sideFork(side, st);
             if (e != cudaSuccess) return e;
         }
-        else if (native) launchFree<3, true>(S, dt, pos, vel, force, st);
-        else launchFree<3, false>(S, dt, pos, vel, force, st);
-        if (S.numTiles == 0) return cudaGetLastError();
+        else {
+            cudaError_t e = native ? launchFree<3, true>(S, dt, pos, vel, force, st) : launchFree<3, false>(S, dt, pos, vel, force, st);
+            if (e != cudaSuccess) return e;
+        }
+        if (S.numTiles == 0) return cudaSuccess;
         cudaError_t e = native ? launchPart2Formats<true>(S, dt, pos, vel, force, false, st) : launchPart2Formats<false>(S, dt, pos, vel, force, false, st);
         if (e != cudaSuccess) return e;
         if (overlap) {
@@ -1328,9 +1411,16 @@ cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, Ato
         return overlap ? sideJoin(side, st) : cudaSuccess;
     }
     const bool small = S.maxBodySize <= kSmallBody;
-    if (S.rotationMode == 0) return small ? launchFused<true, true>(S, dt, pos, vel, force, st) : launchFused<true, false>(S, dt, pos, vel, force, st);
-    return small ? launchFused<false, true>(S, dt, pos, vel, force, st) : launchFused<false, false>(S, dt, pos, vel, force, st);
+    const bool storeFT = !S.lazyForceTorque;
+    if (nativeIO(pos, vel, force) && S.atomLoc == nullptr) {
+        if (S.rotationMode == 0) return small ? launchFused<true, true, false>(S, dt, pos, vel, force, st, storeFT) : launchFused<true, false, false>(S, dt, pos, vel, force, st, storeFT);
+        return small ? launchFused<false, true, false>(S, dt, pos, vel, force, st, storeFT) : launchFused<false, false, false>(S, dt, pos, vel, force, st, storeFT);
+    }
+    if (S.rotationMode == 0) return small ? launchFused<true, true, true>(S, dt, pos, vel, force, st, storeFT) : launchFused<true, false, true>(S, dt, pos, vel, force, st, storeFT);
+    return small ? launchFused<false, true, true>(S, dt, pos, vel, force, st, storeFT) : launchFused<false, false, true>(S, dt, pos, vel, force, st, storeFT);
 }
+
+bool part2Part1LeavesForceTorque(const DeviceSystem& S) { return !(S.fusable && S.lazyForceTorque) || S.numTiles == 0; }
 
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out,
                           cudaStream_t st) {

@@ -173,6 +173,17 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_part2_openmm(self.h, float(dt), _ptr(posq), _ptr(posqCorrection), _ptr(velm), _ptr(force),
                                         int(paddedNumAtoms), int(precision), _stream(stream)))
 
+    def part2_part1_openmm(self, dt, posq, posqCorrection, velm, force, paddedNumAtoms, precision, stream=None):
+        """Part 2 of this step fused with Part 1 of the next on the OpenMM-CUDA formats (rbk_part2_part1_openmm)."""
+        check(self.lib.rbk_part2_part1_openmm(self.h, float(dt), _ptr(posq), _ptr(posqCorrection), _ptr(velm), _ptr(force),
+                                              int(paddedNumAtoms), int(precision), _stream(stream)))
+
+    def reorder_openmm(self, location, force, paddedNumAtoms, stream=None):
+        """The CUDA platform's ReorderListener on the device: permute the owned atoms' forces to the new order and install
+        the new plugin-order -> device-index map."""
+        loc = None if location is None else np.ascontiguousarray(location, dtype=np.int32)
+        check(self.lib.rbk_reorder_openmm(self.h, _i(loc), _ptr(force), int(paddedNumAtoms), _stream(stream)))
+
     def free_delta_openmm(self, dt, velm, force, paddedNumAtoms, precision, posDelta, stream=None):
         """posDelta.xyz = (v + f invMass dt/2) dt for the free atoms (the hook before integration.applyConstraints)."""
         check(self.lib.rbk_free_delta_openmm(self.h, float(dt), _ptr(velm), _ptr(force), int(paddedNumAtoms), int(precision),
@@ -241,7 +252,8 @@ class DeviceRigidBodySystem:
         return o
 
     def execute_host(self, dt, steps, R, V, F, forces=None, stream=None, constrain_positions=None, constrain_velocities=None):
-        """R, V, F: host float64 buffers [N,3] (numpy arrays or pinned torch CPU tensors), updated in place.
+        """R, V, F: host float64 buffers [N,3] (numpy arrays or pinned torch CPU tensors), updated in place; V is written
+        once per call (after its last step) and may be None: the velocities then stay on the device until a later call.
         constrain_positions(oldR_ptr, R_ptr, n, user) / constrain_velocities(R_ptr, V_ptr, n, user) are the free-atom
         constraint / virtual-site hooks of rbk_execute_host_hooks; they return nonzero when they changed the array."""
         cb = _lib.FORCE_FN(forces) if forces is not None else C.cast(None, _lib.FORCE_FN)

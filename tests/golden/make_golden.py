@@ -68,19 +68,30 @@ def run_case(name, sysd, modes, checkpoints, tether=False, full_bodies=True):
         s.close()
 
 
-def drift_case(name, sysd, modes, steps=10000, every=50):
+def _energy_series(sysd, mode, steps, every):
+    s = CpuStepper("reference", sysd["bodyIndices"], sysd["masses"], mode)
+    common.init_like_reference(s, sysd, tether=True)
+    E = []
+    for i in range(steps // every + 1):
+        U = s.compute_forces()
+        ke = s.kinetic()
+        E.append([i * every * DT, U, ke[0], ke[1]])
+        if i < steps // every:
+            s.step(DT, every)
+    return s, E
+
+
+def drift_case(name, sysd, modes, steps=10000, every=50, twin=False):
+    """twin=True also records the TRUE reference run from initial velocities scaled by (1 + 1e-13): how far the
+    reference's own energy series and fitted slope move under a perturbation at rounding level (the dynamics is chaotic)."""
     for mode in modes:
-        s = CpuStepper("reference", sysd["bodyIndices"], sysd["masses"], mode)
-        common.init_like_reference(s, sysd, tether=True)
-        E = []
-        for i in range(steps // every + 1):
-            U = s.compute_forces()
-            ke = s.kinetic()
-            E.append([i * every * DT, U, ke[0], ke[1]])
-            if i < steps // every:
-                s.step(DT, every)
+        s, E = _energy_series(sysd, mode, steps, every)
         out = {k: sysd[k] for k in ("bodyIndices", "masses", "R", "V", "F", "charges")}
         out.update(mode=np.int32(mode), dt=np.float64(DT), every=np.int32(every), series=np.array(E))
+        if twin:
+            s2, E2 = _energy_series(dict(sysd, V=sysd["V"] * (1.0 + 1e-13)), mode, steps, every)
+            out["series_twin"] = np.array(E2)
+            s2.close()
         R, V, _ = s.get_state()
         out["R_end"], out["V_end"] = R, V
         path = os.path.join(HERE, f"{name}_mode{mode}.npz")
@@ -149,6 +160,8 @@ def main():
     for nm, (sysd, modes) in common.edge_cases().items():
         run_case("edge_" + nm, sysd, modes, [1, 5])
     drift_case("drift_water128", synth.water_box(128, seed=14), [0, 10])
+    # SURVEY.md section 8c's probe size: 512 waters, with the reference's own rounding-level twin
+    drift_case("drift_water512", synth.water_box(512, seed=14), [0], twin=True)
     gravity_case("gravity_water128", synth.water_box(128, seed=15), [0, 10])
     special_function_kats()
 

@@ -85,3 +85,23 @@ def test_no_device_means_loud_failure(rbk):
     s.update(np.array([[0, 0, 0], [0.1, 0, 0], [0, 0.1, 0.0]]), np.zeros((3, 3)), np.zeros((3, 3)), True, True)
     with pytest.raises(RbkError, match="no CPU fallback"):
         s.upload()
+
+
+def test_velocities_set_twice_give_the_same_momentum():
+    """setVelocities(V) twice must leave the same body momenta as once (the reference's buildDynamics adds into its
+    previous pcm, RigidBody.cpp:126-130, which doubles p and quadruples 2Kt; the product SETS p = sum m v, like its
+    GPU-side build)."""
+    from openmm_rigidbody_plugin_b200 import DeviceRigidBodySystem
+    sysd = common.synth.mixed_system(50, 30, seed=3, max_atoms=12)
+    n = len(sysd["masses"])
+    s = DeviceRigidBodySystem(sysd["bodyIndices"], sysd["masses"], 0)
+    s.update(sysd["R"], np.zeros((n, 3)), sysd["F"], True, True)
+    s.update(V=sysd["V"], geometry=False, velocities=True)
+    once = s.host_bodies()
+    s.update(V=sysd["V"], geometry=False, velocities=True)
+    twice = s.host_bodies()
+    for k in ("pcm", "pi", "twoK"):
+        assert np.array_equal(once[k], twice[k]), k
+    s.update(sysd["R"], sysd["V"], sysd["F"], True, True)
+    third = s.host_bodies()
+    assert np.array_equal(once["pcm"], third["pcm"]) and np.allclose(once["twoK"], third["twoK"], rtol=1e-13)

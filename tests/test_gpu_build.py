@@ -1,5 +1,5 @@
-"""GPU-side body build (rbk_update_device) against the host model, which is itself
-bit-identical to the reference's RigidBodySystem::update."""
+"""GPU-side body build (rbk_update_device) against the CPU oracle (RigidBodySystem::update
+restated, oracle/rb_oracle.c, bit-identical to the reference sources) and against the host model."""
 import numpy as np
 import pytest
 
@@ -66,6 +66,19 @@ def test_device_build_matches_host_build(case):
     assert float((Va - Vb).abs().max()) <= 1e-10 * float(Va.abs().max())
     assert np.allclose(a.kinetic(Va), b.kinetic(Vb), rtol=1e-11)
     assert ha["dof"].sum() + a.counts()["numFree"] == a.counts()["numDOF"]
+    # ... and directly against the oracle: body state right after the build, trajectory after three steps
+    from oracle.checkers import CpuStepper
+    o = CpuStepper("oracle", sysd["bodyIndices"], sysd["masses"], mode)
+    common.init_like_reference(o, sysd)
+    ob = o.bodies()
+    for k in ("rcm", "pcm", "pi", "force", "torque"):
+        assert rel_inf(db[k], ob[k]) <= tol, ("oracle", k, rel_inf(db[k], ob[k]))
+    assert quat_rel(db["q"], ob["q"]) <= tol
+    assert b.counts()["numDOF"] == o.counts()["numDOF"]
+    o.step(0.001, 3)
+    Ro, Vo, _ = o.get_state()
+    assert rel_inf(Rb.cpu().numpy(), Ro) <= 2e-10 and rel_inf(Vb.cpu().numpy(), Vo) <= 2e-10
+    assert rel_inf(b.kinetic(Vb), o.kinetic()) <= 2e-10
 
 
 def test_device_build_1M_waters_is_fast():

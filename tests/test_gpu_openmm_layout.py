@@ -89,3 +89,101 @@ def test_openmm_formats_match_vec3_path(precision, mode):
         assert bool((corr[:, 3] == 7.0).all())
     pad = np.setdiff1d(np.arange(padded), order)
     assert float(posq[pad].abs().max()) == 0.0 and float(velm[pad].abs().max()) == 0.0
+
+
+class OpenMMArrays:
+    """posq / posqCorrection / velm / force planes as OpenMM's CUDA platform holds them, atoms stored at slot order[i]."""
+
+    def __init__(self, sysd, order, padded, precision, Fq):
+        import torch
+        self.torch, self.dev, self.precision, self.padded = torch, torch.device("cuda:0"), precision, padded
+        n = len(sysd["masses"])
+        pos0 = np.zeros((padded, 4)); pos0[order, :3] = sysd["R"]; pos0[order, 3] = sysd["charges"]
+        vel0 = np.zeros((padded, 4)); vel0[order, :3] = sysd["V"]; vel0[order, 3] = 1.0 / sysd["masses"]
+        p64 = torch.from_numpy(pos0).to(self.dev)
+        if precision == RBK_OPENMM_MIXED:
+            self.posq = p64.float().contiguous()
+            self.corr = (p64 - self.posq.double()).float().contiguous()
+        else:
+            self.posq, self.corr = p64.contiguous(), None
+        self.velm = torch.from_numpy(vel0).to(self.dev).contiguous()
+        planes = np.zeros((3, padded), np.int64)
+        planes[:, order] = Fq.T
+        self.force = torch.from_numpy(planes).to(self.dev).contiguous()
+        self.order = order.copy()
+
+    def args(self):
+        return self.posq, self.corr, self.velm, self.force, self.padded, self.precision
+
+    def reorder(self, new_order):
+        """what cu.reorderAtoms() does to posq / posqCorrection / velm (the forces are the listener's job)"""
+        t = self.torch
+        src = t.from_numpy(self.order).to(self.dev)
+        dst = t.from_numpy(new_order).to(self.dev)
+        for name in ("posq", "corr", "velm"):
+            a = getattr(self, name)
+            if a is None:
+                continue
+            b = t.zeros_like(a)
+            b[dst] = a[src]
+            setattr(self, name, b)
+        self.order = new_order.copy()
+
+    def host(self):
+        R = self.posq.double()[:, :3]
+        if self.corr is not None:
+            R = R + self.corr.double()[:, :3]
+        return R.cpu().numpy()[self.order], self.velm[:, :3].cpu().numpy()[self.order]
+
+
+@pytest.mark.parametrize("precision", [RBK_OPENMM_MIXED, RBK_OPENMM_DOUBLE])
+@pytest.mark.parametrize("case,mode", [("water", 0), ("water", 3), ("small_mixed", 0), ("medium_mixed", 0), ("large_mixed", 0)])
+def test_openmm_fused_stepping_and_reorder_vs_oracle(case, mode, precision):
+    """The CUDA-platform flow on the OpenMM formats against the CPU ORACLE (not against this repo's own fp64 path):
+    part1, [rbk_part2_part1_openmm, atoms reordered every other step through rbk_reorder_openmm] x n, part2 - with the
+    reordering at the only point a fused step leaves for it, after the one-pass call (state: Part 1 of the next step done)."""
+    import torch
+    from oracle.checkers import CpuStepper
+    if case == "water":
+        sysd = common.synth.water_box(4100, seed=51)
+    elif case == "small_mixed":
+        sysd = common.synth.mixed_system(2500, 3000, seed=52, max_atoms=7)
+    elif case == "medium_mixed":
+        sysd = common.synth.mixed_system(2500, 1000, seed=53, max_atoms=12)
+    else:
+        sysd = common.synth.mixed_system(500, 600, seed=54, max_atoms=60)
+    n = len(sysd["masses"])
+    Fq = np.round(sysd["F"] * 4294967296.0).astype(np.int64)
+    sysd = dict(sysd, F=Fq.astype(np.float64) / 4294967296.0)
+    steps, dt = 6, 0.001
+    o = CpuStepper("oracle", sysd["bodyIndices"], sysd["masses"], mode)
+    common.init_like_reference(o, sysd)
+    o.step(dt, steps)
+    Ro, Vo, _ = o.get_state()
+
+    rng = np.random.Generator(np.random.Philox(key=55))
+    padded = ((n + 31) // 32) * 32 + 32
+    s = build(sysd, mode)
+    index = s.atom_index()
+    A = OpenMMArrays(sysd, rng.permutation(n), padded, precision, Fq)
+    s.set_atom_location(A.order[index].astype(np.int32))
+    s.part1_openmm(dt, *A.args())
+    for k in range(steps - 1):
+        s.part2_part1_openmm(dt, *A.args())
+        if k % 2 == 1:
+            new_order = rng.permutation(n)
+            expect = torch.zeros_like(A.force)
+            expect[:, torch.from_numpy(new_order).to(A.dev)] = A.force[:, torch.from_numpy(A.order).to(A.dev)]
+            A.reorder(new_order)
+            s.reorder_openmm(new_order[index].astype(np.int32), A.force, padded)
+            assert torch.equal(A.force, expect)               # the listener moved every owned atom's force to its new slot
+    s.part2_openmm(dt, *A.args())
+    Rg, Vg = A.host()
+    eR, eV = common.rel_inf(Rg, Ro), common.rel_inf(Vg, Vo)
+    assert eR <= 2e-10 and eV <= 2e-10, (case, mode, precision, eR, eV)
+    ke = s.kinetic_openmm(A.velm, precision)
+    assert common.rel_inf(ke, o.kinetic()) <= 2e-10
+    b, ob = s.download_bodies(), o.bodies()
+    for k in ("rcm", "pcm", "pi", "force", "torque"):
+        assert common.rel_inf(b[k], ob[k]) <= 1e-8, k
+    assert common.quat_rel(b["q"], ob["q"]) <= 2e-10

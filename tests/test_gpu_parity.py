@@ -212,6 +212,38 @@ def test_energy_drift_tracks_reference():
               f"slope gpu {fit[0]:.3e} ref {fit_ref[0]:.3e} (s.e. {slope_se:.1e}) kJ/mol/ps")
 
 
+def test_energy_drift_512_waters_literal_slope():
+    """SURVEY.md section 8c's probe: 512 TIP3P waters in the tether + field potential, 10k steps of 1 fs, mode 0.  The
+    survey hoped the literal bar - fitted slope within 10% of the reference's - would be resolvable at this size.  It is
+    not: the TRUE reference started from velocities scaled by (1 + 1e-13) (fixture `series_twin`) moves its own slope by
+    18% (2.02e-2 -> 1.65e-2 kJ/mol/ps) while its rms excursion moves by 0.1%.  So the test reports the literal slope
+    ratio, requires the slope to lie as close to the reference's as the reference's twin does (x2) or within 10%, and
+    holds the 10% bar on the drift measure that IS reproducible, the rms excursion of E(t) from E(0)."""
+    g = load("drift_water512_mode0")
+    s = GpuStepper(g["bodyIndices"], g["masses"], 0)
+    s.fused = True
+    common.init_like_reference(s, sysd_of(g), tether=True)
+    every, dt = int(g["every"]), float(g["dt"])
+    ref, twin = g["series"], g["series_twin"]
+    series = []
+    for i in range(ref.shape[0]):
+        U = s.compute_forces()
+        ke = s.kinetic()
+        series.append([i * every * dt, U, ke[0], ke[1]])
+        if i < ref.shape[0] - 1:
+            s.step(dt, every)
+    e = np.array(series)
+    t, tot, tot_ref, tot_twin = e[:, 0], e[:, 1:].sum(1), ref[:, 1:].sum(1), twin[:, 1:].sum(1)
+    early = t <= 1000 * dt + 1e-12
+    assert np.max(np.abs(tot[early] - tot_ref[early])) <= 1e-9 * abs(tot_ref[0])
+    slope, slope_ref, slope_twin = (np.polyfit(t, x, 1)[0] for x in (tot, tot_ref, tot_twin))
+    exc, exc_ref = (np.sqrt(np.mean((x - x[0]) ** 2)) for x in (tot, tot_ref))
+    print(f"drift 512 waters: slope gpu {slope:.4e} ref {slope_ref:.4e} (ratio {slope/slope_ref:.3f}; reference twin {slope_twin:.4e}, "
+          f"ratio {slope_twin/slope_ref:.3f}); rms excursion gpu {exc:.4f} ref {exc_ref:.4f} kJ/mol")
+    assert abs(exc - exc_ref) <= 0.1 * exc_ref, (exc, exc_ref)
+    assert abs(slope - slope_ref) <= max(0.1 * abs(slope_ref), 2.0 * abs(slope_twin - slope_ref)), (slope, slope_ref, slope_twin)
+
+
 def test_energy_conservation_integrable_10k_steps():
     """Deterministic companion of the drift test: forces proportional to mass (uniform gravity) exert no
     torque, so every body is a free rotor on a parabola - integrable, no chaotic amplification - and the
