@@ -5,10 +5,13 @@
 #include "Vec3.h"
 #include <vector>
 namespace OpenMM {
+class ContextImpl;
 class Force {
 public:
     virtual ~Force() {}
     virtual double calcForcesAndEnergy(const std::vector<Vec3>& positions, std::vector<Vec3>& forces) const = 0;
+    // ForceImpl::updateContextState: thermostats, barostats, CMMotionRemover change the state here, once per step
+    virtual void updateContextState(ContextImpl& context) const {}
 };
 }
 #endif

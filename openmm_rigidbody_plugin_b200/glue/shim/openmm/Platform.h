@@ -25,6 +25,12 @@ public:
     virtual void contextCreated(ContextImpl& context) const {}
     virtual void contextDestroyed(ContextImpl& context) const {}
     void registerKernelFactory(const std::string& name, KernelFactory* factory) { factories[name] = factory; }
+    void setPropertyDefaultValue(const std::string& property, const std::string& value) { properties[property] = value; }
+    const std::string& getPropertyDefaultValue(const std::string& property) const {
+        std::map<std::string, std::string>::const_iterator it = properties.find(property);
+        if (it == properties.end()) throw OpenMMException("getPropertyDefaultValue: Illegal property name");
+        return it->second;
+    }
     bool supportsKernels(const std::vector<std::string>& kernelNames) const {
         for (size_t i = 0; i < kernelNames.size(); i++) if (factories.find(kernelNames[i]) == factories.end()) return false;
         return true;
@@ -44,6 +50,7 @@ public:
 private:
     static std::vector<Platform*>& getPlatforms() { static std::vector<Platform*> platforms; return platforms; }
     std::map<std::string, KernelFactory*> factories;
+    std::map<std::string, std::string> properties;
 };
 }
 #endif
