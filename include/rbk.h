@@ -39,6 +39,9 @@ typedef struct rbk_system rbk_system;
 
 int         rbk_version(void);
 const char* rbk_last_error(void);
+/* Diagnostics: host<->device copies issued by librbk in this process so far - out[4] = H2D calls, H2D bytes, D2H calls,
+ * D2H bytes.  The device entry points (rbk_part1/2*, rbk_part2_part1*, rbk_free_*) must not move any of them. */
+int         rbk_debug_copy_counters(const rbk_system* sys, long long* out);
 
 /* ---- host model -------------------------------------------------------------------------- */
 
@@ -90,7 +93,8 @@ int rbk_update_device(rbk_system* sys, const double* pos, const double* vel, con
 /* Replace the plugin-order -> caller-order atom map (CUDA platform's atomLocation,
  * CudaRigidBodyKernels.cpp:277-284 and ReorderListener :69-113).  location[i] is the index in the
  * caller's pos/vel/force arrays of plugin atom i (i indexes rbk_get_atom_index order).
- * NULL restores the default location[i] = atomIndex[i]. */
+ * NULL restores the default location[i] = atomIndex[i].  Allocates the handle's device state when called before any
+ * rbk_upload / rbk_update_device (callers that build the bodies on the device). */
 int rbk_set_atom_location(rbk_system* sys, const int* location, void* stream);
 
 /* RigidBodySystem::integratePart1 (RigidBodySystem.cpp:170-187): free atoms half-kick + drift,

@@ -7,6 +7,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +42,24 @@ template <class T> cudaError_t devAlloc(T*& p, size_t count) {
 }
 
 size_t padTo(size_t n, size_t m) { return (n + m - 1)/m*m; }
+
+// Every host<->device copy librbk issues goes through these two wrappers and is counted (rbk_debug_copy_counters): the
+// claim "a step moves nothing between host and device" is then something a test can assert.
+std::atomic<long long> g_copies[4];                 // H2D calls, H2D bytes, D2H calls, D2H bytes
+void countCopy(size_t bytes, cudaMemcpyKind kind) {
+    const int base = kind == cudaMemcpyHostToDevice ? 0 : (kind == cudaMemcpyDeviceToHost ? 2 : -1);
+    if (base < 0) return;
+    g_copies[base]++;
+    g_copies[base + 1] += (long long) bytes;
+}
+cudaError_t copyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    countCopy(bytes, kind);
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
+cudaError_t copySync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    countCopy(bytes, kind);
+    return cudaMemcpy(dst, src, bytes, kind);
+}
 
 } // namespace
 
@@ -220,9 +239,9 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(devAlloc(sys->dBodyTileMeta, bodyMeta.size()));
     if (warpMeta.empty()) warpMeta.push_back(make_int4(0, 0, 0, 0));
     RBK_CUDA(devAlloc(sys->dWarpTileMeta, warpMeta.size()));
-    RBK_CUDA(cudaMemcpyAsync(sys->dWarpTileMeta, warpMeta.data(), warpMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
-    RBK_CUDA(cudaMemcpyAsync(sys->dTileMeta, meta.data(), meta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
-    RBK_CUDA(cudaMemcpyAsync(sys->dBodyTileMeta, bodyMeta.data(), bodyMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dWarpTileMeta, warpMeta.data(), warpMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dTileMeta, meta.data(), meta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dBodyTileMeta, bodyMeta.data(), bodyMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
     RBK_CUDA(devAlloc(sys->dFreeInvMass, (size_t) std::max(nF, 1)));
     RBK_CUDA(devAlloc(sys->dSavedPos, d.freeStride*3));
@@ -230,7 +249,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     for (int a = 0; a < nA; a++) atomMass[a] = h.mass[h.atomIndex[(size_t) nF + a]];
     RBK_CUDA(devAlloc(sys->dAtomMass, atomMass.size()));
     RBK_CUDA(devAlloc(sys->dDofSum, 1));
-    RBK_CUDA(cudaMemcpyAsync(sys->dAtomMass, atomMass.data(), atomMass.size()*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dAtomMass, atomMass.data(), atomMass.size()*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaMemsetAsync(sys->dState, 0, d.bodyStride*rbk::NPLANES*sizeof(double), st));
     RBK_CUDA(devAlloc(sys->dKinPartial, (size_t) 2*rbk::kKineticBlocks));
     RBK_CUDA(devAlloc(sys->dKinCounter, 1));
@@ -238,9 +257,9 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(cudaMallocHost((void**) &sys->hKinOut, 2*sizeof(double)));
     RBK_CUDA(cudaMemsetAsync(sys->dKinCounter, 0, sizeof(unsigned), st));
     RBK_CUDA(cudaMemsetAsync(sys->dSavedPos, 0, d.freeStride*3*sizeof(double), st));
-    RBK_CUDA(cudaMemcpyAsync(sys->dLocalBody, local.data(), local.size(), cudaMemcpyHostToDevice, st));
-    RBK_CUDA(cudaMemcpyAsync(sys->dLoc, loc.data(), loc.size()*sizeof(int), cudaMemcpyHostToDevice, st));
-    if (nF) RBK_CUDA(cudaMemcpyAsync(sys->dFreeInvMass, h.freeInvMass.data(), (size_t) nF*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dLocalBody, local.data(), local.size(), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dLoc, loc.data(), loc.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+    if (nF) RBK_CUDA(copyAsync(sys->dFreeInvMass, h.freeInvMass.data(), (size_t) nF*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));       // the host vectors above die at scope exit
 
     d.state = sys->dState;
@@ -269,7 +288,7 @@ int setLocation(rbk_system* sys, const int* location, cudaStream_t st) {
     for (int i = 0; i < n && identity; i++) identity = src[i] == i;
     for (int i = 0; i < n && !identity; i++)
         if (src[i] < 0) return fail(RBK_EINVAL, "rbk_set_atom_location: negative location");
-    if (!identity) RBK_CUDA(cudaMemcpyAsync(sys->dAtomLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!identity) RBK_CUDA(copyAsync(sys->dAtomLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));             // `location` is the caller's
     sys->dev.atomLoc = identity ? nullptr : sys->dAtomLoc;
     return RBK_OK;
@@ -293,6 +312,12 @@ int viewOf(const void* p, int layout, long long stride, AtomView& v) {
 extern "C" {
 
 int rbk_version(void) { return RBK_VERSION; }
+
+int rbk_debug_copy_counters(const rbk_system*, long long* out) {
+    if (!out) return fail(RBK_EINVAL, "rbk_debug_copy_counters: NULL argument");
+    for (int i = 0; i < 4; i++) out[i] = g_copies[i].load();
+    return RBK_OK;
+}
 const char* rbk_last_error(void) { return g_error.c_str(); }
 
 int rbk_create(int numAtoms, const int* bodyIndices, const double* masses, const unsigned char* isVirtual,
@@ -351,7 +376,7 @@ int pullHostModel(rbk_system* sys) {
     RBK_CUDA(cudaDeviceSynchronize());                 // no stream argument here: whatever was queued must be done
     std::vector<double>& buf = sys->staging;
     buf.resize(std::max(buf.size(), std::max(ld*rbk::NPLANES, as*3)));
-    RBK_CUDA(cudaMemcpy(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost));
+    RBK_CUDA(copySync(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost));
     for (int b = 0; b < h.numBodies; b++) {
         HostBody& B = h.body[b];
         for (int c = 0; c < 3; c++) {
@@ -375,7 +400,7 @@ int pullHostModel(rbk_system* sys) {
         B.torque[3] =  q[2]*B.tau[0] - q[1]*B.tau[1] + q[0]*B.tau[2];
     }
     if (sys->hostStale) {                               // geometry was built on the device: the coordinates too
-        RBK_CUDA(cudaMemcpy(buf.data(), sys->dDxyz, as*3*sizeof(double), cudaMemcpyDeviceToHost));
+        RBK_CUDA(copySync(buf.data(), sys->dDxyz, as*3*sizeof(double), cudaMemcpyDeviceToHost));
         for (int a = 0; a < h.numBodyAtoms; a++)
             for (int c = 0; c < 3; c++) h.d[3*(size_t) a + c] = buf[c*as + a];
     }
@@ -468,12 +493,12 @@ int rbk_upload(rbk_system* sys, void* stream) {
         }
         buf[rbk::PL_INVM*ld + b] = B.invMass;
     }
-    RBK_CUDA(cudaMemcpyAsync(sys->dState, buf.data(), ld*rbk::NPLANES*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dState, buf.data(), ld*rbk::NPLANES*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     const size_t as = d.atomStride;
     for (int a = 0; a < h.numBodyAtoms; a++)
         for (int c = 0; c < 3; c++) buf[c*as + a] = h.d[3*(size_t) a + c];
-    RBK_CUDA(cudaMemcpyAsync(sys->dDxyz, buf.data(), as*3*sizeof(double), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(copyAsync(sys->dDxyz, buf.data(), as*3*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     sys->uploaded = true;
     sys->mirrorsLoaded = false;
@@ -494,7 +519,7 @@ int updateDevice(rbk_system* sys, AtomView p, AtomView v, AtomView f, int geomet
     RBK_CUDA(rbk::launchBuild(sys->dev, sys->dAtomMass, p, v, f, sys->dDxyz, geometry != 0, velocities != 0, sys->dDofSum, st));
     if (geometry) {
         int dofSum = 0;
-        RBK_CUDA(cudaMemcpyAsync(&dofSum, sys->dDofSum, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RBK_CUDA(copyAsync(&dofSum, sys->dDofSum, sizeof(int), cudaMemcpyDeviceToHost, st));
         RBK_CUDA(cudaStreamSynchronize(st));
         sys->host.numDOF = sys->host.numFree - sys->host.numConstraints + dofSum;      // RigidBodySystem.cpp:130-134
     }
@@ -517,7 +542,9 @@ int rbk_update_device(rbk_system* sys, const double* pos, const double* vel, con
 
 int rbk_set_atom_location(rbk_system* sys, const int* location, void* stream) {
     if (!sys) return fail(RBK_EINVAL, "rbk_set_atom_location: NULL system");
-    if (!sys->allocated) return fail(RBK_ESTATE, "rbk_set_atom_location: call rbk_upload first");
+    if (!sys->allocated) {                           // a caller that builds on the device never uploads: allocate here
+        if (int rc = allocateDevice(sys, (cudaStream_t) stream)) return rc;
+    }
     return setLocation(sys, location, (cudaStream_t) stream);
 }
 
@@ -576,7 +603,7 @@ int stepPart2Part1(rbk_system* sys, double dt, AtomView p, AtomView v, AtomView 
 }
 
 int reduceOut(rbk_system* sys, double* out, int count, cudaStream_t st) {
-    RBK_CUDA(cudaMemcpyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(copyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < count; i++) out[i] = sys->hKinOut[i];
     return RBK_OK;
@@ -667,7 +694,7 @@ int rbk_kinetic(rbk_system* sys, const double* vel, int layout, long long stride
     AtomView v;
     if (viewOf(vel, layout, stride, v)) return RBK_EINVAL;
     RBK_CUDA(rbk::launchKinetic(sys->dev, v, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
-    RBK_CUDA(cudaMemcpyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(copyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     out[0] = sys->hKinOut[0];
     out[1] = sys->hKinOut[1];
@@ -797,7 +824,7 @@ int rbk_kinetic_openmm(rbk_system* sys, const void* velm, int precision, double*
     cudaStream_t st = (cudaStream_t) stream;
     AtomView v{(double*) velm, 0, 0, precision == RBK_OPENMM_SINGLE ? rbk::FMT_REAL4_F32 : rbk::FMT_REAL4_F64, nullptr};
     RBK_CUDA(rbk::launchKinetic(sys->dev, v, sys->dKinPartial, sys->dKinCounter, sys->dKinOut, st));
-    RBK_CUDA(cudaMemcpyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(copyAsync(sys->hKinOut, sys->dKinOut, 2*sizeof(double), cudaMemcpyDeviceToHost, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     out[0] = sys->hKinOut[0];
     out[1] = sys->hKinOut[1];
@@ -838,7 +865,7 @@ int rbk_refined_kinetic_host(rbk_system* sys, double dt, const double* V, double
     if (!sys->mVel) return fail(RBK_ESTATE, "rbk_refined_kinetic_host: no step has been taken with rbk_execute_host");
     cudaStream_t st = (cudaStream_t) stream;
     const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
-    if (sys->host.numFree > 0 && !sys->hostVelStale) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+    if (sys->host.numFree > 0 && !sys->hostVelStale) RBK_CUDA(copyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
     return rbk_refined_kinetic(sys, dt, sys->mVel, RBK_LAYOUT_VEC3, 0, out, stream);
 }
 
@@ -848,7 +875,7 @@ int rbk_potential_refinement_host(rbk_system* sys, double dt, const double* F, d
     if (!sys->mForce) return fail(RBK_ESTATE, "rbk_potential_refinement_host: no step has been taken with rbk_execute_host");
     cudaStream_t st = (cudaStream_t) stream;
     const size_t bytes = (size_t) sys->host.numAtoms*3*sizeof(double);
-    if (sys->host.numFree > 0) RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
+    if (sys->host.numFree > 0) RBK_CUDA(copyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
     return rbk_potential_refinement(sys, dt, sys->mForce, RBK_LAYOUT_VEC3, 0, out, stream);
 }
 
@@ -863,7 +890,7 @@ int rbk_kinetic_host(rbk_system* sys, const double* V, double* out, void* stream
         RBK_CUDA(cudaMalloc((void**) &sys->mForce, bytes));
     }
     // (after an rbk_execute_host call that left the velocities on the device, V == NULL, the mirror is the current copy)
-    if (sys->host.numFree > 0 && !sys->hostVelStale) RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+    if (sys->host.numFree > 0 && !sys->hostVelStale) RBK_CUDA(copyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
     return rbk_kinetic(sys, sys->mVel, RBK_LAYOUT_VEC3, 0, out, stream);
 }
 
@@ -877,7 +904,7 @@ int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, do
     const size_t ld = sys->dev.bodyStride;
     std::vector<double>& buf = sys->staging;
     buf.resize(std::max(buf.size(), ld*rbk::NPLANES));
-    RBK_CUDA(cudaMemcpyAsync(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RBK_CUDA(copyAsync(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     for (int b = 0; b < sys->host.numBodies; b++) {
         double qq[4], tt[3];
@@ -926,9 +953,9 @@ int executeHost(rbk_system* sys, double dt, int steps, double* R, double* V, dou
     const bool hostFlow = forces || constrainPositions;       // something on the host needs R between Part 1 and Part 2
     if (!sys->mirrorsLoaded) {
         if (!V) return fail(RBK_EINVAL, "rbk_execute_host: the first call after an upload needs V (the device mirror is empty)");
-        RBK_CUDA(cudaMemcpyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
-        RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
-        RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
+        RBK_CUDA(copyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
+        RBK_CUDA(copyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+        RBK_CUDA(copyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
         sys->mirrorsLoaded = true;
         sys->hostVelStale = false;
     }
@@ -936,7 +963,7 @@ int executeHost(rbk_system* sys, double dt, int steps, double* R, double* V, dou
         // F holds the forces at the current positions and the caller may have re-evaluated them since the last call
         // (updateParametersInContext, setParameter): the reference reads data.forces every step
         // (ReferenceRigidBodyKernels.cpp:96), so Part 1's half kick must not use a stale mirror
-        RBK_CUDA(cudaMemcpyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
+        RBK_CUDA(copyAsync(sys->mForce, F, bytes, cudaMemcpyHostToDevice, st));
     const AtomView p{sys->mPos, 3, 1, rbk::FMT_F64, nullptr}, v{sys->mVel, 3, 1, rbk::FMT_F64, nullptr};
     // step(n) = part1, forces, [part2+part1 in one pass, forces] x (n-1), part2 whenever nothing sits between Part 2 of
     // one step and Part 1 of the next (no velocity hook, no diagnostics): rbk_part2_part1
@@ -954,25 +981,25 @@ int executeHost(rbk_system* sys, double dt, int steps, double* R, double* V, dou
                 std::memcpy(sys->oldPositions.data(), R, bytes);
             }
             if (i == 0 || !fuse) RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
-            RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
+            RBK_CUDA(copyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
             RBK_CUDA(cudaStreamSynchronize(st));
             if (constrainPositions && constrainPositions(sys->oldPositions.data(), R, sys->host.numAtoms, user))
-                RBK_CUDA(cudaMemcpyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
+                RBK_CUDA(copyAsync(sys->mPos, R, bytes, cudaMemcpyHostToDevice, st));
             if (forces) forces(R, F, sys->host.numAtoms, user);
-            RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, st));
+            RBK_CUDA(copyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, st));
         }
         else if (i == 0) {
             // F is this call's input, known up front and the same for all of its steps: the upload (H2D engine) runs under
             // Part 1 - and, in a one-step call, under the download of the positions (D2H engine); Part 2 waits for it only
             RBK_CUDA(cudaEventRecord(sys->evStart, st));
             RBK_CUDA(cudaStreamWaitEvent(sys->h2dStream, sys->evStart, 0));
-            RBK_CUDA(cudaMemcpyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, sys->h2dStream));
+            RBK_CUDA(copyAsync(sys->mForce2, F, bytes, cudaMemcpyHostToDevice, sys->h2dStream));
             RBK_CUDA(cudaEventRecord(sys->evForces, sys->h2dStream));
             RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
             if (last) {
                 RBK_CUDA(cudaEventRecord(sys->evPart1, st));
                 RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
-                RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
+                RBK_CUDA(copyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
                 RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
             }
             RBK_CUDA(cudaStreamWaitEvent(st, sys->evForces, 0));
@@ -983,7 +1010,7 @@ int executeHost(rbk_system* sys, double dt, int steps, double* R, double* V, dou
             if (!hostFlow && i == steps - 2) {                // positions are final after the last Part 1
                 RBK_CUDA(cudaEventRecord(sys->evPart1, st));
                 RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
-                RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
+                RBK_CUDA(copyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
                 RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
             }
         }
@@ -991,22 +1018,22 @@ int executeHost(rbk_system* sys, double dt, int steps, double* R, double* V, dou
             if (!hostFlow && !fuse && last && steps > 1) {
                 RBK_CUDA(cudaEventRecord(sys->evPart1, st));
                 RBK_CUDA(cudaStreamWaitEvent(sys->d2hStream, sys->evPart1, 0));
-                RBK_CUDA(cudaMemcpyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
+                RBK_CUDA(copyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, sys->d2hStream));
                 RBK_CUDA(cudaEventRecord(sys->evPositions, sys->d2hStream));
             }
             RBK_CUDA(stepPart2(sys, dt, p, v, fNew, st));
         }
         if (constrainVelocities) {
-            RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
+            RBK_CUDA(copyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
             RBK_CUDA(cudaStreamSynchronize(st));
             if (constrainVelocities(R, V, sys->host.numAtoms, user))
-                RBK_CUDA(cudaMemcpyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
+                RBK_CUDA(copyAsync(sys->mVel, V, bytes, cudaMemcpyHostToDevice, st));
         }
         if (newForces) std::swap(sys->mForce, sys->mForce2);             // mForce = the forces of the latest evaluation
     }
     // velocities leave the device once per call (nothing on the host reads them between the steps of a call unless a
     // velocity hook is installed), and not at all when the caller passes V = NULL
-    if (V && !constrainVelocities) RBK_CUDA(cudaMemcpyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
+    if (V && !constrainVelocities) RBK_CUDA(copyAsync(V, sys->mVel, bytes, cudaMemcpyDeviceToHost, st));
     sys->hostVelStale = V == nullptr;
     if (!hostFlow) RBK_CUDA(cudaStreamWaitEvent(st, sys->evPositions, 0));     // R is complete when `st` is
     RBK_CUDA(cudaStreamSynchronize(st));

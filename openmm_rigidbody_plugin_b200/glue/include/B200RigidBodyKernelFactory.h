@@ -16,4 +16,5 @@ public:
 extern "C" void registerPlatforms();
 extern "C" void registerKernelFactories();
 extern "C" void registerRigidBodyB200KernelFactories();
+extern "C" void registerRigidBodyCudaKernelFactories();      // the name the reference's CUDA plugin exports
 #endif

@@ -22,6 +22,7 @@ public:
     void step(int steps);
     std::vector<int> getBodyIndices() const { return bodyIndices; }
     const RigidBodySystem& getRigidBodySystem() const { return bodySystem; }
+    OpenMM::ContextImpl& getContextImpl() { return *context; }      // (tests) the ContextImpl this integrator is bound to
     std::vector<double> getKineticEnergies();        // {translational, rotational}
     std::vector<double> getRefinedKineticEnergies();
     double getPotentialEnergyRefinement();

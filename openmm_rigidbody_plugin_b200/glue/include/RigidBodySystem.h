@@ -21,6 +21,7 @@ public:
     int getNumActualAtoms() const { return count(2); }
     int getNumBodyAtoms() const { return count(3); }
     int getAtomIndex(int i) const;
+    const std::vector<int>& getAtomIndices() const { return atomIndex; }      // plugin order -> particle, all of it
     double getTranslationalEnergy() const { return transKE; }
     double getRotationalEnergy() const { return rotKE; }
     double getKineticEnergy() const { return transKE + rotKE; }
@@ -31,6 +32,7 @@ private:
     RigidBodySystem& operator=(const RigidBodySystem&);
     int count(int which) const;
     rbk_system* handle;
+    std::vector<int> atomIndex;              // filled once in initialize (the index mapping never changes afterwards)
     double transKE, rotKE;
 };
 

@@ -66,6 +66,14 @@ int B200IntegrateRigidBodyStepKernel::constrainVelocities(const double*, double*
 }
 
 void B200IntegrateRigidBodyStepKernel::execute(ContextImpl& contextRef, const RigidBodyIntegrator& integrator) {
+    executeSteps(contextRef, integrator, 1);
+}
+
+// step(n) as one call of the host-buffer entry point: the forces go up and the positions come down every step (the
+// Reference platform evaluates forces on the host), Part 2 of a step and Part 1 of the next run as one pass where no
+// velocity hook sits between them, and the velocities come back once, after the last step.
+void B200IntegrateRigidBodyStepKernel::executeSteps(ContextImpl& contextRef, const RigidBodyIntegrator& integrator, int steps) {
+    if (steps <= 0) return;
     if (system == NULL) throw OpenMMException("B200 rigid-body kernel: positions have not been set");
     vector<Vec3>& R = *data.positions;
     vector<Vec3>& V = *data.velocities;
@@ -74,11 +82,11 @@ void B200IntegrateRigidBodyStepKernel::execute(ContextImpl& contextRef, const Ri
     context = &contextRef;
     tolerance = integrator.getConstraintTolerance();
     const bool freeAtoms = bodies != NULL && bodies->getNumFree() != 0;
-    check(rbk_execute_host_hooks(system, dt, 1, &R[0][0], &V[0][0], &F[0][0], &evaluateForces,
+    check(rbk_execute_host_hooks(system, dt, steps, &R[0][0], &V[0][0], &F[0][0], &evaluateForces,
                                  positionHook ? &constrainPositions : NULL,
                                  velocityHook && freeAtoms ? &constrainVelocities : NULL, this, NULL));
-    data.time += dt;
-    data.stepCount++;
+    data.time += dt*steps;
+    data.stepCount += steps;
 }
 
 double B200IntegrateRigidBodyStepKernel::computeKineticEnergy(ContextImpl&, const RigidBodyIntegrator& integrator) {

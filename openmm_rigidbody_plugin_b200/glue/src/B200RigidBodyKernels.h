@@ -17,6 +17,7 @@ public:
     void initialize(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator);
     void uploadBodySystem(RigidBodySystem& bodySystem);
     void execute(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator);
+    void executeSteps(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator, int steps);
     double computeKineticEnergy(OpenMM::ContextImpl& context, const RigidBodyIntegrator& integrator);
     std::vector<double> getKineticEnergies(const RigidBodyIntegrator& integrator);
     std::vector<double> getRefinedKineticEnergies(const RigidBodyIntegrator& integrator);

@@ -44,13 +44,15 @@ vector<string> RigidBodyIntegrator::getKernelNames() { return vector<string>(1, 
 
 void RigidBodyIntegrator::stateChanged(State::DataType changed) {
     if (changed != State::Positions && changed != State::Velocities) return;
-    if (changed == State::Positions) {
+    const bool positions = changed == State::Positions;
+    if (positions) {
         context->updateContextState();
         context->calcForcesAndEnergy(true, false);           // the body build needs F and tau at the new positions
-        bodySystem.update(*context, true, true);
     }
-    else bodySystem.update(*context, false, true);
-    kernel.getAs<IntegrateRigidBodyStepKernel>().uploadBodySystem(bodySystem);
+    IntegrateRigidBodyStepKernel& impl = kernel.getAs<IntegrateRigidBodyStepKernel>();
+    if (impl.updateBodySystem(*context, bodySystem, positions, true)) return;      // built where the kernel keeps the bodies
+    bodySystem.update(*context, positions, true);
+    impl.uploadBodySystem(bodySystem);
 }
 
 double RigidBodyIntegrator::computeKineticEnergy() {
@@ -71,5 +73,5 @@ double RigidBodyIntegrator::getPotentialEnergyRefinement() {
 
 void RigidBodyIntegrator::step(int steps) {
     if (context == NULL) throw OpenMMException("This Integrator is not bound to a context!");
-    for (int i = 0; i < steps; ++i) kernel.getAs<IntegrateRigidBodyStepKernel>().execute(*context, *this);
+    kernel.getAs<IntegrateRigidBodyStepKernel>().executeSteps(*context, *this, steps);
 }

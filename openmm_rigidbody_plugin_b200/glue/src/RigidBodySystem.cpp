@@ -31,6 +31,8 @@ void RigidBodySystem::initialize(ContextImpl& context, const vector<int>& bodyIn
     handle = NULL;
     check(rbk_create(n, bodyIndices.data(), mass.data(), isVirtual.data(), system.getNumConstraints(),
                      constraintAtoms.empty() ? NULL : constraintAtoms.data(), rotationMode, &handle));
+    atomIndex.assign(getNumActualAtoms(), 0);
+    if (!atomIndex.empty()) check(rbk_get_atom_index(handle, atomIndex.data()));
 }
 
 void RigidBodySystem::update(ContextImpl& context, bool geometry, bool velocities) {
@@ -50,8 +52,4 @@ int RigidBodySystem::count(int which) const {
     return c[which];
 }
 
-int RigidBodySystem::getAtomIndex(int i) const {
-    vector<int> index(getNumActualAtoms());
-    check(rbk_get_atom_index(handle, index.data()));
-    return index[i];
-}
+int RigidBodySystem::getAtomIndex(int i) const { return atomIndex.at(i); }

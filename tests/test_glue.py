@@ -52,3 +52,55 @@ def test_stepping_without_gpu_fails_loudly(glue):
 def test_cpp_integration_tests_on_gpu(glue):
     r = run(os.path.join(glue, "TestB200RigidBodyIntegrator"))
     assert r.returncode == 0 and r.stdout.strip().endswith("Done"), r.stdout + r.stderr
+
+
+def test_glue_registers_on_the_cuda_platform(glue):
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(glue, "libRigidBodyPluginB200.so")],
+                         capture_output=True, text=True, check=True).stdout
+    assert " T registerRigidBodyCudaKernelFactories" in out          # the symbol the reference's CUDA plugin exports
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(glue, "libRigidBodyPluginB200.so")],
+                               capture_output=True, text=True, check=True).stdout
+    for sym in ("rbk_part1_openmm", "rbk_part2_openmm", "rbk_part2_part1_openmm", "rbk_reorder_openmm", "rbk_update_device_openmm",
+                "rbk_free_delta_openmm", "rbk_part1_delta_openmm", "rbk_kinetic_openmm"):
+        assert sym in undefined, sym
+
+
+@pytest.mark.gpu
+def test_cuda_platform_kernel_on_gpu_and_against_the_oracle(glue, tmp_path):
+    """The CUDA-platform KernelImpl (B200CudaIntegrateRigidBodyStepKernel) driven through RigidBodyIntegrator::step on
+    the shim CudaContext: the C++ program runs the reference-style tests in mixed and double precision, checks both
+    kernels of the plugin against each other, asserts zero host<->device copies by librbk inside step(n), and dumps one
+    run (700 tethered waters, fused step(8) x 3 with the atoms reordered every 3 steps, mixed precision) that is
+    replayed here on the CPU oracle."""
+    import numpy as np
+    from oracle.checkers import CpuStepper
+    dump = str(tmp_path / "cuda_run.bin")
+    r = subprocess.run([os.path.join(glue, "TestB200CudaRigidBodyIntegrator"), dump], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("Done"), r.stdout + r.stderr
+    raw = np.fromfile(dump, dtype=np.float64)
+    n, n_mol, mode, steps, dt, k = int(raw[0]), int(raw[1]), int(raw[2]), int(raw[3]), raw[4], raw[5]
+    ke = raw[6:8]
+    field = raw[8:11]
+    o = 11
+    charges = raw[o:o + n]; o += n
+    R0 = raw[o:o + 3 * n].reshape(n, 3); o += 3 * n
+    V0 = raw[o:o + 3 * n].reshape(n, 3); o += 3 * n
+    R1 = raw[o:o + 3 * n].reshape(n, 3); o += 3 * n
+    V1 = raw[o:o + 3 * n].reshape(n, 3); o += 3 * n
+    assert o == raw.shape[0] and n == 3 * n_mol
+    masses = np.tile([15.99943, 1.007947, 1.007947], n_mol)
+    body = np.repeat(np.arange(1, n_mol + 1, dtype=np.int32), 3)
+    s = CpuStepper("oracle", body, masses, mode)
+    # the CUDA platform holds forces in fixed point (2^-32 kJ/mol/nm): the oracle steps with exact fp64 forces, which
+    # bounds the agreement at ~1e-10 relative per force evaluation
+    s.set_state(R0, np.zeros((n, 3)), np.zeros((n, 3)))
+    s.set_tether(k, field, charges, R0)
+    s.compute_forces()
+    s.update(True, True)
+    s.set_state(V=V0)
+    s.update(False, True)
+    s.step(dt, steps)
+    Ro, Vo, _ = s.get_state()
+    eR, eV = common.rel_inf(R1, Ro), common.rel_inf(V1, Vo)
+    assert eR <= 1e-9 and eV <= 1e-8, (eR, eV)
+    assert common.rel_inf(ke, s.kinetic()) <= 1e-8
