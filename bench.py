@@ -54,12 +54,15 @@ def parse_args():
     ap.add_argument("--workload", default="water", choices=["water", "mixed"])
     ap.add_argument("--layout", default="vec3", choices=["vec3", "soa", "openmm-mixed", "openmm-double"],
                     help="caller-owned atom arrays: fp64 Vec3 / SoA planes, or the OpenMM-CUDA boundary formats")
-    ap.add_argument("--shuffle", action="store_true", help="atoms stored in a random permutation (rbk_set_atom_location)")
+    ap.add_argument("--shuffle", nargs="?", const="molecules", default=None, choices=["molecules", "atoms"],
+                    help="caller's atom order differs from the plugin's (rbk_set_atom_location): 'molecules' = whole bodies / free atoms "
+                         "permuted as units, what OpenMM's reorderAtoms does; 'atoms' = every atom on its own (worst case)")
     ap.add_argument("--forces", default="alternating", choices=["alternating", "constant"],
                     help="fixed synthetic forces: sign flipping every step (default) or literally constant (SURVEY 8d)")
     ap.add_argument("--no-parity", action="store_true", help="skip the CPU-oracle subsample check after the timed region")
     ap.add_argument("--no-fuse", action="store_true", help="step with separate part1/part2 launches only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (baseline/ref_cuda)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dt-fs", type=float, default=1.0, help="time step in fs (BASELINE: 1 fs)")
     return ap.parse_args()
@@ -231,8 +234,19 @@ class AtomArrays:
         self.t, self.sys, self.layout, self.dev = torch, system, layout, dev
         n = self.n = sysd["masses"].shape[0]
         self.order = None
-        if shuffle:
-            self.order = np.random.Generator(np.random.Philox(key=12345)).permutation(n)     # atom i lives at slot order[i]
+        if shuffle and system is not None:
+            rng = np.random.Generator(np.random.Philox(key=12345))
+            if shuffle == "atoms":
+                self.order = rng.permutation(n)                   # atom i lives at slot order[i]
+            else:
+                # units = runs of consecutive atoms with the same positive body label, and single free atoms
+                body = sysd["bodyIndices"]
+                start = np.nonzero(np.concatenate([[True], (body[1:] != body[:-1]) | (body[1:] <= 0)]))[0]
+                length = np.diff(np.concatenate([start, [n]]))
+                perm = rng.permutation(start.shape[0])            # unit perm[k] is stored k-th
+                new_start = np.empty_like(start)
+                new_start[perm] = np.concatenate([[0], np.cumsum(length[perm])[:-1]])
+                self.order = (np.repeat(new_start - start, length) + np.arange(n)).astype(np.int64)
             system.set_atom_location(self.order[system.atom_index()].astype(np.int32))
         self.openmm = layout.startswith("openmm")
         F = sysd["F"]
@@ -338,6 +352,42 @@ def parity_subsample(sysd, arrays, mode, total_steps, alternate, n_bodies=2000, 
             "bodies": int(pick.shape[0]), "atoms": int(atoms.shape[0]),
             "how": "random subsample re-run on the CPU oracle (oracle/rb_oracle.c) for every step the device arrays have seen; "
                    "||gpu - cpu||_inf / ||cpu||_inf"}
+
+
+def gpu_reference(system, sysd, mode, steps, alternate, dev):
+    """The kernels this library replaces, on the same GPU and workload: the reference's own CUDA kernels
+    (platforms/cuda/src/kernels/rigidbodyintegrator.cu, compiled in place for sm_100a by baseline/ref_cuda/Makefile) driven as
+    CudaIntegrateRigidBodyStepKernel::execute drives them - integrateRigidBodyPart1, integrateRigidBodyPart2, blocks of 128
+    threads - on OpenMM-format arrays (mixed and double precision).  Bench infrastructure, like cpu_baseline."""
+    try:
+        from baseline.ref_cuda import refcuda
+    except Exception:
+        return None
+    out = {}
+    n = sysd["masses"].shape[0]
+    quant = dict(sysd, F=np.round(sysd["F"] * 4294967296.0) / 4294967296.0)
+    for precision in ("mixed", "double"):
+        if not refcuda.available(precision, mode, 0):
+            continue
+        A = AtomArrays(None, quant, "openmm-" + precision, None, dev, alternate)
+        best = None
+        for blocks in (6, 12, 24):                           # OpenMM's grid cap is 6 blocks per SM; larger grids tried in the reference's favour
+            ref = refcuda.RefCudaSystem(precision, mode, 0, system.host_bodies(), system.body_fixed(), system.atom_index(),
+                                        system.counts()["numFree"], A.padded)
+            ref.blocks_per_sm = blocks
+            B = AtomArrays(None, quant, "openmm-" + precision, None, dev, alternate)
+            _, cur = ref.time_steps(DT, 3, B.posq, B.corr, B.velm, B.forces[0], B.forces[1], 0)
+            ms, _ = ref.time_steps(DT, steps, B.posq, B.corr, B.velm, B.forces[0], B.forces[1], cur)
+            if best is None or ms < best[0]:
+                best = (ms, blocks)
+            ref.close()
+        nB = system.counts()["numBodies"]
+        out[precision] = {"value": nB * steps / (best[0] * 1e-3), "unit": UNIT, "ms_per_step": best[0] / steps, "blocks_per_sm": best[1], "steps": steps}
+    if not out:
+        return None
+    out["kernels"] = ("integrateRigidBodyPart1 + integrateRigidBodyPart2 of the reference (one thread per body, AoS BodyData), "
+                      "sources compiled in place from /root/reference, CUDA-event timed, inputs resident")
+    return out
 
 
 def committed_json(name):
@@ -503,7 +553,7 @@ def run_b200_arm(args):
     ach = dom[1] / (dom[2] * 1e-3) / 1e9
     kernel_name = {"part2Part1": "rbk::part2Part1Kernel" if not large else "rbk_part2_part1 call = part2LargeKernel + part1Kernel (rotation) + atomPositionKernel + freeAtomsKernel<3>",
                    "part1": "rbk_part1 call", "part2": "rbk_part2 call"}[dom[0]]
-    traffic = ncu_traffic(f"{dom[0]}_mode{args.mode}_{args.workload}{args.molecules}_{args.layout}{'_shuffle' if args.shuffle else ''}")
+    traffic = ncu_traffic(f"{dom[0]}_mode{args.mode}_{args.workload}{args.molecules}_{args.layout}{'_shuffle_' + args.shuffle if args.shuffle else ''}")
     work_ach = (work1 + work2) / (dom[2] * 1e-3) / 1e9 if tf is not None else None
     fp64 = committed_json("fp64_peak.json")
     roofline = {
@@ -549,6 +599,11 @@ def run_b200_arm(args):
                "call": "one rbk_execute_host per step with that step's forces in pinned host memory: forces H2D (copy stream) under part1 + "
                        "positions D2H, part2, sync; velocities D2H once, after the last step"}
 
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference and args.workload == "water":
+        system.upload()                                   # host model = the initial state; the reference starts from it too
+        gpu_ref = gpu_reference(system, sysd, args.mode, max(3, min(args.steps, 30)), alternate, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -562,10 +617,10 @@ def run_b200_arm(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": name, "per_gpu": "one independent replica per GPU (replicas only, no collective)",
-                       "layout": args.layout, "shuffle": bool(args.shuffle), "forces": args.forces, "dt_ps": DT, "bodies": nB, "body_atoms": nA, "free_atoms": nF,
+                       "layout": args.layout, "shuffle": args.shuffle, "series_order": system.series_order(), "forces": args.forces, "dt_ps": DT, "bodies": nB, "body_atoms": nA, "free_atoms": nF,
                        "l2": "no flush needed: the per-step working set (state + atoms, >500 MB at 1M waters) exceeds the 126 MB L2"},
             "ns_per_day": (args.steps / (ms * 1e-3)) * DT * 1e-3 * 86400.0,
-            "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
             "parity_subsample": parity,
             "kinetic_energy_kJmol": {"start": [float(ke_start[0]), float(ke_start[1])], "end": [float(ke[0]), float(ke[1])],
                                      "note": "translational, rotational"},

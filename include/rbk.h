@@ -42,6 +42,9 @@ const char* rbk_last_error(void);
 /* Diagnostics: host<->device copies issued by librbk in this process so far - out[4] = H2D calls, H2D bytes, D2H calls,
  * D2H bytes.  The device entry points (rbk_part1/2*, rbk_part2_part1*, rbk_free_*) must not move any of them. */
 int         rbk_debug_copy_counters(const rbk_system* sys, long long* out);
+/* Diagnostics: the Taylor order the mode-0 water kernels will use at their next launch (11, 13 or 16; DESIGN.md, "series
+ * ladder").  The choice is made on the device from the previous launch's convergence statistics. */
+int         rbk_debug_series_order(rbk_system* sys, int* out, void* stream);
 
 /* ---- host model -------------------------------------------------------------------------- */
 

@@ -3,6 +3,7 @@
 #include "../../include/rbk.h"
 #include "rbk_device.hpp"
 #include "rbk_host.hpp"
+#include "rbk_math.cuh"
 
 #include <cuda.h>
 
@@ -76,6 +77,7 @@ struct rbk_system {
     int4* dBodyTileMeta = nullptr;
     int4* dWarpTileMeta = nullptr;
     int* dTileCounter = nullptr;
+    rbk::SeriesControl* dSeriesCtl = nullptr;
     rbk::TileMaps tileMaps{};        // TMA descriptors of the one-warp-tile pipeline (valid when dev.tileMaps != NULL)
     int* dAtomLoc = nullptr;
     long long* dForcePacked = nullptr;   // scratch of rbk_reorder_openmm
@@ -105,7 +107,7 @@ struct rbk_system {
     std::vector<double> staging, oldPositions;
 
     ~rbk_system() {
-        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter);
+        cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter); cudaFree(dSeriesCtl);
         cudaFree(dAtomLoc); cudaFree(dForcePacked); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (side.stream) cudaStreamDestroy(side.stream);
@@ -272,6 +274,11 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(devAlloc(sys->dTileCounter, 1));
     RBK_CUDA(cudaMemsetAsync(sys->dTileCounter, 0, sizeof(int), st));
     d.tileCounter = sys->dTileCounter;
+    RBK_CUDA(devAlloc(sys->dSeriesCtl, 1));
+    const rbk::SeriesControl ctl0 = {1, 0u, 0u, 0u};           // start on the middle rung (order 13); the kernels move it
+    RBK_CUDA(copyAsync(sys->dSeriesCtl, &ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, st));
+    RBK_CUDA(cudaStreamSynchronize(st));
+    d.seriesCtl = sys->dSeriesCtl;
     d.tileMaps = d.numWarpTiles > 0 && encodeTileMaps(sys) ? &sys->tileMaps : nullptr;
     d.atomLoc = nullptr;
     d.freeInvMass = sys->dFreeInvMass;
@@ -312,6 +319,16 @@ int viewOf(const void* p, int layout, long long stride, AtomView& v) {
 extern "C" {
 
 int rbk_version(void) { return RBK_VERSION; }
+
+int rbk_debug_series_order(rbk_system* sys, int* out, void* stream) {
+    if (!sys || !out) return fail(RBK_EINVAL, "rbk_debug_series_order: NULL argument");
+    if (!sys->allocated) return fail(RBK_ESTATE, "rbk_debug_series_order: call rbk_upload first");
+    rbk::SeriesControl ctl;
+    RBK_CUDA(cudaMemcpyAsync(&ctl, sys->dSeriesCtl, sizeof(ctl), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+    RBK_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    *out = rbk::kSeriesLadder[ctl.rung < 0 ? 0 : (ctl.rung > 2 ? 2 : ctl.rung)];
+    return RBK_OK;
+}
 
 int rbk_debug_copy_counters(const rbk_system*, long long* out) {
     if (!out) return fail(RBK_EINVAL, "rbk_debug_copy_counters: NULL argument");

@@ -39,6 +39,15 @@ constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
 
 struct TileMaps;
 
+// Device-resident control block of the exact rotation's series ladder (rbk_math.cuh, exactRotationLadder): the hot water
+// kernels read `rung` at launch, count the bodies whose truncation check failed at this rung / would have failed one rung
+// lower, and the last CTA of the launch moves the rung for the next launch.  No host involvement: works under CUDA graphs,
+// and the sequence of rungs is a deterministic function of the trajectory.
+struct SeriesControl {
+    int rung;
+    unsigned done, fails, lower;
+};
+
 struct DeviceSystem {
     int numBodies, numFree, numBodyAtoms, numTiles, numBodyTiles, numFreeBlocks;
     int rotationMode, maxBodySize, numSMs, splitPart1;
@@ -56,6 +65,7 @@ struct DeviceSystem {
     const int4* warpTileMeta;    // per one-warp tile (subdivision of the atom tiles), same fields
     const TileMaps* tileMaps;    // HOST pointer (kernel-parameter copies are made at launch); NULL = no TMA tensor path
     const int* atomLoc;
+    SeriesControl* seriesCtl;
     int* tileCounter;            // zero between launches: tiles claimed so far by the persistent step-fused kernel
     const double* freeInvMass;
     double* savedPos;

@@ -786,7 +786,8 @@ __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k 
 // per-thread 8-byte cp.async through the slot ring (raw words, converted where they are consumed); positions and velocities
 // leave through the format-aware stores.  storeFT = false: interior step of step(n) - nothing reads F and tau before the
 // next Part 2 rewrites them, so they stay in registers (48 B per body-step less).
-template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER>
+// LADDER (one-warp exact-rotation tiles): the series order comes from the device-resident ladder control (SeriesControl).
+template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER, bool LADDER>
 __global__ void __launch_bounds__(BODIES, (STAGES == 2 ? 256 : 512)/BODIES)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force,
                  const __grid_constant__ TileMaps maps, const bool useMaps, const bool storeFT) {
@@ -795,6 +796,9 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     FusedSmem<BODIES, ATOMS, STAGES, GATHER>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS, STAGES, GATHER>*>(smemRaw);
     constexpr int kBlock = BODIES, kWarps = BODIES/32;          // shadow the file-level constants inside this kernel
     constexpr int RING = GATHER ? 4 : 3;
+    static_assert(!LADDER || (EXACT && BODIES == 32), "the series ladder is wired for one-warp exact-rotation tiles");
+    const int rung = LADDER ? S.seriesCtl->rung : 0;
+    unsigned ladderFails = 0u, ladderLower = 0u;               // bodies of this CTA's tiles (warp-uniform)
     const int4* const tileMeta = BODIES == 32 ? S.warpTileMeta : S.tileMeta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
@@ -1032,6 +1036,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             }
             // ---- C: thread per body: second kick of this step, then first kick + drift + rotation of the next
             double (*B)[kBlock] = T.body;
+            unsigned flags = 0u;
             if (tid < m.y) {
                 d3 r = {B[0][tid], B[1][tid], B[2][tid]};
                 d3 p = {B[3][tid], B[4][tid], B[5][tid]};
@@ -1074,7 +1079,8 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     sm.acc[0][tid] = vcm.x; sm.acc[1][tid] = vcm.y; sm.acc[2][tid] = vcm.z;
                     sm.acc[3][tid] = om.x; sm.acc[4][tid] = om.y; sm.acc[5][tid] = om.z;
                 }
-                bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
+                if (LADDER) bodyPart1Ladder(rung, dt, F, tau, invm, invI, r, p, q, pi, flags);
+                else bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
                 double* s = S.state + (size_t) (m.x + tid);
                 storePlane3(s + PL_R*ld, ld, r);
                 storePlane3(s + PL_P*ld, ld, p);
@@ -1086,6 +1092,10 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 }
                 B[0][tid] = r.x; B[1][tid] = r.y; B[2][tid] = r.z;
                 B[6][tid] = q.w; B[7][tid] = q.x; B[8][tid] = q.y; B[9][tid] = q.z;
+            }
+            if (LADDER) {
+                ladderFails += __popc(__ballot_sync(kFull, (flags & 1u) != 0u));
+                ladderLower += __popc(__ballot_sync(kFull, (flags & 2u) != 0u));
             }
             __syncthreads();
 
@@ -1109,7 +1119,26 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         }
         cpWait<0>();
     }
-
+    if (LADDER && tid == 0) {
+        // publish this CTA's counts; the last CTA of the launch moves the rung for the next launch: up when more than 4e-4
+        // of the bodies needed the retry path, down when fewer than 1e-4 would need it one rung lower
+        SeriesControl* c = S.seriesCtl;
+        if (ladderFails) atomicAdd(&c->fails, ladderFails);
+        if (ladderLower) atomicAdd(&c->lower, ladderLower);
+        __threadfence();
+        if (atomicAdd(&c->done, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const unsigned fails = atomicAdd(&c->fails, 0u), lower = atomicAdd(&c->lower, 0u);
+            const double n = (double) S.numBodies;
+            int next = rung;
+            if ((double) fails > 4.0e-4*n && rung < 2) next = rung + 1;
+            else if (rung > 0 && (double) lower < 1.0e-4*n) next = rung - 1;
+            c->rung = next;
+            c->fails = 0u;
+            c->lower = 0u;
+            c->done = 0u;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1284,7 +1313,8 @@ cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, Ato
                              bool freeAtoms = true, bool storeFT = true) {
     typedef FusedSmem<BODIES, ATOMS, STAGES, GATHER> Smem;
     constexpr bool NATIVE = !GATHER;
-    auto kernel = part2Part1Kernel<EXACT, SMALL, NATIVE, BODIES, ATOMS, STAGES, P1ONLY, GATHER>;
+    constexpr bool LADDER = EXACT && BODIES == 32;
+    auto kernel = part2Part1Kernel<EXACT, SMALL, NATIVE, BODIES, ATOMS, STAGES, P1ONLY, GATHER, LADDER>;
     static LaunchCache cache;
     int blocks = 0;                                            // persistent CTAs: one full wave, whatever fits
     cudaError_t e = cache.get(kernel, BODIES, sizeof(Smem), blocks);

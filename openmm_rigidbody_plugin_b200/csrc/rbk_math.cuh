@@ -394,11 +394,13 @@ RBK_HD d4 quatTimesDiag(d4 q, double s) {                  // q (x) 1/2 (1, s, s
             0.5*(q.y + s*(q.w - q.x + q.z)), 0.5*(q.z + s*(q.w + q.x - q.y))};
 }
 
-template <int K>
-RBK_HD double exactRotationSeriesAxis1(double dt, d3 invI, d3 l0, d4& q, d3& lOut);
+// KLOW > 0: also report (lowerFails) whether the truncation check of an order-KLOW series would have failed on this body -
+// the same test on orders KLOW-1, KLOW, six additions - so that a caller running a ladder of orders can step down.
+template <int K, int KLOW>
+RBK_HD double exactRotationSeriesAxis1(double dt, d3 invI, d3 l0, d4& q, d3& lOut, bool& lowerFails);
 
-template <int K>
-RBK_HD double exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
+template <int K, int KLOW = 0>
+RBK_HD double exactRotationSeries(double dt, d3 invI, d4& q, d4& pi, bool* lowerFails = nullptr) {
     const d3 l = quatBt(q, pi)*0.5;
     const int j = l.y < l.x ? (l.z < l.y ? 2 : 1) : (l.z < l.x ? 2 : 0);       // argmin: the new "axis 1"
     const double s = j == 1 ? 1.0 : -1.0;
@@ -406,7 +408,9 @@ RBK_HD double exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
     const d3 invIp = j == 0 ? invI : (j == 1 ? d3{invI.y, invI.z, invI.x} : d3{invI.z, invI.x, invI.y});
     d4 qp = j == 0 ? q : quatTimesDiag(q, s);
     d3 ln;
-    const double excess = exactRotationSeriesAxis1<K>(dt, invIp, lp, qp, ln);
+    bool low = false;
+    const double excess = exactRotationSeriesAxis1<K, KLOW>(dt, invIp, lp, qp, ln, low);
+    if (KLOW > 0 && lowerFails != nullptr) *lowerFails = low;
     if (excess != 0.0) return excess;
     q = j == 0 ? qp : quatTimesDiag(qp, -s);
     const d3 lb = j == 0 ? ln : (j == 1 ? d3{ln.z, ln.x, ln.y} : d3{ln.y, ln.z, ln.x});
@@ -416,8 +420,9 @@ RBK_HD double exactRotationSeries(double dt, d3 invI, d4& q, d4& pi) {
 
 // The series proper, reduction about axis 1 of the (relabelled) body frame: advances q and returns the new body-frame
 // angular momentum in lOut.
-template <int K>
-RBK_HD double exactRotationSeriesAxis1(double dt, d3 invI, d3 l0, d4& q, d3& lOut) {
+template <int K, int KLOW>
+RBK_HD double exactRotationSeriesAxis1(double dt, d3 invI, d3 l0, d4& q, d3& lOut, bool& lowerFails) {
+    lowerFails = false;
     if (l0.y*l0.y + l0.z*l0.z < DBL_EPSILON) {             // rotation about axis 1 itself
         d4 pi = quatB(q, l0*2.0);
         uniaxial<0>(dt, invI.x, q, pi);
@@ -477,6 +482,11 @@ RBK_HD double exactRotationSeriesAxis1(double dt, d3 invI, d3 l0, d4& q, d3& lOu
     const double tailL = fabs(x[K]) + fabs(y[K]) + fabs(z[K]) + fabs(x[K - 1]) + fabs(y[K - 1]) + fabs(z[K - 1]);
     // truncation check on the last two orders of every series (relative to L, resp. r[0])
     const double tailR = fabs(r[K]) + fabs(r[K - 1]);
+    if (KLOW > 0) {
+        constexpr int J = KLOW > 0 && KLOW <= K ? KLOW : K;
+        const double lowL = fabs(x[J]) + fabs(y[J]) + fabs(z[J]) + fabs(x[J - 1]) + fabs(y[J - 1]) + fabs(z[J - 1]);
+        lowerFails = !(lowL <= 2.0e-16*L && fabs(r[J]) + fabs(r[J - 1]) <= 2.0e-16*fabs(r[0]));
+    }
 #ifndef RBK_EXPERIMENT_SKIP_CHECK
     if (!(tailL <= 2.0e-16*L && tailR <= 2.0e-16*fabs(r[0]))) return fmax(tailL/(2.0e-16*L), tailR/(2.0e-16*fabs(r[0])));
 #endif
@@ -505,14 +515,15 @@ constexpr int kSeriesOrder = RBK_SERIES_ORDER;
 // suffices - a slow body holds up its whole warp, and with few tiles per CTA the whole launch.  Only when that would
 // need more than kMaxSubSteps, or still fails, the elliptic-integral route (which needs I = 1/invI) takes over.
 constexpr int kMaxSubSteps = 32;
+template <int K>
 RBK_HD_NOINLINE void exactRotationRetry(double dt, d3 invI, d4& q, d4& pi, double excess) {
-    const double want = 1.25*exp2(log2(excess)/(kSeriesOrder - 1));
+    const double want = 1.25*exp2(log2(excess)/(K - 1));
     if (want <= (double) kMaxSubSteps) {                       // false for inf / NaN as well
         const int n = want < 2.0 ? 2 : (int) ceil(want);
         d4 q1 = q, p1 = pi;
         const double h = dt/n;
         bool ok = true;
-        for (int i = 0; i < n && ok; i++) ok = exactRotationSeries<kSeriesOrder>(h, invI, q1, p1) == 0.0;
+        for (int i = 0; i < n && ok; i++) ok = exactRotationSeries<K>(h, invI, q1, p1) == 0.0;
         if (ok) { q = q1; pi = p1; return; }
     }
 #ifndef RBK_EXPERIMENT_NO_ELLIPTIC
@@ -525,7 +536,26 @@ RBK_HD_NOINLINE void exactRotationRetry(double dt, d3 invI, d4& q, d4& pi, doubl
 // long step) the retry path above.
 RBK_HD void exactRotation(double dt, d3 invI, d4& q, d4& pi) {
     const double excess = exactRotationSeries<kSeriesOrder>(dt, invI, q, pi);
-    if (excess != 0.0) exactRotationRetry(dt, invI, q, pi, excess);
+    if (excess != 0.0) exactRotationRetry<kSeriesOrder>(dt, invI, q, pi, excess);
+}
+
+// The same with the series order chosen at run time from a short ladder (the hot water kernels; the choice is uniform over
+// a launch, so only one of the inlined copies is ever in the instruction cache).  A body-step costs ~2 K^2 FMAs and order K
+// covers |omega| dt up to ~(2e-16)^(1/K): for TIP3P water at 300 K order 11 fails its check for 1e-5 of the bodies at 1 fs
+// (order 12: none; order 10: 0.5 %), order 13 for 1.5e-4 at 2 fs, order 16 for 3e-4 at 4 fs (tools/series_stats.py).
+// flags: bit 0 = the check failed at this order (the retry path ran), bit 1 = it would have failed one rung lower.
+constexpr int kSeriesLadder[3] = {11, 13, 16};
+template <int K, int KLOW>
+RBK_HD void exactRotationRung(double dt, d3 invI, d4& q, d4& pi, unsigned& flags) {
+    bool low = false;
+    const double excess = exactRotationSeries<K, KLOW>(dt, invI, q, pi, &low);
+    flags = (excess != 0.0 ? 1u : 0u) | (low ? 2u : 0u);
+    if (excess != 0.0) exactRotationRetry<K>(dt, invI, q, pi, excess);
+}
+RBK_HD void exactRotationLadder(int rung, double dt, d3 invI, d4& q, d4& pi, unsigned& flags) {
+    if (rung <= 0) exactRotationRung<11, 0>(dt, invI, q, pi, flags);
+    else if (rung == 1) exactRotationRung<13, 11>(dt, invI, q, pi, flags);
+    else exactRotationRung<16, 13>(dt, invI, q, pi, flags);
 }
 
 } // namespace rbk

@@ -26,6 +26,14 @@ RBK_HD void bodyPart1(double dt, int nSplit, d3 F, d3 tau, double invm, d3 invI,
     else noSquish(dt, nSplit, invI, q, pi);
 }
 
+// Part 1 with the exact rotation's series order taken from the ladder (rbk_math.cuh): rung = 0, 1, 2
+RBK_HD void bodyPart1Ladder(int rung, double dt, d3 F, d3 tau, double invm, d3 invI, d3& r, d3& p, d4& q, d4& pi, unsigned& flags) {
+    p = p + F*(0.5*dt);
+    pi = pi + quatC(q, tau)*dt;
+    r = r + p*(invm*dt);
+    exactRotationLadder(rung, dt, invI, q, pi, flags);
+}
+
 RBK_HD d3 atomPosition(d3 r, d4 q, d3 d) { return r + bodyToSpace(q, d); }
 
 // Second half kick of one body from the reduced force / torque; returns what the atoms need to

@@ -125,6 +125,12 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_get_body_fixed(self.h, _d(d)))
         return d
 
+    def series_order(self, stream=None):
+        """Taylor order the mode-0 water kernels will use at their next launch (rbk_debug_series_order)."""
+        out = np.zeros(1, np.int32)
+        check(self.lib.rbk_debug_series_order(self.h, _i(out), _stream(stream)))
+        return int(out[0])
+
     # ---- device
     def upload(self, stream=None):
         check(self.lib.rbk_upload(self.h, _stream(stream)))

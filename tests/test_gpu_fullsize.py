@@ -32,6 +32,7 @@ def check_against_oracle(sysd, mode, steps, layout="vec3", shuffle=False, dt=0.0
     s = GpuStepper(sysd["bodyIndices"], sysd["masses"], mode, layout=layout, shuffle=shuffle)
     s.fused = True
     common.init_like_reference(s, sysd)
+    norm0 = np.linalg.norm(s.bodies()["q"], axis=1)
     s.step(dt, steps)
     R, V, _ = s.get_state()
     assert np.isfinite(R).all() and np.isfinite(V).all()
@@ -46,12 +47,15 @@ def check_against_oracle(sysd, mode, steps, layout="vec3", shuffle=False, dt=0.0
     ke = s.kinetic()
     ke_atoms = 0.5 * float(np.sum(sysd["masses"][:, None] * V * V))
     assert abs(ke_atoms - ke.sum()) <= 1e-10 * ke_atoms, (ke_atoms, ke)
-    q = s.bodies()["q"]
-    assert np.max(np.abs(np.linalg.norm(q, axis=1) - 1.0)) < 1e-13
+    # |q|: the exact rotation renormalises every step; NO-SQUISH (like the reference's) only preserves the norm the body
+    # build left (1 to ~1e-11, set by the orthonormality of the eigenvectors), so it is compared with the initial one
+    norm = np.linalg.norm(s.bodies()["q"], axis=1)
+    assert np.max(np.abs(norm - (1.0 if mode == 0 else norm0))) < 1e-13
+    order = s.sys.series_order()
     s.close()
     del s
     torch.cuda.empty_cache()
-    return R, V, eR, eV
+    return R, V, eR, eV, order
 
 
 @pytest.mark.parametrize("mode", [0, 10])
@@ -59,7 +63,8 @@ def test_c2_c3_1M_waters_fused(mode):
     """BASELINE configs 2 (mode 0) and 3 (mode 10): 1,000,000 rigid waters stepped with the one-pass kernel."""
     n_mol = 1_000_000
     sysd = common.synth.water_box(n_mol, seed=20240001)
-    R, V, eR, eV = check_against_oracle(sysd, mode, 3)
+    R, V, eR, eV, order = check_against_oracle(sysd, mode, 3)
+    assert mode != 0 or order == 11                     # 1 fs at 300 K: the series ladder settles on its lowest rung
     Rm = R.reshape(n_mol, 3, 3)
     assert np.max(np.abs(np.linalg.norm(Rm[:, 1] - Rm[:, 0], axis=1) - common.synth.R_OH)) < 1e-12
     assert np.max(np.abs(np.linalg.norm(Rm[:, 2] - Rm[:, 1], axis=1) - 2 * common.synth.R_OH * np.sin(0.5 * common.synth.ANGLE_HOH))) < 1e-12
@@ -69,21 +74,21 @@ def test_c2_c3_1M_waters_fused(mode):
 def test_c4_mixed_200k_bodies_500k_free():
     """BASELINE config 4: 200,000 bodies of 3-60 atoms (merged labels) + 500,000 interleaved free atoms, mode 0."""
     sysd = common.synth.mixed_system(200_000, 500_000)
-    _, _, eR, eV = check_against_oracle(sysd, 0, 3)
+    _, _, eR, eV, _ = check_against_oracle(sysd, 0, 3)
     print(f"config 4, fused stepping: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}")
 
 
 def test_c5_250k_waters_fused():
     """BASELINE config 5's per-GPU replica: 250,000 rigid waters (working set about the size of the L2)."""
     sysd = common.synth.water_box(250_000, seed=20240001)
-    _, _, eR, eV = check_against_oracle(sysd, 0, 4)
+    _, _, eR, eV, _ = check_against_oracle(sysd, 0, 4)
     print(f"250k waters, fused stepping: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}")
 
 
 def test_1M_waters_reordered_soa_fused():
     """The one-pass kernel's gather instantiation (atoms in a random permutation, SoA planes) at full size."""
     sysd = common.synth.water_box(1_000_000, seed=20240002)
-    _, _, eR, eV = check_against_oracle(sysd, 0, 3, layout="soa", shuffle=True)
+    _, _, eR, eV, _ = check_against_oracle(sysd, 0, 3, layout="soa", shuffle=True)
     print(f"1M waters reordered, fused stepping: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}")
 
 
@@ -91,5 +96,7 @@ def test_1M_waters_reordered_soa_fused():
 def test_long_time_steps_1M_waters(dt_fs):
     """Rigid bodies exist to allow 2-5 fs steps: the mode-0 kernel at 2 and 4 fs against the oracle."""
     sysd = common.synth.water_box(300_000, seed=20240003)
-    _, _, eR, eV = check_against_oracle(sysd, 0, 3, dt=dt_fs * 1e-3)
-    print(f"300k waters, dt {dt_fs} fs: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}")
+    _, _, eR, eV, order = check_against_oracle(sysd, 0, 4, dt=dt_fs * 1e-3)
+    # the device-side series ladder (DESIGN.md) has climbed: order 13 (or 16) at 2 fs, 16 at 4 fs
+    assert order == 16 if dt_fs == 4.0 else order in (13, 16), order
+    print(f"300k waters, dt {dt_fs} fs: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}, series order {order}")

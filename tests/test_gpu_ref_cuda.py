@@ -1,0 +1,124 @@
+"""librbk against the reference's OWN CUDA kernels (platforms/cuda/src/kernels/rigidbodyintegrator.cu, compiled in place
+by baseline/ref_cuda/Makefile and driven without OpenMM, baseline/ref_cuda/refcuda.py) on the same OpenMM-format device
+arrays:
+  * trajectories: the kernels this repo replaces ("the design to beat") and the replacement
+    agree to rounding - they differ in formulation (centre-of-mass velocity instead of momentum, rsqrt normalisation);
+  * refined ("shadow") energies, which the reference implements ONLY in these kernels (COMPMOD paths): this is the
+    pinned oracle of SURVEY.md section 8f row 4.  tests/golden/refcuda_refined_*.npz hold the same comparison as
+    committed vectors (generated on a B200 by tests/golden/make_golden_refcuda.py), so the pin survives without the
+    prebuilt libraries."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common
+from openmm_rigidbody_plugin_b200 import DeviceRigidBodySystem
+from openmm_rigidbody_plugin_b200._lib import RBK_OPENMM_DOUBLE, RBK_OPENMM_MIXED
+from test_gpu_openmm_layout import OpenMMArrays, build
+
+pytestmark = pytest.mark.gpu
+
+PREC = {"mixed": RBK_OPENMM_MIXED, "double": RBK_OPENMM_DOUBLE}
+
+
+def refcuda():
+    from baseline.ref_cuda import refcuda as rc
+    return rc
+
+
+def make_case(case):
+    if case == "water":
+        sysd = common.synth.water_box(3000, seed=81)
+    else:       # ragged bodies + interleaved free atoms (no constraints: the reference's free-atom path without a solver)
+        sysd = common.synth.mixed_system(700, 900, seed=82, max_atoms=24)
+    Fq = np.round(sysd["F"] * 4294967296.0).astype(np.int64)
+    return dict(sysd, F=Fq.astype(np.float64) / 4294967296.0), Fq
+
+
+def both(case, precision, mode, compmod, steps, dt=0.001, seed=83):
+    """The same system stepped by the reference's CUDA kernels and by librbk; returns the two array sets and handles."""
+    rc = refcuda()
+    if not rc.available(precision, mode, compmod):
+        pytest.skip(f"baseline/ref_cuda/_build variant {precision}/mode {mode}/COMPMOD {compmod} not built (needs /root/reference at build time)")
+    sysd, Fq = make_case(case)
+    n = len(sysd["masses"])
+    padded = ((n + 31) // 32) * 32
+    order = np.random.Generator(np.random.Philox(key=seed)).permutation(n)
+    s = build(sysd, mode)
+    loc = order[s.atom_index()].astype(np.int32)
+    s.set_atom_location(loc)
+    if compmod:
+        s.set_refined_energies(1)
+    A = OpenMMArrays(sysd, order, padded, PREC[precision], Fq)        # librbk's arrays
+    B = OpenMMArrays(sysd, order, padded, PREC[precision], Fq)        # the reference kernels' arrays
+    ref = rc.RefCudaSystem(precision, mode, compmod, s.host_bodies(), s.body_fixed(), loc, s.counts()["numFree"], padded)
+    for _ in range(steps):
+        s.part1_openmm(dt, *A.args())
+        s.part2_openmm(dt, *A.args())
+        ref.part1(dt, B.posq, B.corr, B.velm, B.force)
+        ref.part2(dt, B.posq, B.corr, B.velm, B.force)
+    return s, ref, A, B, dt
+
+
+@pytest.mark.parametrize("case", ["water", "mixed"])
+@pytest.mark.parametrize("precision,mode", [("mixed", 0), ("double", 0), ("double", 10)])
+def test_trajectories_agree_with_the_reference_cuda_kernels(case, precision, mode):
+    s, ref, A, B, dt = both(case, precision, mode, 0, steps=5)
+    Ra, Va = A.host()
+    Rb, Vb = B.host()
+    eR, eV = common.rel_inf(Ra, Rb), common.rel_inf(Va, Vb)
+    assert eR <= 1e-10 and eV <= 1e-9, (case, precision, mode, eR, eV)
+    ke = s.kinetic_openmm(A.velm, PREC[precision])
+    assert common.rel_inf(ke, ref.kinetic(B.velm)) <= 1e-9
+    rb, ob = ref.bodies(), s.download_bodies()
+    assert common.rel_inf(ob["rcm"], rb["r"]) <= 1e-10 and common.quat_rel(ob["q"], rb["q"]) <= 1e-9
+    assert common.rel_inf(ob["pi"], rb["pi"]) <= 1e-8 and common.rel_inf(ob["force"], rb["F"]) <= 1e-9
+    assert common.rel_inf(ob["torque"], rb["Ctau"]) <= 1e-8
+
+
+def refined_pair(case, precision, mode, steps):
+    s, ref, A, B, dt = both(case, precision, mode, 1, steps=steps)
+    ours = np.concatenate([s.refined_kinetic_openmm(dt, A.velm, PREC[precision]),
+                           [s.potential_refinement_openmm(dt, A.force, A.padded)]])
+    theirs = np.concatenate([ref.kinetic(B.velm, dt, refined=True), [ref.potential_refinement(dt, B.velm, B.force)]])
+    plain = s.kinetic_openmm(A.velm, PREC[precision])
+    return ours, theirs, plain
+
+
+@pytest.mark.parametrize("case", ["water", "mixed"])
+@pytest.mark.parametrize("precision,mode", [("double", 0), ("mixed", 0), ("double", 3)])
+def test_refined_energies_match_the_reference_cuda_kernels(case, precision, mode):
+    """rbk_refined_kinetic_openmm / rbk_potential_refinement_openmm against refinedKineticEnergies /
+    potentialEnergyRefinement of the reference (rigidbodyintegrator.cu:433-469, host sums CudaRigidBodyKernels.cpp:118-194)."""
+    ours, theirs, plain = refined_pair(case, precision, mode, steps=4)
+    assert np.all(np.isfinite(theirs)) and abs(theirs[2]) > 0.0
+    for k, name in enumerate(("refined KE translational", "refined KE rotational", "potential refinement")):
+        assert abs(ours[k] - theirs[k]) <= 1e-9 * abs(theirs[k]), (case, precision, mode, name, ours[k], theirs[k])
+    # (sanity: the refined kinetic energy is a small correction of the plain one for bodies)
+    if case == "water":
+        assert abs(ours[0] - plain[0]) < 0.05 * plain[0]
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(common.GOLDEN_DIR, "refcuda_refined_*.npz"))))
+def test_refined_energies_match_committed_reference_cuda_vectors(path):
+    """The same pin from committed vectors: inputs + the reference CUDA kernels' outputs recorded on a B200."""
+    g = dict(np.load(path))
+    sysd = {k: g[k] for k in ("bodyIndices", "masses", "R", "V", "F", "charges")}
+    precision, mode, steps, dt = str(g["precision"]), int(g["mode"]), int(g["steps"]), float(g["dt"])
+    n = len(sysd["masses"])
+    padded = ((n + 31) // 32) * 32
+    Fq = np.round(sysd["F"] * 4294967296.0).astype(np.int64)
+    s = build(sysd, mode)
+    order = g["order"]
+    s.set_atom_location(order[s.atom_index()].astype(np.int32))
+    s.set_refined_energies(1)
+    A = OpenMMArrays(sysd, order, padded, PREC[precision], Fq)
+    for _ in range(steps):
+        s.part1_openmm(dt, *A.args())
+        s.part2_openmm(dt, *A.args())
+    ours = np.concatenate([s.refined_kinetic_openmm(dt, A.velm, PREC[precision]), [s.potential_refinement_openmm(dt, A.force, padded)]])
+    assert np.all(np.abs(ours - g["reference"]) <= 1e-9 * np.abs(g["reference"])), (ours, g["reference"])
+    Ra, Va = A.host()
+    assert common.rel_inf(Ra, g["R_end"]) <= 1e-10 and common.rel_inf(Va, g["V_end"]) <= 1e-9
