@@ -33,7 +33,9 @@ typedef double mixed; typedef double2 mixed2; typedef double3 mixed3; typedef do
 #define make_mixed3 make_double3
 #define make_mixed4 make_double4
 #else
-#define USE_MIXED_PRECISION 1
+// OpenMM's CudaContext defines USE_DOUBLE_PRECISION *instead of* USE_MIXED_PRECISION in double-precision mode, so the
+// reference's elliptic.cu (which tests USE_MIXED_PRECISION) runs its Carlson / Jacobi routines with the single-precision
+// tolerances (errtol 0.03, FLT_EPSILON) on doubles there - reproduced as it is.
 #define USE_DOUBLE_PRECISION 1
 typedef double real; typedef double2 real2; typedef double3 real3; typedef double4 real4;
 typedef double mixed; typedef double2 mixed2; typedef double3 mixed3; typedef double4 mixed4;

@@ -52,6 +52,18 @@ double rbkh_series_excess(double dt, const double* I, const double* q, const dou
     return exactRotationSeries<kSeriesOrder>(dt, inv, qq, pp);
 }
 
+// The ladder entry point of the hot kernels: rung 0, 1, 2 = order 11, 13, 16; returns the flags (bit 0: check failed at this
+// rung and the retry path ran, bit 1: the check would have failed one rung lower).
+unsigned rbkh_exact_ladder(int rung, double dt, const double* I, double* q, double* pi) {
+    d3 inv = {1.0/I[0], 1.0/I[1], 1.0/I[2]};
+    d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};
+    unsigned flags = 0;
+    exactRotationLadder(rung, dt, inv, qq, pp, flags);
+    q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z;
+    pi[0] = pp.w; pi[1] = pp.x; pi[2] = pp.y; pi[3] = pp.z;
+    return flags;
+}
+
 void rbkh_nosquish(double dt, int n, const double* invI, double* q, double* pi) {
     d3 inv = {invI[0], invI[1], invI[2]};
     d4 qq = {q[0], q[1], q[2], q[3]}, pp = {pi[0], pi[1], pi[2], pi[3]};

@@ -54,6 +54,21 @@ def test_cpp_integration_tests_on_gpu(glue):
     assert r.returncode == 0 and r.stdout.strip().endswith("Done"), r.stdout + r.stderr
 
 
+def test_cmake_packaging_configures_and_builds_against_the_shim(glue, tmp_path):
+    """glue/CMakeLists.txt (OPENMM_DIR-based, like the reference's CMake): without an OpenMM installation it must fall
+    back to the header shim and build the plugin library and the three test programs."""
+    import shutil
+    if shutil.which("cmake") is None:
+        pytest.skip("cmake not available")
+    src = os.path.join(common.ROOT, "openmm_rigidbody_plugin_b200", "glue")
+    cfg = subprocess.run(["cmake", "-S", src, "-B", str(tmp_path), "-DOPENMM_DIR=/nonexistent"], capture_output=True, text=True)
+    assert cfg.returncode == 0, cfg.stdout + cfg.stderr
+    assert "header shim" in cfg.stdout
+    bld = subprocess.run(["cmake", "--build", str(tmp_path), "-j", "8"], capture_output=True, text=True, timeout=900)
+    assert bld.returncode == 0, bld.stdout[-2000:] + bld.stderr[-2000:]
+    assert os.path.exists(os.path.join(str(tmp_path), "libRigidBodyPluginB200.so"))
+
+
 def test_glue_registers_on_the_cuda_platform(glue):
     out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(glue, "libRigidBodyPluginB200.so")],
                          capture_output=True, text=True, check=True).stdout

@@ -69,13 +69,19 @@ def test_trajectories_agree_with_the_reference_cuda_kernels(case, precision, mod
     Ra, Va = A.host()
     Rb, Vb = B.host()
     eR, eV = common.rel_inf(Ra, Rb), common.rel_inf(Va, Vb)
-    assert eR <= 1e-10 and eV <= 1e-9, (case, precision, mode, eR, eV)
+    # In double-precision mode OpenMM defines USE_DOUBLE_PRECISION instead of USE_MIXED_PRECISION and the reference's
+    # elliptic.cu then runs with its single-precision tolerances (errtol 0.03, FLT_EPSILON): its exact rotation is only
+    # good to ~1e-7 there (baseline/ref_cuda/ref_cuda_harness.cu); mixed precision and NO-SQUISH compare tightly.
+    loose = precision == "double" and mode == 0
+    tR, tV = (2e-6, 2e-5) if loose else (1e-10, 1e-9)
+    assert eR <= tR and eV <= tV, (case, precision, mode, eR, eV)
     ke = s.kinetic_openmm(A.velm, PREC[precision])
-    assert common.rel_inf(ke, ref.kinetic(B.velm)) <= 1e-9
+    assert common.rel_inf(ke, ref.kinetic(B.velm)) <= (1e-5 if loose else 1e-9)
     rb, ob = ref.bodies(), s.download_bodies()
-    assert common.rel_inf(ob["rcm"], rb["r"]) <= 1e-10 and common.quat_rel(ob["q"], rb["q"]) <= 1e-9
-    assert common.rel_inf(ob["pi"], rb["pi"]) <= 1e-8 and common.rel_inf(ob["force"], rb["F"]) <= 1e-9
-    assert common.rel_inf(ob["torque"], rb["Ctau"]) <= 1e-8
+    f = 1e4 if loose else 1.0
+    assert common.rel_inf(ob["rcm"], rb["r"]) <= 1e-10 and common.quat_rel(ob["q"], rb["q"]) <= 1e-9*f
+    assert common.rel_inf(ob["pi"], rb["pi"]) <= 1e-8*f and common.rel_inf(ob["force"], rb["F"]) <= 1e-9
+    assert common.rel_inf(ob["torque"], rb["Ctau"]) <= 1e-8*f
 
 
 def refined_pair(case, precision, mode, steps):
@@ -94,8 +100,11 @@ def test_refined_energies_match_the_reference_cuda_kernels(case, precision, mode
     potentialEnergyRefinement of the reference (rigidbodyintegrator.cu:433-469, host sums CudaRigidBodyKernels.cpp:118-194)."""
     ours, theirs, plain = refined_pair(case, precision, mode, steps=4)
     assert np.all(np.isfinite(theirs)) and abs(theirs[2]) > 0.0
+    # (double precision + exact rotation: the reference's own rotation is only ~1e-7 accurate there, see above; the
+    # refined rotational term is a difference of rotated quaternions divided by dt and amplifies it)
+    tol = 1e-3 if precision == "double" and mode == 0 else 1e-9
     for k, name in enumerate(("refined KE translational", "refined KE rotational", "potential refinement")):
-        assert abs(ours[k] - theirs[k]) <= 1e-9 * abs(theirs[k]), (case, precision, mode, name, ours[k], theirs[k])
+        assert abs(ours[k] - theirs[k]) <= (tol if k == 1 else max(tol*1e-3, 1e-9)) * abs(theirs[k]), (case, precision, mode, name, ours[k], theirs[k])
     # (sanity: the refined kinetic energy is a small correction of the plain one for bodies)
     if case == "water":
         assert abs(ours[0] - plain[0]) < 0.05 * plain[0]
@@ -119,6 +128,8 @@ def test_refined_energies_match_committed_reference_cuda_vectors(path):
         s.part1_openmm(dt, *A.args())
         s.part2_openmm(dt, *A.args())
     ours = np.concatenate([s.refined_kinetic_openmm(dt, A.velm, PREC[precision]), [s.potential_refinement_openmm(dt, A.force, padded)]])
-    assert np.all(np.abs(ours - g["reference"]) <= 1e-9 * np.abs(g["reference"])), (ours, g["reference"])
+    loose = precision == "double" and mode == 0
+    tol = np.array([1e-6, 1e-3, 1e-6]) if loose else 1e-9
+    assert np.all(np.abs(ours - g["reference"]) <= tol * np.abs(g["reference"])), (ours, g["reference"])
     Ra, Va = A.host()
-    assert common.rel_inf(Ra, g["R_end"]) <= 1e-10 and common.rel_inf(Va, g["V_end"]) <= 1e-9
+    assert common.rel_inf(Ra, g["R_end"]) <= (2e-6 if loose else 1e-10) and common.rel_inf(Va, g["V_end"]) <= (2e-5 if loose else 1e-9)
