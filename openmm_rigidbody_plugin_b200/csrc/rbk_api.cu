@@ -80,7 +80,19 @@ struct rbk_system {
     rbk::SeriesControl* dSeriesCtl = nullptr;
     rbk::TileMaps tileMaps{};        // TMA descriptors of the one-warp-tile pipeline (valid when dev.tileMaps != NULL)
     int* dAtomLoc = nullptr;
+    int* dPluginLoc = nullptr;           // plugin-order atom -> caller slot, as last set (rbk_reorder_openmm moves forces with it)
     long long* dForcePacked = nullptr;   // scratch of rbk_reorder_openmm
+    // Storage order of the bodies / free atoms on the device.  When every body has the same size and the caller keeps each
+    // body's atoms together (what OpenMM's reorderAtoms does: whole molecules move), the device arrays are kept SORTED by
+    // the caller's slots, so that every kernel streams through the caller's arrays front to back however the caller has
+    // permuted its molecules (setLocation re-sorts after each reorder).  Identity otherwise.
+    std::vector<int> bodyOrder, bodyPos; // storage position -> plugin body, and its inverse
+    std::vector<int> freeOrder, freePos; // the same for the free atoms
+    int uniformBodySize = 0;             // > 0: every body has this many atoms
+    bool sorted = false;                 // storage order differs from plugin order
+    int* dGather = nullptr;              // scratch: gather indices of a re-sort
+    double* dScratch = nullptr;          // scratch: destination of a re-sort
+    size_t scratchDoubles = 0;
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
     double* dAtomMass = nullptr;     // body atoms, plugin order (GPU-side body build)
@@ -105,10 +117,11 @@ struct rbk_system {
     bool mirrorsLoaded = false;
     bool hostVelStale = false;       // the last rbk_execute_host call left the velocities on the device (V == NULL)
     std::vector<double> staging, oldPositions;
+    std::vector<int> locationTable;
 
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter); cudaFree(dSeriesCtl);
-        cudaFree(dAtomLoc); cudaFree(dForcePacked); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
+        cudaFree(dAtomLoc); cudaFree(dPluginLoc); cudaFree(dForcePacked); cudaFree(dGather); cudaFree(dScratch); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (side.stream) cudaStreamDestroy(side.stream);
         if (side.fork) cudaEventDestroy(side.fork);
@@ -245,9 +258,16 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(copyAsync(sys->dTileMeta, meta.data(), meta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(copyAsync(sys->dBodyTileMeta, bodyMeta.data(), bodyMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
-    RBK_CUDA(devAlloc(sys->dFreeInvMass, (size_t) std::max(nF, 1)));
+    RBK_CUDA(devAlloc(sys->dPluginLoc, (size_t) std::max(h.numActualAtoms, 1)));
+    sys->uniformBodySize = maxSize;
+    for (int b = 0; b < nB; b++) if (h.body[b].N != maxSize) sys->uniformBodySize = 0;
+    sys->bodyOrder.resize(nB); sys->bodyPos.resize(nB); sys->freeOrder.resize(nF); sys->freePos.resize(nF);
+    for (int b = 0; b < nB; b++) sys->bodyOrder[b] = sys->bodyPos[b] = b;
+    for (int k = 0; k < nF; k++) sys->freeOrder[k] = sys->freePos[k] = k;
+    sys->sorted = false;
+    RBK_CUDA(devAlloc(sys->dFreeInvMass, d.freeStride));
     RBK_CUDA(devAlloc(sys->dSavedPos, d.freeStride*3));
-    std::vector<double> atomMass((size_t) std::max(nA, 1), 0.0);
+    std::vector<double> atomMass(d.atomStride, 0.0);
     for (int a = 0; a < nA; a++) atomMass[a] = h.mass[h.atomIndex[(size_t) nF + a]];
     RBK_CUDA(devAlloc(sys->dAtomMass, atomMass.size()));
     RBK_CUDA(devAlloc(sys->dDofSum, 1));
@@ -287,15 +307,112 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     return RBK_OK;
 }
 
+// out[p][s*width + j] = in[p][src[s]*width + j] for every plane p: moves whole bodies (width = atoms per body, or 1)
+__global__ void gatherRowsKernel(double* __restrict__ out, const double* __restrict__ in, const int* __restrict__ src, int n, int width,
+                                 size_t stride, int planes) {
+    const long long i = (long long) blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= (long long) n*width) return;
+    const int s = (int) (i/width), j = (int) (i - (long long) s*width);
+    const size_t from = (size_t) src[s]*width + j;
+    for (int p = 0; p < planes; p++) out[p*stride + i] = in[p*stride + from];
+}
+
+// Re-sort one device array (planes x stride doubles) in place through the scratch buffer.
+int resortArray(rbk_system* sys, double* data, int n, int width, size_t stride, int planes, cudaStream_t st) {
+    if (data == nullptr || n == 0) return RBK_OK;
+    const size_t need = stride*planes;
+    if (sys->scratchDoubles < need) {
+        cudaFree(sys->dScratch);
+        sys->dScratch = nullptr;
+        sys->scratchDoubles = 0;
+        RBK_CUDA(devAlloc(sys->dScratch, need));
+        sys->scratchDoubles = need;
+    }
+    const long long items = (long long) n*width;
+    gatherRowsKernel<<<(unsigned) ((items + 255)/256), 256, 0, st>>>(sys->dScratch, data, sys->dGather, n, width, stride, planes);
+    RBK_CUDA(cudaGetLastError());
+    for (int p = 0; p < planes; p++)                   // (only the entries that exist: the planes' padding stays as it was)
+        RBK_CUDA(cudaMemcpyAsync(data + p*stride, sys->dScratch + p*stride, (size_t) items*sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return RBK_OK;
+}
+
+// Bring the device arrays from the current storage order to (bodyOrder, freeOrder).
+int resortStorage(rbk_system* sys, const std::vector<int>& bodyOrder, const std::vector<int>& freeOrder, cudaStream_t st) {
+    const DeviceSystem& d = sys->dev;
+    const int nB = d.numBodies, nF = d.numFree, N = sys->uniformBodySize;
+    if (!sys->dGather) RBK_CUDA(devAlloc(sys->dGather, (size_t) std::max(std::max(nB, nF), 1)));
+    std::vector<int> gather;
+    if (nB > 0 && bodyOrder != sys->bodyOrder) {
+        gather.resize(nB);
+        for (int s = 0; s < nB; s++) gather[s] = sys->bodyPos[bodyOrder[s]];          // where the body that goes to s is now
+        RBK_CUDA(copyAsync(sys->dGather, gather.data(), (size_t) nB*sizeof(int), cudaMemcpyHostToDevice, st));
+        if (int rc = resortArray(sys, sys->dState, nB, 1, d.bodyStride, rbk::NPLANES, st)) return rc;
+        if (int rc = resortArray(sys, sys->dDxyz, nB, N, d.atomStride, 3, st)) return rc;
+        if (int rc = resortArray(sys, sys->dAtomMass, nB, N, d.atomStride, 1, st)) return rc;
+        if (int rc = resortArray(sys, sys->refined.rdot, nB, 1, d.bodyStride, 3, st)) return rc;
+        if (int rc = resortArray(sys, sys->refined.qdot, nB, 1, d.bodyStride, 4, st)) return rc;
+        RBK_CUDA(cudaStreamSynchronize(st));                                            // `gather` is reused below
+        sys->bodyOrder = bodyOrder;
+        for (int s = 0; s < nB; s++) sys->bodyPos[bodyOrder[s]] = s;
+    }
+    if (nF > 0 && freeOrder != sys->freeOrder) {
+        gather.resize(nF);
+        for (int k = 0; k < nF; k++) gather[k] = sys->freePos[freeOrder[k]];
+        RBK_CUDA(copyAsync(sys->dGather, gather.data(), (size_t) nF*sizeof(int), cudaMemcpyHostToDevice, st));
+        if (int rc = resortArray(sys, sys->dFreeInvMass, nF, 1, d.freeStride, 1, st)) return rc;
+        if (int rc = resortArray(sys, sys->dSavedPos, nF, 1, d.freeStride, 3, st)) return rc;
+        if (int rc = resortArray(sys, sys->refined.posDot, nF, 1, d.freeStride, 3, st)) return rc;
+        RBK_CUDA(cudaStreamSynchronize(st));
+        sys->freeOrder = freeOrder;
+        for (int k = 0; k < nF; k++) sys->freePos[freeOrder[k]] = k;
+    }
+    sys->sorted = false;
+    for (int s = 0; s < nB && !sys->sorted; s++) sys->sorted = sys->bodyOrder[s] != s;
+    for (int k = 0; k < nF && !sys->sorted; k++) sys->sorted = sys->freeOrder[k] != k;
+    return RBK_OK;
+}
+
+// storage atom index (the order of dxyz, atomLoc, ...) of atom j of plugin body b / of plugin free atom k
+inline size_t storageBodyAtom(const rbk_system* sys, int b, int j) {
+    return sys->sorted ? (size_t) sys->bodyPos[b]*sys->uniformBodySize + j : (size_t) sys->host.body[b].loc + j;
+}
+
 int setLocation(rbk_system* sys, const int* location, cudaStream_t st) {
     const HostModel& h = sys->host;
-    const int n = h.numFree + h.numBodyAtoms;        // slots actually addressed by the kernels
+    const int nF = h.numFree, nB = h.numBodies, N = sys->uniformBodySize;
+    const int n = nF + h.numBodyAtoms;               // slots actually addressed by the kernels
     const int* src = location ? location : h.atomIndex.data();
-    bool identity = true;
-    for (int i = 0; i < n && identity; i++) identity = src[i] == i;
-    for (int i = 0; i < n && !identity; i++)
+    for (int i = 0; i < n; i++)
         if (src[i] < 0) return fail(RBK_EINVAL, "rbk_set_atom_location: negative location");
-    if (!identity) RBK_CUDA(copyAsync(sys->dAtomLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n > 0) RBK_CUDA(copyAsync(sys->dPluginLoc, src, (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
+    // Can the storage order follow the caller's?  Needs bodies of one size whose atoms the caller keeps together, in order.
+    bool sortable = nB == 0 || N > 0;
+    for (int b = 0; b < nB && sortable; b++) {
+        const int* a = src + nF + (size_t) b*N;
+        for (int j = 1; j < N && sortable; j++) sortable = a[j] == a[0] + j;
+    }
+    std::vector<int> bodyOrder(nB), freeOrder(nF);
+    for (int b = 0; b < nB; b++) bodyOrder[b] = b;
+    for (int k = 0; k < nF; k++) freeOrder[k] = k;
+    if (sortable) {
+        std::sort(bodyOrder.begin(), bodyOrder.end(), [&](int x, int y) { return src[nF + (size_t) x*N] < src[nF + (size_t) y*N]; });
+        std::sort(freeOrder.begin(), freeOrder.end(), [&](int x, int y) { return src[x] < src[y]; });
+    }
+    if (bodyOrder != sys->bodyOrder || freeOrder != sys->freeOrder)
+        if (int rc = resortStorage(sys, bodyOrder, freeOrder, st)) return rc;
+    // the table the kernels use: storage atom -> caller slot
+    std::vector<int>& table = sys->locationTable;
+    table.resize(n);
+    for (int k = 0; k < nF; k++) table[k] = src[sys->freeOrder[k]];
+    if (sys->sorted)
+        for (int s = 0; s < nB; s++) {
+            const int* a = src + nF + (size_t) sys->bodyOrder[s]*N;
+            for (int j = 0; j < N; j++) table[nF + (size_t) s*N + j] = a[j];
+        }
+    else for (int i = nF; i < n; i++) table[i] = src[i];
+    bool identity = true;
+    for (int i = 0; i < n && identity; i++) identity = table[i] == i;
+    if (!identity) RBK_CUDA(copyAsync(sys->dAtomLoc, table.data(), (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));             // `location` is the caller's
     sys->dev.atomLoc = identity ? nullptr : sys->dAtomLoc;
     return RBK_OK;
@@ -394,8 +511,9 @@ int pullHostModel(rbk_system* sys) {
     std::vector<double>& buf = sys->staging;
     buf.resize(std::max(buf.size(), std::max(ld*rbk::NPLANES, as*3)));
     RBK_CUDA(copySync(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost));
-    for (int b = 0; b < h.numBodies; b++) {
-        HostBody& B = h.body[b];
+    for (int pb = 0; pb < h.numBodies; pb++) {
+        HostBody& B = h.body[pb];
+        const size_t b = (size_t) sys->bodyPos[pb];
         for (int c = 0; c < 3; c++) {
             B.rcm[c] = buf[(rbk::PL_R + c)*ld + b];
             B.pcm[c] = buf[(rbk::PL_P + c)*ld + b];
@@ -418,8 +536,11 @@ int pullHostModel(rbk_system* sys) {
     }
     if (sys->hostStale) {                               // geometry was built on the device: the coordinates too
         RBK_CUDA(copySync(buf.data(), sys->dDxyz, as*3*sizeof(double), cudaMemcpyDeviceToHost));
-        for (int a = 0; a < h.numBodyAtoms; a++)
-            for (int c = 0; c < 3; c++) h.d[3*(size_t) a + c] = buf[c*as + a];
+        for (int pb = 0; pb < h.numBodies; pb++)
+            for (int j = 0; j < h.body[pb].N; j++) {
+                const size_t a = storageBodyAtom(sys, pb, j), ha = (size_t) h.body[pb].loc + j;
+                for (int c = 0; c < 3; c++) h.d[3*ha + c] = buf[c*as + a];
+            }
     }
     sys->hostStale = false;
     sys->deviceAhead = false;
@@ -494,8 +615,9 @@ int rbk_upload(rbk_system* sys, void* stream) {
     const size_t ld = d.bodyStride;
     std::vector<double>& buf = sys->staging;
     buf.assign(std::max(ld*rbk::NPLANES, d.atomStride*3), 0.0);
-    for (int b = 0; b < h.numBodies; b++) {
-        const HostBody& B = h.body[b];
+    for (int pb = 0; pb < h.numBodies; pb++) {
+        const HostBody& B = h.body[pb];
+        const size_t b = (size_t) sys->bodyPos[pb];           // storage position of plugin body pb
         for (int c = 0; c < 3; c++) {
             buf[(rbk::PL_R + c)*ld + b] = B.rcm[c];
             buf[(rbk::PL_P + c)*ld + b] = B.pcm[c];
@@ -513,8 +635,11 @@ int rbk_upload(rbk_system* sys, void* stream) {
     RBK_CUDA(copyAsync(sys->dState, buf.data(), ld*rbk::NPLANES*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     const size_t as = d.atomStride;
-    for (int a = 0; a < h.numBodyAtoms; a++)
-        for (int c = 0; c < 3; c++) buf[c*as + a] = h.d[3*(size_t) a + c];
+    for (int pb = 0; pb < h.numBodies; pb++)
+        for (int j = 0; j < h.body[pb].N; j++) {
+            const size_t a = storageBodyAtom(sys, pb, j), ha = (size_t) h.body[pb].loc + j;
+            for (int c = 0; c < 3; c++) buf[c*as + a] = h.d[3*ha + c];
+        }
     RBK_CUDA(copyAsync(sys->dDxyz, buf.data(), as*3*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     sys->uploaded = true;
@@ -793,12 +918,12 @@ int rbk_reorder_openmm(rbk_system* sys, const int* location, long long* force, i
     if (force && n > 0) {
         if (paddedNumAtoms <= 0) return fail(RBK_EINVAL, "rbk_reorder_openmm: paddedNumAtoms must be positive");
         if (!sys->dForcePacked) RBK_CUDA(devAlloc(sys->dForcePacked, (size_t) 3*n));
-        gatherForcesKernel<<<(n + 255)/256, 256, 0, st>>>(force, paddedNumAtoms, sys->dev.atomLoc, n, sys->dForcePacked);
+        gatherForcesKernel<<<(n + 255)/256, 256, 0, st>>>(force, paddedNumAtoms, sys->dPluginLoc, n, sys->dForcePacked);
         RBK_CUDA(cudaGetLastError());
     }
     if (int rc = setLocation(sys, location, st)) return rc;
     if (force && n > 0) {
-        scatterForcesKernel<<<(n + 255)/256, 256, 0, st>>>(force, paddedNumAtoms, sys->dev.atomLoc, n, sys->dForcePacked);
+        scatterForcesKernel<<<(n + 255)/256, 256, 0, st>>>(force, paddedNumAtoms, sys->dPluginLoc, n, sys->dForcePacked);
         RBK_CUDA(cudaGetLastError());
     }
     return RBK_OK;
@@ -923,18 +1048,19 @@ int rbk_download_bodies(rbk_system* sys, double* rcm, double* pcm, double* q, do
     buf.resize(std::max(buf.size(), ld*rbk::NPLANES));
     RBK_CUDA(copyAsync(buf.data(), sys->dState, ld*rbk::NPLANES*sizeof(double), cudaMemcpyDeviceToHost, st));
     RBK_CUDA(cudaStreamSynchronize(st));
-    for (int b = 0; b < sys->host.numBodies; b++) {
+    for (int b = 0; b < sys->host.numBodies; b++) {              // b: plugin order (the caller's); sb: where it is stored
+        const size_t sb = (size_t) sys->bodyPos[b];
         double qq[4], tt[3];
         for (int c = 0; c < 3; c++) {
-            if (rcm) rcm[3*b+c] = buf[(rbk::PL_R + c)*ld + b];
-            if (pcm) pcm[3*b+c] = buf[(rbk::PL_P + c)*ld + b];
-            if (force) force[3*b+c] = buf[(rbk::PL_F + c)*ld + b];
-            tt[c] = buf[(rbk::PL_TAU + c)*ld + b];
+            if (rcm) rcm[3*b+c] = buf[(rbk::PL_R + c)*ld + sb];
+            if (pcm) pcm[3*b+c] = buf[(rbk::PL_P + c)*ld + sb];
+            if (force) force[3*b+c] = buf[(rbk::PL_F + c)*ld + sb];
+            tt[c] = buf[(rbk::PL_TAU + c)*ld + sb];
         }
         for (int c = 0; c < 4; c++) {
-            qq[c] = buf[(rbk::PL_Q + c)*ld + b];
+            qq[c] = buf[(rbk::PL_Q + c)*ld + sb];
             if (q) q[4*b+c] = qq[c];
-            if (pi) pi[4*b+c] = buf[(rbk::PL_PI + c)*ld + b];
+            if (pi) pi[4*b+c] = buf[(rbk::PL_PI + c)*ld + sb];
         }
         if (torque) {                                   // C(q) tau, the form the reference stores
             torque[4*b+0] = -qq[1]*tt[0] - qq[2]*tt[1] - qq[3]*tt[2];

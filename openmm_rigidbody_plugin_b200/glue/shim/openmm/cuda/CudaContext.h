@@ -50,6 +50,7 @@ public:
     static std::string intToString(int value) { std::stringstream s; s << value; return s.str(); }
     // ---- shim-only helpers (what Context / ContextImpl / the platform's own kernels do in real OpenMM)
     void setReorderInterval(int steps) { reorderInterval = steps; }       // 0 = atoms are never reordered
+    void setReorderUnit(int atoms) { reorderUnit = atoms; }               // permute blocks of this many consecutive particles ("molecules")
     int getNumReorders() const { return numReorders; }
     void uploadPositions(const std::vector<Vec3>& positions);
     void uploadVelocities(const std::vector<Vec3>& velocities);
@@ -63,7 +64,7 @@ private:
     template <class T4> void get(CudaArray& array, std::vector<Vec3>& values);
     template <class T4> void permute(CudaArray& array, const std::vector<int>& oldSlotOfNew);
     const System& system;
-    int numAtoms, paddedNumAtoms, stepCount, reorderInterval, sinceReorder, numReorders;
+    int numAtoms, paddedNumAtoms, stepCount, reorderInterval, sinceReorder, numReorders, reorderUnit;
     bool useDouble, useMixed;
     double time;
     CudaArray *posq, *posqCorrection, *velm, *force;
@@ -77,7 +78,7 @@ private:
 #include "openmm/cuda/CudaIntegrationUtilities.h"
 namespace OpenMM {
 inline CudaContext::CudaContext(const System& system, const std::string& precision)
-    : system(system), numAtoms(system.getNumParticles()), stepCount(0), reorderInterval(0), sinceReorder(0), numReorders(0),
+    : system(system), numAtoms(system.getNumParticles()), stepCount(0), reorderInterval(0), sinceReorder(0), numReorders(0), reorderUnit(1),
       useDouble(precision == "double"), useMixed(precision == "mixed"), time(0.0), posqCorrection(NULL), pinned(NULL), rngState(88172645463325252ULL) {
     if (!useDouble && !useMixed && precision != "single") throw OpenMMException("Illegal value for CudaPrecision: " + precision);
     paddedNumAtoms = TileSize*((numAtoms + TileSize - 1)/TileSize);
@@ -187,11 +188,15 @@ inline void CudaContext::reorderAtoms() {
     numReorders++;
     std::vector<int> oldSlotOfNew(paddedNumAtoms);
     for (int s = 0; s < paddedNumAtoms; s++) oldSlotOfNew[s] = s;
-    for (int s = numAtoms - 1; s > 0; s--) {                 // Fisher-Yates over the real atoms (padding stays at the end)
+    const int unit = reorderUnit > 0 && numAtoms % reorderUnit == 0 ? reorderUnit : 1, units = numAtoms/unit;
+    std::vector<int> unitOrder(units);
+    for (int u = 0; u < units; u++) unitOrder[u] = u;
+    for (int u = units - 1; u > 0; u--) {                    // Fisher-Yates over the units (padding stays at the end)
         rngState ^= rngState << 13; rngState ^= rngState >> 7; rngState ^= rngState << 17;
-        const int r = (int) (rngState % (unsigned long long) (s + 1));
-        std::swap(oldSlotOfNew[s], oldSlotOfNew[r]);
+        std::swap(unitOrder[u], unitOrder[(int) (rngState % (unsigned long long) (u + 1))]);
     }
+    for (int u = 0; u < units; u++)
+        for (int j = 0; j < unit; j++) oldSlotOfNew[u*unit + j] = unitOrder[u]*unit + j;
     if (useDouble) permute<double4>(*posq, oldSlotOfNew); else permute<float4>(*posq, oldSlotOfNew);
     if (useMixed) permute<float4>(*posqCorrection, oldSlotOfNew);
     if (useDouble || useMixed) permute<double4>(*velm, oldSlotOfNew); else permute<float4>(*velm, oldSlotOfNew);

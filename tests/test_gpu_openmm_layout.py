@@ -165,13 +165,16 @@ def test_openmm_fused_stepping_and_reorder_vs_oracle(case, mode, precision):
     padded = ((n + 31) // 32) * 32 + 32
     s = build(sysd, mode)
     index = s.atom_index()
-    A = OpenMMArrays(sysd, rng.permutation(n), padded, precision, Fq)
+    # water: whole molecules are permuted, as OpenMM's reorderAtoms does (the handle re-sorts its bodies each time);
+    # the other cases: every atom on its own, the general gather path
+    permutation = (lambda: common.molecule_permutation(sysd["bodyIndices"], int(rng.integers(1 << 30)))) if case == "water" else (lambda: rng.permutation(n))
+    A = OpenMMArrays(sysd, permutation(), padded, precision, Fq)
     s.set_atom_location(A.order[index].astype(np.int32))
     s.part1_openmm(dt, *A.args())
     for k in range(steps - 1):
         s.part2_part1_openmm(dt, *A.args())
         if k % 2 == 1:
-            new_order = rng.permutation(n)
+            new_order = permutation()
             expect = torch.zeros_like(A.force)
             expect[:, torch.from_numpy(new_order).to(A.dev)] = A.force[:, torch.from_numpy(A.order).to(A.dev)]
             A.reorder(new_order)

@@ -32,6 +32,19 @@ def sysd_of(g):
     return {k: g[k] for k in ("bodyIndices", "masses", "R", "V", "F", "charges")}
 
 
+def insert_free_atoms(sysd, rng, every):
+    """a copy of a water system with one free atom (mass 35.45) inserted after every `every`-th molecule"""
+    n = sysd["masses"].shape[0]
+    after = np.arange(3 * every - 1, n, 3 * every)                 # insert behind these atoms
+    out = {}
+    k = after.shape[0]
+    extra = {"masses": np.full(k, 35.45), "bodyIndices": np.zeros(k, np.int32), "charges": np.full(k, -1.0),
+             "R": sysd["R"][after] + 0.15, "V": rng.standard_normal((k, 3)) * 0.26, "F": rng.standard_normal((k, 3)) * 300.0}
+    for key in ("masses", "bodyIndices", "charges", "R", "V", "F"):
+        out[key] = np.ascontiguousarray(np.insert(sysd[key], after + 1, extra[key], axis=0))
+    return out
+
+
 def compare_state(tag, s, ref_R, ref_V, ref_KE, ref_b=None, tol=REL_TIGHT):
     R, V, _ = s.get_state()
     eR, eV = rel_inf(R, ref_R), rel_inf(V, ref_V)
@@ -75,12 +88,17 @@ def test_golden_from_true_reference(name, layout, shuffle):
 
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("mode", [0, 1, 10])
-@pytest.mark.parametrize("layout", ["vec3", "soa"])
-def test_water_vs_oracle(mode, layout, fused):
-    """fused=True steps with rbk_part2_part1 (one pass per step) instead of separate part1/part2 launches."""
+@pytest.mark.parametrize("layout,shuffle", [("vec3", False), ("soa", False), ("vec3", "molecules")])
+def test_water_vs_oracle(mode, layout, shuffle, fused):
+    """fused=True steps with rbk_part2_part1 (one pass per step) instead of separate part1/part2 launches.
+    shuffle="molecules": the caller stores whole molecules in a permuted order (what OpenMM's reorderAtoms produces) - the
+    handle then keeps its own bodies sorted by the caller's slots and streams through the caller's arrays."""
     sysd = common.synth.water_box(20000, seed=100 + mode)
+    if shuffle:        # + free atoms (ions) sprinkled between the waters: they are re-sorted as well
+        rng = np.random.Generator(np.random.Philox(key=7))
+        sysd = insert_free_atoms(sysd, rng, every=37)
     o = CpuStepper("oracle", sysd["bodyIndices"], sysd["masses"], mode)
-    s = GpuStepper(sysd["bodyIndices"], sysd["masses"], mode, layout=layout)
+    s = GpuStepper(sysd["bodyIndices"], sysd["masses"], mode, layout=layout, shuffle=shuffle)
     s.fused = fused
     for st in (o, s):
         common.init_like_reference(st, sysd)
