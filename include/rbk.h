@@ -208,7 +208,9 @@ int rbk_reorder_openmm(rbk_system* sys, const int* location, long long* force, i
  *   rbk_free_delta_openmm      posDelta[i].xyz = (v + f invMass dt/2) dt for every free atom (mixed4 array:
  *                              float4 in single precision, double4 otherwise; .w untouched);
  *   <caller>                   integration.applyConstraints(tol) corrects posDelta;
- *   rbk_part1_delta_openmm     Part 1 in which free atoms move by posDelta instead of v dt;
+ *   rbk_part1_delta_openmm     Part 1 in which free atoms move by posDelta instead of v dt (the difference between the
+ *                              two, i.e. what the solver did, reaches the velocities in Part 2 as (x - savedPos)/dt -
+ *                              the Reference platform's arithmetic; the reference's CUDA kernel drops that term);
  *   <caller>                   computeVirtualSites, forces, rbk_part2_openmm, applyVelocityConstraints. */
 int rbk_free_delta_openmm(rbk_system* sys, double dt, const void* velm, const long long* force, int paddedNumAtoms,
                           int precision, void* posDelta, void* stream);

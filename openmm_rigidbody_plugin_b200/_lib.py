@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librbk.so")
+# RBK_LIB_PATH: load another build of the same library (A/B experiments with different compile-time settings)
+LIB_PATH = os.environ.get("RBK_LIB_PATH") or os.path.join(_HERE, "lib", "librbk.so")
 
 RBK_LAYOUT_VEC3 = 0
 RBK_LAYOUT_SOA = 1

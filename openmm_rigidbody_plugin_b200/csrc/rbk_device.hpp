@@ -34,7 +34,10 @@ constexpr int kLargeBodyTileAtoms = kBlock*kLargePerThread;    // atom-tile cap 
                                                                // arms are staged in shared memory by part2LargeKernel
 constexpr int kMaxTileAtoms = 8192;
 constexpr int kSplitAtomsPerBody = 8;  // mean body size above which part 1 runs as rotation kernel + atom kernel
-constexpr int kWarpTileAtoms = 128;    // atom capacity of the one-warp tiles (32 bodies of <= 4 atoms) of the step-fused kernel
+#ifndef RBK_WARP_TILE_ATOMS
+#define RBK_WARP_TILE_ATOMS 128
+#endif
+constexpr int kWarpTileAtoms = RBK_WARP_TILE_ATOMS;    // atom capacity of the one-warp tiles (32 bodies of <= 4 atoms) of the step-fused kernel
 constexpr int kFreePerBlock = 512;     // free atoms per CTA (4 per thread)
 
 struct TileMaps;

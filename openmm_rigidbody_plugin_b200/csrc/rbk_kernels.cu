@@ -787,8 +787,11 @@ __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k 
 // leave through the format-aware stores.  storeFT = false: interior step of step(n) - nothing reads F and tau before the
 // next Part 2 rewrites them, so they stay in registers (48 B per body-step less).
 // LADDER (one-warp exact-rotation tiles): the series order comes from the device-resident ladder control (SeriesControl).
+#ifndef RBK_WARP_TILE_CTAS
+#define RBK_WARP_TILE_CTAS 8            // resident one-warp CTAs per SM the register budget is cut for (254 registers at 8)
+#endif
 template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER, bool LADDER>
-__global__ void __launch_bounds__(BODIES, (STAGES == 2 ? 256 : 512)/BODIES)
+__global__ void __launch_bounds__(BODIES, BODIES == 32 ? RBK_WARP_TILE_CTAS : (STAGES == 2 ? 256 : 512)/BODIES)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force,
                  const __grid_constant__ TileMaps maps, const bool useMaps, const bool storeFT) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -1207,12 +1210,20 @@ __global__ void __launch_bounds__(256) freeDeltaKernel(const DeviceSystem S, con
     d3 v = loadAtom<false>(vel, gi);
     v = v + f*S.freeInvMass[k]*(0.5*dt);
     if (!CONSUME) {
-        storeAtom<false>(delta, gi, v*dt);
+        storeAtom<false>(delta, gi, d3{__dmul_rn(v.x, dt), __dmul_rn(v.y, dt), __dmul_rn(v.z, dt)});
         return;
     }
-    const d3 x = loadAtom<false>(pos, gi) + loadAtom<false>(delta, gi);
+    // x moves by the (constrained) displacement; savedPos remembers where the UNCONSTRAINED step would have put it, so that
+    // Part 2's (x - savedPos)/dt hands the constraint displacement to the velocity - the Reference platform's arithmetic
+    // (RigidBodySystem.cpp:172-176,196-197 with ReferenceConstraints::apply in between).  The reference's CUDA kernel saves
+    // the constrained position instead (rigidbodyintegrator.cu:303-312), which drops that term: constrained free atoms
+    // then lose the centripetal part of their velocity change every step and cool down.  Without a solver the two
+    // displacements are the same bits (round(v dt), no FMA contraction) and the term is exactly zero.
+    const d3 x0 = loadAtom<false>(pos, gi);
+    const d3 du = {__dmul_rn(v.x, dt), __dmul_rn(v.y, dt), __dmul_rn(v.z, dt)};
+    const d3 x = x0 + loadAtom<false>(delta, gi);
     storeAtom<false>(pos, gi, x);
-    storePlane3(S.savedPos + k, S.freeStride, asStored<false>(pos, x));
+    storePlane3(S.savedPos + k, S.freeStride, asStored<false>(pos, x0 + du));
     storeAtom<false>(vel, gi, v);
 }
 
@@ -1313,7 +1324,11 @@ cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, Ato
                              bool freeAtoms = true, bool storeFT = true) {
     typedef FusedSmem<BODIES, ATOMS, STAGES, GATHER> Smem;
     constexpr bool NATIVE = !GATHER;
+#ifdef RBK_EXPERIMENT_NOLADDER
+    constexpr bool LADDER = false;
+#else
     constexpr bool LADDER = EXACT && BODIES == 32;
+#endif
     auto kernel = part2Part1Kernel<EXACT, SMALL, NATIVE, BODIES, ATOMS, STAGES, P1ONLY, GATHER, LADDER>;
     static LaunchCache cache;
     int blocks = 0;                                            // persistent CTAs: one full wave, whatever fits

@@ -141,7 +141,8 @@ def test_hooks_that_change_nothing_equal_the_plain_call():
 @pytest.mark.parametrize("precision", [0, 1, 2])
 def test_device_delta_hooks_openmm_formats(precision):
     """delta pre-pass + part1_delta == plain part1 when the solver leaves posDelta alone, and a modified posDelta
-    moves the free atoms by exactly that displacement (savedPos follows, so part 2 adds no spurious velocity)."""
+    moves the free atoms by exactly that displacement; what the solver changed reaches the velocities in part 2 as
+    (x - savedPos)/dt, the Reference platform's arithmetic (RigidBodySystem.cpp:196-197)."""
     import torch
     from openmm_rigidbody_plugin_b200 import DeviceRigidBodySystem
     dev = torch.device("cuda:0")
@@ -194,7 +195,7 @@ def test_device_delta_hooks_openmm_formats(precision):
     assert common.rel_inf(positions(posqB, corrB).cpu().numpy(), positions(posqA, corrA).cpu().numpy()) <= tol
     assert torch.equal(velmB, velmA)
 
-    # a solver that shifts every free displacement: positions follow, and part 2 sees x == savedPos
+    # a solver that shifts every free displacement: positions follow, and part 2 turns the shift into velocity
     c, posqC, corrC, velmC, forceC = fresh()
     c.free_delta_openmm(dt, velmC, forceC, padded, precision, delta)
     fr = torch.from_numpy(free).to(dev)
@@ -209,7 +210,15 @@ def test_device_delta_hooks_openmm_formats(precision):
     forceC.zero_()
     c.part2_openmm(dt, posqC, corrC, velmC, forceC, padded, precision)
     torch.cuda.synchronize()
-    assert torch.equal(velmC[fr], vBefore[fr])                                    # (x - savedPos)/dt == 0, zero force
+    dv = (velmC[fr, :3] - vBefore[fr, :3]).double().cpu().numpy()                 # zero force: only (x - savedPos)/dt
+    assert np.allclose(dv, (shift.double()/dt).cpu().numpy()[None, :], rtol=0, atol=1e-3 if precision == 0 else 1e-9)
+    assert torch.equal(velmC[fr, 3], vBefore[fr, 3])
+    # ... and without a solver (b above) part 2 adds exactly nothing
+    vB = velmB.clone()
+    forceB.zero_()
+    b.part2_openmm(dt, posqB, corrB, velmB, forceB, padded, precision)
+    if precision != 0:
+        assert torch.equal(velmB[fr], vB[fr])
 
 
 def test_python_context_with_constrained_free_atoms():
