@@ -26,7 +26,7 @@ static void buildWaters(int nMol, unsigned seed0, System& system, vector<int>& b
             x = Vec3(x[0], cos(b)*x[1] - sin(b)*x[2], sin(b)*x[1] + cos(b)*x[2]);
             system.addParticle(mass[k]);
             positions.push_back(c + x);
-            velocities.push_back(Vec3(rnd(), rnd(), rnd())*(k == 0 ? 0.8 : 3.0));
+            velocities.push_back(Vec3(rnd(), rnd(), rnd())*(k == 0 ? 0.7 : 2.7));       // about 300 K
             bodyIndices.push_back(m + 1);
             charges.push_back(q[k]);
         }
