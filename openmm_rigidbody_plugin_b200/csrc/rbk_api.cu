@@ -78,6 +78,7 @@ struct rbk_system {
     int4* dWarpTileMeta = nullptr;
     int* dTileCounter = nullptr;
     rbk::SeriesControl* dSeriesCtl = nullptr;
+    int* hRung = nullptr;            // mapped pinned: the kernels' published rung, read by the launchers as a hint
     rbk::TileMaps tileMaps{};        // TMA descriptors of the one-warp-tile pipeline (valid when dev.tileMaps != NULL)
     int* dAtomLoc = nullptr;
     int* dPluginLoc = nullptr;           // plugin-order atom -> caller slot, as last set (rbk_reorder_openmm moves forces with it)
@@ -130,6 +131,7 @@ struct rbk_system {
         if (d2hStream) cudaStreamDestroy(d2hStream);
         for (cudaEvent_t e : {evStart, evForces, evPart1, evPositions}) if (e) cudaEventDestroy(e);
         if (hKinOut) cudaFreeHost(hKinOut);
+        if (hRung) cudaFreeHost(hRung);
     }
 };
 
@@ -299,6 +301,12 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(copyAsync(sys->dSeriesCtl, &ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     d.seriesCtl = sys->dSeriesCtl;
+    RBK_CUDA(cudaHostAlloc((void**) &sys->hRung, sizeof(int), cudaHostAllocMapped));
+    *sys->hRung = ctl0.rung;
+    RBK_CUDA(cudaHostGetDevicePointer((void**) &d.hostRungDevice, sys->hRung, 0));
+    d.hostRung = sys->hRung;
+    const char* full = std::getenv("RBK_FULL_LADDER");
+    d.fullLadderOnly = full && full[0] == '1';
     d.tileMaps = d.numWarpTiles > 0 && encodeTileMaps(sys) ? &sys->tileMaps : nullptr;
     d.atomLoc = nullptr;
     d.freeInvMass = sys->dFreeInvMass;

@@ -69,6 +69,9 @@ struct DeviceSystem {
     const TileMaps* tileMaps;    // HOST pointer (kernel-parameter copies are made at launch); NULL = no TMA tensor path
     const int* atomLoc;
     SeriesControl* seriesCtl;
+    const volatile int* hostRung;    // HOST pointer: the rung as the kernels last published it (mapped pinned memory) ...
+    int* hostRungDevice;             // ... and the device alias they write it through
+    int fullLadderOnly;              // RBK_FULL_LADDER=1: never use the lean rung-0 kernel (A/B measurements, tests)
     int* tileCounter;            // zero between launches: tiles claimed so far by the persistent step-fused kernel
     const double* freeInvMass;
     double* savedPos;

@@ -786,11 +786,15 @@ __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k 
 // per-thread 8-byte cp.async through the slot ring (raw words, converted where they are consumed); positions and velocities
 // leave through the format-aware stores.  storeFT = false: interior step of step(n) - nothing reads F and tau before the
 // next Part 2 rewrites them, so they stay in registers (48 B per body-step less).
-// LADDER (one-warp exact-rotation tiles): the series order comes from the device-resident ladder control (SeriesControl).
+// LADDER (one-warp exact-rotation tiles): 1 = the series order comes from the device-resident ladder control
+// (SeriesControl); 2 = the lowest rung only (order 11, 232 registers instead of 254 and one inlined series instead of three:
+// 4 % faster), launched when the host's copy of the rung says 0 - a hint that may be a few launches old, which is safe
+// because every rung is a complete algorithm (bodies that fail its check take the retry path) and this kernel keeps the
+// control block up to date like the full one; 0 = fixed order, no control block.
 #ifndef RBK_WARP_TILE_CTAS
 #define RBK_WARP_TILE_CTAS 8            // resident one-warp CTAs per SM the register budget is cut for (254 registers at 8)
 #endif
-template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER, bool LADDER>
+template <bool EXACT, bool SMALL, bool NATIVE, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER, int LADDER>
 __global__ void __launch_bounds__(BODIES, BODIES == 32 ? RBK_WARP_TILE_CTAS : (STAGES == 2 ? 256 : 512)/BODIES)
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force,
                  const __grid_constant__ TileMaps maps, const bool useMaps, const bool storeFT) {
@@ -800,7 +804,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     constexpr int kBlock = BODIES, kWarps = BODIES/32;          // shadow the file-level constants inside this kernel
     constexpr int RING = GATHER ? 4 : 3;
     static_assert(!LADDER || (EXACT && BODIES == 32), "the series ladder is wired for one-warp exact-rotation tiles");
-    const int rung = LADDER ? S.seriesCtl->rung : 0;
+    const int rung = LADDER == 1 ? S.seriesCtl->rung : 0;
     unsigned ladderFails = 0u, ladderLower = 0u;               // bodies of this CTA's tiles (warp-uniform)
     const int4* const tileMeta = BODIES == 32 ? S.warpTileMeta : S.tileMeta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1082,7 +1086,8 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     sm.acc[0][tid] = vcm.x; sm.acc[1][tid] = vcm.y; sm.acc[2][tid] = vcm.z;
                     sm.acc[3][tid] = om.x; sm.acc[4][tid] = om.y; sm.acc[5][tid] = om.z;
                 }
-                if (LADDER) bodyPart1Ladder(rung, dt, F, tau, invm, invI, r, p, q, pi, flags);
+                if (LADDER == 2) bodyPart1Ladder(0, dt, F, tau, invm, invI, r, p, q, pi, flags);
+                else if (LADDER == 1) bodyPart1Ladder(rung, dt, F, tau, invm, invI, r, p, q, pi, flags);
                 else bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
                 double* s = S.state + (size_t) (m.x + tid);
                 storePlane3(s + PL_R*ld, ld, r);
@@ -1137,6 +1142,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             if ((double) fails > 4.0e-4*n && rung < 2) next = rung + 1;
             else if (rung > 0 && (double) lower < 1.0e-4*n) next = rung - 1;
             c->rung = next;
+            *S.hostRungDevice = next;                          // the host's hint for its choice of kernel (mapped pinned memory)
             c->fails = 0u;
             c->lower = 0u;
             c->done = 0u;
@@ -1319,16 +1325,28 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     return overlap ? sideJoin(side, st) : cudaSuccess;
 }
 
+template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER, int LADDER>
+cudaError_t launchFusedLadder(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
+                              bool freeAtoms, bool storeFT);
+
 template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER>
 cudaError_t launchFusedShape(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
                              bool freeAtoms = true, bool storeFT = true) {
+#ifndef RBK_EXPERIMENT_NOLADDER
+    if (EXACT && BODIES == 32) {
+        // the host's copy of the rung (written by the kernels through mapped memory) picks the lean rung-0 kernel or the full ladder
+        if (*S.hostRung == 0 && !S.fullLadderOnly) return launchFusedLadder<EXACT, SMALL, BODIES, ATOMS, STAGES, P1ONLY, GATHER, EXACT && BODIES == 32 ? 2 : 0>(S, dt, pos, vel, force, st, freeAtoms, storeFT);
+        return launchFusedLadder<EXACT, SMALL, BODIES, ATOMS, STAGES, P1ONLY, GATHER, EXACT && BODIES == 32 ? 1 : 0>(S, dt, pos, vel, force, st, freeAtoms, storeFT);
+    }
+#endif
+    return launchFusedLadder<EXACT, SMALL, BODIES, ATOMS, STAGES, P1ONLY, GATHER, 0>(S, dt, pos, vel, force, st, freeAtoms, storeFT);
+}
+
+template <bool EXACT, bool SMALL, int BODIES, int ATOMS, int STAGES, bool P1ONLY, bool GATHER, int LADDER>
+cudaError_t launchFusedLadder(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st,
+                              bool freeAtoms, bool storeFT) {
     typedef FusedSmem<BODIES, ATOMS, STAGES, GATHER> Smem;
     constexpr bool NATIVE = !GATHER;
-#ifdef RBK_EXPERIMENT_NOLADDER
-    constexpr bool LADDER = false;
-#else
-    constexpr bool LADDER = EXACT && BODIES == 32;
-#endif
     auto kernel = part2Part1Kernel<EXACT, SMALL, NATIVE, BODIES, ATOMS, STAGES, P1ONLY, GATHER, LADDER>;
     static LaunchCache cache;
     int blocks = 0;                                            // persistent CTAs: one full wave, whatever fits

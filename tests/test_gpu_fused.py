@@ -78,3 +78,26 @@ def test_one_warp_tiles_ragged_ends_vs_oracle(n_mol, n_free):
         Rg, Vg, _ = g.get_state()
         assert common.rel_inf(Rg, Ro) < 1e-12 and common.rel_inf(Vg, Vo) < 1e-11, (fused, n_mol, n_free)
         assert common.rel_inf(g.kinetic(), o.kinetic()) < 1e-12
+
+
+def test_lean_rung0_kernel_and_full_ladder_kernel_give_the_same_bits(monkeypatch):
+    """Mode-0 water kernels: the launcher picks the lean order-11 kernel or the full-ladder kernel from a host-side copy
+    of the rung that may be a few launches old (csrc/rbk_kernels.cu, launchFusedShape).  Both run the same inlined
+    series on rung 0, so which one ran must not show in the results: RBK_FULL_LADDER=1 (never the lean kernel) against
+    the default, bit for bit - otherwise runs would not be reproducible."""
+    sysd = common.synth.water_box(5000, seed=96)
+    sysd = dict(sysd, F=sysd["F"] * 0.05)          # constant forces: keep them small, so that the bodies stay on rung 0
+    out = []
+    for full in ("0", "1"):
+        monkeypatch.setenv("RBK_FULL_LADDER", full)
+        for fused in (True, False):
+            s = GpuStepper(sysd["bodyIndices"], sysd["masses"], 0)
+            s.fused = fused
+            common.init_like_reference(s, sysd)
+            s.step(0.001, 8)
+            R, V, _ = s.get_state()
+            assert s.sys.series_order() == 11
+            out.append((R, V, s.kinetic()))
+            s.close()
+    assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1]) and np.array_equal(out[0][2], out[2][2])
+    assert np.array_equal(out[1][0], out[3][0]) and np.array_equal(out[1][1], out[3][1])
