@@ -135,9 +135,37 @@ def test_exact_vs_nosquish_converge(oracle_lib):
         assert np.max(np.abs(q1 - q2)) < 1e-7 and np.max(np.abs(p1 - p2)) < 1e-6 * np.max(np.abs(p2))
 
 
+def test_refined_energy_restatement_matches_the_reference_cuda_kernels():
+    """The reference computes refined kinetic energies / the potential-energy refinement only in its CUDA kernels
+    (rigidbodyintegrator.cu:433-469).  Those kernels, compiled in place and run on a B200 (baseline/ref_cuda,
+    tests/golden/make_golden_refcuda.py), produced tests/golden/refcuda_refined_*.npz: inputs, trajectory end point and
+    the three energies.  oracle/rb_oracle.c's restatement must reproduce them - this pins the oracle's last section.
+    (double precision + exact rotation: OpenMM defines USE_DOUBLE_PRECISION instead of USE_MIXED_PRECISION there and the
+    reference's elliptic.cu then runs with its single-precision tolerances - its own rotation is only ~1e-7 accurate.)"""
+    import glob
+    paths = sorted(glob.glob(os.path.join(common.GOLDEN_DIR, "refcuda_refined_*.npz")))
+    assert len(paths) >= 6
+    for path in paths:
+        g = dict(np.load(path))
+        sysd = {k: g[k] for k in ("bodyIndices", "masses", "R", "V", "F", "charges")}
+        sysd["F"] = np.round(sysd["F"] * 4294967296.0) / 4294967296.0            # OpenMM's fixed-point forces
+        mode, steps, dt = int(g["mode"]), int(g["steps"]), float(g["dt"])
+        o = CpuStepper("oracle", sysd["bodyIndices"], sysd["masses"], mode)
+        common.init_like_reference(o, sysd)
+        o.set_refined(True)
+        o.step(dt, steps)
+        ours = np.concatenate([o.refined_kinetic(dt), [o.potential_refinement(dt)]])
+        R, V, _ = o.get_state()
+        loose = str(g["precision"]) == "double" and mode == 0
+        tol = np.array([1e-9, 5e-6, 1e-6]) if loose else 1e-11
+        assert np.all(np.abs(ours - g["reference"]) <= tol * np.abs(g["reference"])), (path, ours, g["reference"])
+        assert common.rel_inf(R, g["R_end"]) <= (2e-6 if loose else 1e-12), path
+        assert common.rel_inf(V, g["V_end"]) <= (2e-5 if loose else 1e-10), path
+
+
 def test_refined_energy_restatement_is_a_shadow_energy():
-    """oracle/rb_oracle.c restates the reference's CUDA-only refined-energy diagnostics (PARITY UNPINNED: that platform
-    cannot run here).  What can be checked without it: for rigid bodies KE_refined + U + dU is conserved an order of
+    """oracle/rb_oracle.c restates the reference's CUDA-only refined-energy diagnostics (pinned above against the
+    reference's own kernels).  The physics behind them: for rigid bodies KE_refined + U + dU is conserved an order of
     magnitude better than KE + U, and better still at a smaller step (that is the purpose of the diagnostic); for free
     atoms the reference's factors (-1, 5, 2) give 4/3 of the kinetic energy in uniform motion (documented quirk)."""
     from oracle.checkers import CpuStepper
