@@ -541,19 +541,21 @@ def run_b200_arm(args):
     large = nB > 0 and nA > 8 * nB
     fused_ok = (not args.no_fuse) and nB > 0 and not large
     tf = None
-    if not args.no_fuse:  # event-time the one-pass call (part 2 of step k + part 1 of step k+1 = one step of work)
-        fe = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    if not args.no_fuse:  # event-time the one-pass call (part 2 of step k + part 1 of step k+1 = one step of work):
+        # ONE event pair around K back-to-back launches (an event between every two launches costs the GPU ~8 us of idle
+        # time per launch at this launch length, which is not the kernel's)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         A.part1(DT, cur[0])
+        f0.record(stream)
         for i in range(args.steps):
-            fe[i].record(stream)
             cur[0] ^= 1
             A.part2_part1(DT, cur[0])
-        fe[args.steps].record(stream)
+        f1.record(stream)
         cur[0] ^= 1
         A.part2(DT, cur[0])
         done[0] += args.steps + 1
         torch.cuda.synchronize()
-        tf = float(np.mean([fe[i].elapsed_time(fe[i+1]) for i in range(args.steps)]))
+        tf = f0.elapsed_time(f1) / args.steps
     clk = clocks.stop()
     ke = A.kinetic()
     if not np.isfinite(ke).all():
