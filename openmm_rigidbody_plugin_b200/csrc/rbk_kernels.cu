@@ -791,6 +791,9 @@ __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k 
 // 4 % faster), launched when the host's copy of the rung says 0 - a hint that may be a few launches old, which is safe
 // because every rung is a complete algorithm (bodies that fail its check take the retry path) and this kernel keeps the
 // control block up to date like the full one; 0 = fixed order, no control block.
+#ifndef RBK_UNROLL_TRIATOMIC
+#define RBK_UNROLL_TRIATOMIC 1          // tiles of three-atom bodies: force sums and atom outputs written out (ILP 3)
+#endif
 #ifndef RBK_WARP_TILE_CTAS
 #define RBK_WARP_TILE_CTAS 8            // resident one-warp CTAs per SM the register budget is cut for (254 registers at 8)
 #endif
@@ -1053,6 +1056,25 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     F = {T.f[tid], T.f[BODIES + tid], T.f[2*BODIES + tid]};
                     tau = {T.f[3*BODIES + tid], T.f[4*BODIES + tid], T.f[5*BODIES + tid]};
                 }
+                else if (SMALL && BODIES == 32 && m.w == 3*m.y && RBK_UNROLL_TRIATOMIC) {
+                    // a tile of three-atom bodies (water): the same sums, ((f0 + f1) + f2 like the loop below), with the three
+                    // atoms' rotations written out side by side - three independent dependency chains instead of one
+                    const int j = 3*tid;
+                    d3 f[3], delta[3];
+#pragma unroll
+                    for (int u = 0; u < 3; u++) {
+                        const d3 d = {T.d[0][j + u], T.d[1][j + u], T.d[2][j + u]};
+                        f[u] = {stagedForce<NATIVE>(force, T.f[3*(j + u)]), stagedForce<NATIVE>(force, T.f[3*(j + u) + 1]),
+                                stagedForce<NATIVE>(force, T.f[3*(j + u) + 2])};
+                        delta[u] = bodyToSpace(q, d);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; u++) {
+                        T.f[3*(j + u)] = delta[u].x; T.f[3*(j + u) + 1] = delta[u].y; T.f[3*(j + u) + 2] = delta[u].z;
+                    }
+                    F = (f[0] + f[1]) + f[2];
+                    tau = (cross(delta[0], f[0]) + cross(delta[1], f[1])) + cross(delta[2], f[2]);
+                }
                 else if (SMALL) {
                     const int j0 = T.loc[tid] - m.z, j1 = (tid + 1 < m.y ? T.loc[tid + 1] - m.z : m.w);
                     for (int j = j0; j < j1; j++) {
@@ -1108,7 +1130,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             __syncthreads();
 
             // ---- D: thread per atom: velocities at the end of this step, positions of the next
-            for (int j = tid; j < m.w; j += kBlock) {
+            auto atomOut = [&](int j) {
                 const int k = T.localBody[j + shift] & (BODIES - 1);      // index inside the 128-body atom tile -> this tile
                 const long long slot = GATHER ? (long long) slots[j] : atomSlot(S, S.numFree + m.z + j);
                 if (!P1ONLY) {
@@ -1121,7 +1143,12 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
                 const d3 r = {B[0][k], B[1][k], B[2][k]};
                 storeAtom<NATIVE>(pos, slot, atomPosition(r, q, d));
+            };
+            if (BODIES == 32 && m.w == 96 && RBK_UNROLL_TRIATOMIC) {      // a full tile of waters: three atoms per thread, written out
+#pragma unroll
+                for (int u = 0; u < 3; u++) atomOut(tid + 32*u);
             }
+            else for (int j = tid; j < m.w; j += kBlock) atomOut(j);
             __syncthreads();
             if (STAGES == 1) advance(it, 0);                   // the single stage is free again: request the next tile
         }
