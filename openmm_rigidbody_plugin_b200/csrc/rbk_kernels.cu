@@ -808,6 +808,9 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     constexpr int RING = GATHER ? 4 : 3;
     static_assert(!LADDER || (EXACT && BODIES == 32), "the series ladder is wired for one-warp exact-rotation tiles");
     const int rung = LADDER == 1 ? S.seriesCtl->rung : 0;
+    // three-atom tiles written out (ILP 3) where it measured faster: the lean fp64 kernel (0.1094 -> 0.1073 ms at 1 M waters);
+    // in the full-ladder kernel (255 registers) and the OpenMM-format kernel it measured slower (4 fs 0.199 -> 0.215, mixed 0.143 -> 0.149)
+    constexpr bool kTriatomic = RBK_UNROLL_TRIATOMIC && BODIES == 32 && NATIVE && LADDER == 2;
     unsigned ladderFails = 0u, ladderLower = 0u;               // bodies of this CTA's tiles (warp-uniform)
     const int4* const tileMeta = BODIES == 32 ? S.warpTileMeta : S.tileMeta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1056,7 +1059,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     F = {T.f[tid], T.f[BODIES + tid], T.f[2*BODIES + tid]};
                     tau = {T.f[3*BODIES + tid], T.f[4*BODIES + tid], T.f[5*BODIES + tid]};
                 }
-                else if (SMALL && BODIES == 32 && m.w == 3*m.y && RBK_UNROLL_TRIATOMIC) {
+                else if (SMALL && kTriatomic && m.w == 3*m.y) {
                     // a tile of three-atom bodies (water): the same sums, ((f0 + f1) + f2 like the loop below), with the three
                     // atoms' rotations written out side by side - three independent dependency chains instead of one
                     const int j = 3*tid;
@@ -1144,7 +1147,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                 const d3 r = {B[0][k], B[1][k], B[2][k]};
                 storeAtom<NATIVE>(pos, slot, atomPosition(r, q, d));
             };
-            if (BODIES == 32 && m.w == 96 && RBK_UNROLL_TRIATOMIC) {      // a full tile of waters: three atoms per thread, written out
+            if (kTriatomic && m.w == 96) {                     // a full tile of waters: three atoms per thread, written out
 #pragma unroll
                 for (int u = 0; u < 3; u++) atomOut(tid + 32*u);
             }
