@@ -96,7 +96,8 @@ struct rbk_system {
     size_t scratchDoubles = 0;
     double* dFreeInvMass = nullptr;
     double* dSavedPos = nullptr;
-    double* dAtomMass = nullptr;     // body atoms, plugin order (GPU-side body build)
+    double* dAtomMass = nullptr;     // body atoms, storage order (GPU-side body build)
+    double* dAtomInvMass = nullptr;  // 1/mass of the body atoms, storage order (full-sector velm stores)
     int* dDofSum = nullptr;
     bool hostStale = false;          // device build used: the host copy of the bodies is not current
     bool deviceAhead = false;        // a step has run since the last upload: r, q, p, pi, F, tau live on the device only
@@ -122,7 +123,7 @@ struct rbk_system {
 
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter); cudaFree(dSeriesCtl);
-        cudaFree(dAtomLoc); cudaFree(dPluginLoc); cudaFree(dForcePacked); cudaFree(dGather); cudaFree(dScratch); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dDofSum); cudaFree(dKinPartial);
+        cudaFree(dAtomLoc); cudaFree(dPluginLoc); cudaFree(dForcePacked); cudaFree(dGather); cudaFree(dScratch); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dAtomInvMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (side.stream) cudaStreamDestroy(side.stream);
         if (side.fork) cudaEventDestroy(side.fork);
@@ -274,6 +275,10 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(devAlloc(sys->dAtomMass, atomMass.size()));
     RBK_CUDA(devAlloc(sys->dDofSum, 1));
     RBK_CUDA(copyAsync(sys->dAtomMass, atomMass.data(), atomMass.size()*sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<double> atomInvMass(d.atomStride, 0.0);
+    for (int a = 0; a < nA; a++) atomInvMass[a] = atomMass[a] == 0.0 ? 0.0 : 1.0/atomMass[a];     // as CudaContext fills velm.w
+    RBK_CUDA(devAlloc(sys->dAtomInvMass, atomInvMass.size()));
+    RBK_CUDA(copyAsync(sys->dAtomInvMass, atomInvMass.data(), atomInvMass.size()*sizeof(double), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaMemsetAsync(sys->dState, 0, d.bodyStride*rbk::NPLANES*sizeof(double), st));
     RBK_CUDA(devAlloc(sys->dKinPartial, (size_t) 2*rbk::kKineticBlocks));
     RBK_CUDA(devAlloc(sys->dKinCounter, 1));
@@ -309,6 +314,8 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.fullLadderOnly = full && full[0] == '1';
     d.tileMaps = d.numWarpTiles > 0 && encodeTileMaps(sys) ? &sys->tileMaps : nullptr;
     d.atomLoc = nullptr;
+    const char* keepW = std::getenv("RBK_KEEP_VELM_W");        // =1: never write velm.w (partial-sector velocity stores; A/B runs)
+    d.atomInvMass = keepW && keepW[0] == '1' ? nullptr : sys->dAtomInvMass;
     d.freeInvMass = sys->dFreeInvMass;
     d.savedPos = sys->dSavedPos;
     sys->allocated = true;
@@ -357,6 +364,7 @@ int resortStorage(rbk_system* sys, const std::vector<int>& bodyOrder, const std:
         if (int rc = resortArray(sys, sys->dState, nB, 1, d.bodyStride, rbk::NPLANES, st)) return rc;
         if (int rc = resortArray(sys, sys->dDxyz, nB, N, d.atomStride, 3, st)) return rc;
         if (int rc = resortArray(sys, sys->dAtomMass, nB, N, d.atomStride, 1, st)) return rc;
+        if (int rc = resortArray(sys, sys->dAtomInvMass, nB, N, d.atomStride, 1, st)) return rc;
         if (int rc = resortArray(sys, sys->refined.rdot, nB, 1, d.bodyStride, 3, st)) return rc;
         if (int rc = resortArray(sys, sys->refined.qdot, nB, 1, d.bodyStride, 4, st)) return rc;
         RBK_CUDA(cudaStreamSynchronize(st));                                            // `gather` is reused below

@@ -73,6 +73,7 @@ struct DeviceSystem {
     int* hostRungDevice;             // ... and the device alias they write it through
     int fullLadderOnly;              // RBK_FULL_LADDER=1: never use the lean rung-0 kernel (A/B measurements, tests)
     int* tileCounter;            // zero between launches: tiles claimed so far by the persistent step-fused kernel
+    const double* atomInvMass;   // body atoms, storage order: 1/m as OpenMM stores it in velm.w (NULL: velm.w is never written)
     const double* freeInvMass;
     double* savedPos;
 };

@@ -711,11 +711,12 @@ constexpr int kSmallBody = 8;                       // bodies up to this size ar
 // BODIES = threads per CTA = bodies per tile, ATOMS = atom capacity of a tile.  Two shapes are instantiated:
 // <128, 512> (four warps share a tile) and <32, 128> (ONE warp per CTA, for bodies of <= 4 atoms such as water: no
 // CTA-wide barrier ever waits for a slower warp, eight independent CTAs per SM).
-template <int BODIES, int ATOMS>
+template <int BODIES, int ATOMS, bool GATHER>
 struct alignas(128) FusedStage {                    // 128-byte alignment: destination of TMA tensor copies
     double body[kFPlanes][BODIES];
     double f[3*ATOMS];                              // atom forces as xyzxyz..., later the arms delta = A^T(q) d
     double d[3][ATOMS];
+    double w[GATHER ? ATOMS : 2];                   // GATHER: the atoms' inverse masses (velm.w), see fullVelocity below
     int loc[BODIES + 4];
     unsigned char localBody[ATOMS + 32];
 };
@@ -724,7 +725,7 @@ struct alignas(128) FusedStage {                    // 128-byte alignment: desti
 // entry deeper for it.
 template <int BODIES, int ATOMS, int STAGES, bool GATHER>
 struct FusedSmem {
-    FusedStage<BODIES, ATOMS> stage[STAGES];
+    FusedStage<BODIES, ATOMS, GATHER> stage[STAGES];
     unsigned long long bar[2];                      // one mbarrier per stage (bulk-copy completion)
     double acc[6][BODIES];
     double head[BODIES/32][6];
@@ -802,7 +803,7 @@ __global__ void __launch_bounds__(BODIES, BODIES == 32 ? RBK_WARP_TILE_CTAS : (S
 part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force,
                  const __grid_constant__ TileMaps maps, const bool useMaps, const bool storeFT) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    typedef FusedStage<BODIES, ATOMS> Stage;
+    typedef FusedStage<BODIES, ATOMS, GATHER> Stage;
     FusedSmem<BODIES, ATOMS, STAGES, GATHER>& sm = *reinterpret_cast<FusedSmem<BODIES, ATOMS, STAGES, GATHER>*>(smemRaw);
     constexpr int kBlock = BODIES, kWarps = BODIES/32;          // shadow the file-level constants inside this kernel
     constexpr int RING = GATHER ? 4 : 3;
@@ -836,6 +837,11 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         else
             for (int j = tid; j < m.w; j += kBlock) dst[j] = S.numFree + m.z + j;
     };
+    // OpenMM's velm is mixed4 = (vx, vy, vz, 1/m).  Writing 24 of its 32 bytes makes every sector a partial write that the
+    // memory system completes with a fill read (32 B per atom); the handle knows the masses, so the one-pass kernel writes
+    // the whole double4 with w = 1/m - the same bits OpenMM put there (1.0/mass in double, constant for a Context's lifetime).
+    // posq.w (the charge) can change under updateParametersInContext and is never written.
+    const bool fullVelocity = GATHER && !P1ONLY && vel.fmt == FMT_REAL4_F64 && S.atomInvMass != nullptr;
     // GATHER: the tile's forces, one raw 8-byte word per component (double or fixed-point long long), through the slots
     auto requestForces = [&](int4 m, Stage& T, const int* slots) {
         for (int j = tid; j < m.w; j += kBlock) {
@@ -843,6 +849,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             cpAsync8(&T.f[3*j], fp);
             cpAsync8(&T.f[3*j + 1], fp + force.sc);
             cpAsync8(&T.f[3*j + 2], fp + 2*force.sc);
+            if (fullVelocity) cpAsync8(&T.w[j], S.atomInvMass + m.z + j);
         }
     };
     auto request = [&](int4 m, int st, const int* slots) {
@@ -902,6 +909,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             cpAsync8(&T.d[1][j], g + as);
             cpAsync8(&T.d[2][j], g + 2*as);
             if (!P1ONLY) {
+                if (fullVelocity) cpAsync8(&T.w[j], S.atomInvMass + m.z + j);
                 const double* fp = force.p + (GATHER ? (long long) slots[j] : atomSlot(S, S.numFree + m.z + j))*force.sa;
                 cpAsync8(&T.f[3*j], fp);
                 cpAsync8(&T.f[3*j + 1], fp + force.sc);
@@ -1140,7 +1148,13 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
                     const d3 delta = {T.f[3*j], T.f[3*j + 1], T.f[3*j + 2]};
                     const d3 vcm = {sm.acc[0][k], sm.acc[1][k], sm.acc[2][k]};
                     const d3 om = {sm.acc[3][k], sm.acc[4][k], sm.acc[5][k]};
-                    storeAtom<NATIVE>(vel, slot, atomVelocity(vcm, om, delta));
+                    const d3 vv = atomVelocity(vcm, om, delta);
+                    if (fullVelocity) {
+                        double2* out = reinterpret_cast<double2*>(vel.p + 4*slot);
+                        out[0] = make_double2(vv.x, vv.y);
+                        out[1] = make_double2(vv.z, T.w[GATHER ? j : 0]);
+                    }
+                    else storeAtom<NATIVE>(vel, slot, vv);
                 }
                 const d3 d = {T.d[0][j], T.d[1][j], T.d[2][j]};
                 const d4 q = {B[6][k], B[7][k], B[8][k], B[9][k]};
@@ -1200,7 +1214,12 @@ __global__ void __launch_bounds__(256) freeAtomsKernel(const DeviceSystem S, con
         storeAtom<NATIVE>(pos, gi, x);
         storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x));
     }
-    storeAtom<NATIVE>(vel, gi, v);
+    if (!NATIVE && vel.fmt == FMT_REAL4_F64 && S.atomInvMass != nullptr) {      // whole double4, w = 1/m (see part2Part1Kernel)
+        double2* out = reinterpret_cast<double2*>(vel.p + 4*gi);
+        out[0] = make_double2(v.x, v.y);
+        out[1] = make_double2(v.z, invm);
+    }
+    else storeAtom<NATIVE>(vel, gi, v);
 }
 
 #ifndef RBK_SIDE_FREE_THREADS
