@@ -163,7 +163,8 @@ int rbk_execute_host(rbk_system* sys, double dt, int steps, double* R, double* V
  * has free atoms (ReferenceRigidBodyKernels.cpp:92-104):
  *   constrainPositions(oldR, R, ...)  after Part 1 and before the forces - the place of
  *       ReferenceConstraints::apply(oldPos, R, invMass, tol) and ReferenceVirtualSites::computePositions;
- *       oldR holds the positions before the step, R the unconstrained new ones; return nonzero if R was changed
+ *       oldR holds the positions before the step OF THE FREE ATOMS (the only ones a solver may move; the entries of
+ *       rigid-body atoms and virtual sites are unspecified), R the unconstrained new ones; return nonzero if R was changed
  *       (it is then copied back to the device, where Part 2 turns R - savedPos into the velocity correction of
  *       RigidBodySystem.cpp:196-197);
  *   constrainVelocities(R, V, ...)    after Part 2 - ReferenceConstraints::applyToVelocities(R, V, invMass, tol);

@@ -1136,8 +1136,15 @@ int executeHost(rbk_system* sys, double dt, int steps, double* R, double* V, dou
         if (hostFlow) {
             // forces depend on the new positions: Part 1 -> positions to the host -> hooks -> forces to the device
             if (constrainPositions) {
+                // the solver needs the old positions of the atoms it may move - the free atoms; copying those alone keeps
+                // this O(numFree) instead of a host memcpy of every position per step (rigid-body atoms are outputs of the
+                // body state and never constrained, RigidBodySystem.cpp:107-113)
                 sys->oldPositions.resize((size_t) sys->host.numAtoms*3);
-                std::memcpy(sys->oldPositions.data(), R, bytes);
+                const int* freeAtom = sys->host.atomIndex.data();
+                for (int k = 0; k < sys->host.numFree; k++) {
+                    const size_t a = 3*(size_t) freeAtom[k];
+                    sys->oldPositions[a] = R[a]; sys->oldPositions[a + 1] = R[a + 1]; sys->oldPositions[a + 2] = R[a + 2];
+                }
             }
             if (i == 0 || !fuse) RBK_CUDA(stepPart1(sys, dt, p, v, fOld, nullptr, st));
             RBK_CUDA(copyAsync(R, sys->mPos, bytes, cudaMemcpyDeviceToHost, st));
