@@ -544,18 +544,23 @@ def run_b200_arm(args):
     if not args.no_fuse:  # event-time the one-pass call (part 2 of step k + part 1 of step k+1 = one step of work):
         # ONE event pair around K back-to-back launches (an event between every two launches costs the GPU ~8 us of idle
         # time per launch at this launch length, which is not the kernel's)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        A.part1(DT, cur[0])
-        f0.record(stream)
-        for i in range(args.steps):
+        # Three such passes, the fastest one counts (the host has to stay ahead of a 0.1 ms kernel; one pass in a few is
+        # caught by scheduler jitter on a busy box and then measures the host).
+        tf = None
+        for _ in range(3):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            A.part1(DT, cur[0])
+            f0.record(stream)
+            for i in range(args.steps):
+                cur[0] ^= 1
+                A.part2_part1(DT, cur[0])
+            f1.record(stream)
             cur[0] ^= 1
-            A.part2_part1(DT, cur[0])
-        f1.record(stream)
-        cur[0] ^= 1
-        A.part2(DT, cur[0])
-        done[0] += args.steps + 1
-        torch.cuda.synchronize()
-        tf = f0.elapsed_time(f1) / args.steps
+            A.part2(DT, cur[0])
+            done[0] += args.steps + 1
+            torch.cuda.synchronize()
+            t = f0.elapsed_time(f1) / args.steps
+            tf = t if tf is None else min(tf, t)
     clk = clocks.stop()
     ke = A.kinetic()
     if not np.isfinite(ke).all():
