@@ -310,8 +310,6 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     *sys->hRung = ctl0.rung;
     RBK_CUDA(cudaHostGetDevicePointer((void**) &d.hostRungDevice, sys->hRung, 0));
     d.hostRung = sys->hRung;
-    const char* p2w = std::getenv("RBK_PART2_WARP");          // experiment: CTAs per SM of the warp-per-body Part 2 (0 = staged kernel)
-    d.part2WarpCtasPerSM = p2w ? std::atoi(p2w) : 0;
     const char* full = std::getenv("RBK_FULL_LADDER");
     d.fullLadderOnly = full && full[0] == '1';
     d.tileMaps = d.numWarpTiles > 0 && encodeTileMaps(sys) ? &sys->tileMaps : nullptr;

@@ -71,7 +71,6 @@ struct DeviceSystem {
     SeriesControl* seriesCtl;
     const volatile int* hostRung;    // HOST pointer: the rung as the kernels last published it (mapped pinned memory) ...
     int* hostRungDevice;             // ... and the device alias they write it through
-    int part2WarpCtasPerSM;          // > 0: large-body Part 2 by the warp-per-body kernel with this many CTAs per SM (RBK_PART2_WARP)
     int fullLadderOnly;              // RBK_FULL_LADDER=1: never use the lean rung-0 kernel (A/B measurements, tests)
     int* tileCounter;            // zero between launches: tiles claimed so far by the persistent step-fused kernel
     const double* atomInvMass;   // body atoms, storage order: 1/m as OpenMM stores it in velm.w (NULL: velm.w is never written)

@@ -682,94 +682,8 @@ __global__ void RBK_P2L_REGCAP part2LargeKernel(const DeviceSystem S, const doub
     cpWait<0>();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Part 2 for large-body systems, second formulation: ONE WARP PER BODY, no shared memory, no CTA barrier.
-// Lane j takes atoms j, j+32, ... of the body (coalesced: a body's atoms are consecutive in the handle's arrays and - up to
-// interleaved free atoms - in the caller's), keeps the arms of its first two atoms in registers, a fixed five-level butterfly
-// finishes the six sums, every lane redoes the (short) second kick so that v_cm and omega need no broadcast, lane 0 writes the
-// body state, and the lanes turn their arms into velocities.  Bodies are dealt to the warps round-robin, so that at any time
-// the resident warps cover one contiguous window of the arrays.  Load latency is hidden by occupancy (no staging): ~60
-// registers, 8 warps per CTA.  Deterministic: fixed lane -> atom map, fixed butterfly.
-// ------------------------------------------------------------------------------------------------
-#ifndef RBK_P2W_MINBLOCKS
-#define RBK_P2W_MINBLOCKS 3
-#endif
-constexpr int kP2WThreads = 256;
-template <bool NATIVE>
-__global__ void __launch_bounds__(kP2WThreads, RBK_P2W_MINBLOCKS) part2WarpKernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel,
-                                                                  const AtomView force) {
-    const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x*(kP2WThreads/32) + (threadIdx.x >> 5), numWarps = gridDim.x*(kP2WThreads/32);
-    const size_t ld = S.bodyStride, as = S.atomStride;
-    const int* const atomLoc = S.atomLoc;
-    for (int b = warp; b < S.numBodies; b += numWarps) {
-        const int a0 = S.loc[b], N = S.loc[b + 1] - a0;
-        double* const s = S.state + (size_t) b;
-        const d4 q = loadPlane4(s + PL_Q*ld, ld);
-        d3 arm[2];
-        long long slot[2];
-        double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int j = lane + 32*u;
-            if (j < N) {
-                const int a = a0 + j;
-                slot[u] = atomLoc ? (long long) atomLoc[S.numFree + a] : (long long) (S.numFree + a);
-                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-                const d3 f = loadAtom<NATIVE>(force, slot[u]);
-                arm[u] = bodyToSpace(q, d);
-                const d3 t = cross(arm[u], f);
-                v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
-            }
-        }
-        for (int j = lane + 64; j < N; j += 32) {                // bodies of more than 64 atoms: the arms are recomputed below
-            const int a = a0 + j;
-            const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-            const d3 f = loadAtom<NATIVE>(force, atomSlot(S, S.numFree + a));
-            const d3 t = cross(bodyToSpace(q, d), f);
-            v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-            for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], off);
-        const d3 F = {v[0], v[1], v[2]}, tau = {v[3], v[4], v[5]};
-        d3 p = loadPlane3(s + PL_P*ld, ld);
-        d4 pi = loadPlane4(s + PL_PI*ld, ld);
-        const double invm = s[PL_INVM*ld];
-        const d3 invI = loadPlane3(s + PL_INVI*ld, ld);
-        d3 vcm, om;
-        bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
-        if (lane == 0) {
-            storePlane3(s + PL_P*ld, ld, p);
-            storePlane4(s + PL_PI*ld, ld, pi);
-            storePlane3(s + PL_F*ld, ld, F);
-            storePlane3(s + PL_TAU*ld, ld, tau);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++)
-            if (lane + 32*u < N) storeAtom<NATIVE>(vel, slot[u], atomVelocity(vcm, om, arm[u]));
-        for (int j = lane + 64; j < N; j += 32) {
-            const int a = a0 + j;
-            const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-            storeAtom<NATIVE>(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
-        }
-    }
-}
-
-template <bool NATIVE>
-cudaError_t launchPart2Warp(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    const int perCta = kP2WThreads/32;
-    int ctas = (S.numBodies + perCta - 1)/perCta;
-    const int cap = S.numSMs*S.part2WarpCtasPerSM;                 // one resident wave, bodies dealt round-robin
-    if (ctas > cap) ctas = cap;
-    part2WarpKernel<NATIVE><<<ctas, kP2WThreads, 0, st>>>(S, dt, pos, vel, force);
-    return cudaGetLastError();
-}
-
 template <bool NATIVE>
 cudaError_t launchPart2Large(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    if (S.part2WarpCtasPerSM > 0) return launchPart2Warp<NATIVE>(S, dt, pos, vel, force, st);
     const size_t smem = (size_t) part2LargeLayout(S.stageBodies).total;
     static LaunchCache cache;                                  // persistent CTAs: one full wave, whatever fits
     int blocks = 0;
