@@ -819,16 +819,14 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     const size_t ld = S.bodyStride, as = S.atomStride;
     const int numTiles = BODIES == 32 ? S.numWarpTiles : S.numTiles;
 
-    // A tile can arrive by bulk copies when every segment is 16-byte aligned and a multiple of 16 bytes long and the
-    // tile's forces are one contiguous Vec3 range (water tiles always are); otherwise per-thread cp.async.
-    const bool contiguousForces = S.atomLoc == nullptr && force.sa == 3 && force.sc == 1 && (reinterpret_cast<size_t>(force.p) & 15) == 0;
-    auto bulkOK = [&](int4 m) {
-        return (P1ONLY || GATHER || (contiguousForces && ((S.numFree + m.z) & 1) == 0)) && (m.x & 3) == 0 && (m.y & 3) == 0 &&
-               (m.z & 1) == 0 && (m.w & 1) == 0;
-    };
-    auto tensorOK = [&](int4 m) {
-        return BODIES == 32 && useMaps && (P1ONLY || GATHER || (contiguousForces && ((S.numFree + m.z) & 1) == 0 && (m.w & 1) == 0));
-    };
+    // The handle's own data of a tile (state planes, body-frame coordinates, offsets, body bytes) arrives by TMA: 2-D tensor
+    // boxes for one-warp tiles, else 1-D bulk copies when every segment is 16-byte aligned and a multiple of 16 bytes long,
+    // else per-thread cp.async.  The caller's forces ride along as ONE bulk copy when they are a contiguous, aligned Vec3 range
+    // (water tiles in plugin order always are); otherwise (SoA planes, odd offsets, GATHER) by per-thread 8-byte cp.async.
+    const bool contiguousForces = !GATHER && S.atomLoc == nullptr && force.sa == 3 && force.sc == 1 && (reinterpret_cast<size_t>(force.p) & 15) == 0;
+    auto forcesBulk = [&](int4 m) { return contiguousForces && ((S.numFree + m.z) & 1) == 0 && (m.w & 1) == 0; };
+    auto bulkOK = [&](int4 m) { return (m.x & 3) == 0 && (m.y & 3) == 0 && (m.z & 1) == 0 && (m.w & 1) == 0; };
+    auto tensorOK = [&](int4 m) { return BODIES == 32 && useMaps; };
     // GATHER: array slots of a tile's atoms into ring entry `ring` (two tiles ahead of the data)
     auto requestSlots = [&](int4 m, int ring) {
         int* dst = sm.slot[GATHER ? ring : 0];
@@ -845,7 +843,7 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
     // GATHER: the tile's forces, one raw 8-byte word per component (double or fixed-point long long), through the slots
     auto requestForces = [&](int4 m, Stage& T, const int* slots) {
         for (int j = tid; j < m.w; j += kBlock) {
-            const double* fp = force.p + (long long) slots[j]*force.sa;
+            const double* fp = force.p + (GATHER ? (long long) slots[j] : atomSlot(S, S.numFree + m.z + j))*force.sa;
             cpAsync8(&T.f[3*j], fp);
             cpAsync8(&T.f[3*j + 1], fp + force.sc);
             cpAsync8(&T.f[3*j + 2], fp + 2*force.sc);
@@ -863,20 +861,22 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
             if (tid == 0) {
                 fenceProxyAsync();
                 constexpr unsigned boxBytes = (P1ONLY ? 24u : 18u)*BODIES*8u + 3u*ATOMS*8u + 4u*BODIES;
-                mbarExpectTx(&sm.bar[st], boxBytes + (P1ONLY || GATHER ? 0u : 24u*m.w) + lbBytes);
+                const bool fBulk = !P1ONLY && forcesBulk(m);
+                mbarExpectTx(&sm.bar[st], boxBytes + (fBulk ? 24u*m.w : 0u) + lbBytes);
                 tmaLoad2D(&T.body[0][0], P1ONLY ? &maps.state24 : &maps.state18, m.x, 0, &sm.bar[st]);
                 tmaLoad2D(&T.d[0][0], &maps.dxyz, m.z, 0, &sm.bar[st]);
                 bulkCopy(&T.loc[0], S.loc + m.x, 4u*BODIES, &sm.bar[st]);
-                if (!P1ONLY && !GATHER) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
+                if (fBulk) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
                 bulkCopy(&T.localBody[0], S.localBody + lbFirst, lbBytes, &sm.bar[st]);
             }
-            if (GATHER && !P1ONLY) requestForces(m, T, slots);
+            if (!P1ONLY && !forcesBulk(m)) requestForces(m, T, slots);
             return;
         }
         if (bulkOK(m)) {
             if (tid == 0) {
                 fenceProxyAsync();                             // earlier generic-proxy writes to this stage are ordered first
-                mbarExpectTx(&sm.bar[st], (unsigned) ((kFPlanes + (P1ONLY ? 6 : 0))*8*m.y + 4*m.y + (P1ONLY || GATHER ? 24 : 48)*m.w) + lbBytes);
+                const bool fBulk = !P1ONLY && forcesBulk(m);
+                mbarExpectTx(&sm.bar[st], (unsigned) ((kFPlanes + (P1ONLY ? 6 : 0))*8*m.y + 4*m.y + (fBulk ? 48 : 24)*m.w) + lbBytes);
                 const double* g = S.state + (size_t) m.x;
 #pragma unroll
                 for (int k = 0; k < kFPlanes; k++) bulkCopy(&T.body[k][0], g + fusedGlobalPlane(k)*ld, 8u*m.y, &sm.bar[st]);
@@ -887,10 +887,10 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
 #pragma unroll
                     for (int k = 0; k < 6; k++) bulkCopy(&T.f[k*BODIES], g + ((int) PL_F + k)*ld, 8u*m.y, &sm.bar[st]);
                 }
-                else if (!GATHER) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
+                else if (fBulk) bulkCopy(&T.f[0], force.p + 3*(size_t) (S.numFree + m.z), 24u*m.w, &sm.bar[st]);
                 bulkCopy(&T.localBody[0], S.localBody + lbFirst, lbBytes, &sm.bar[st]);
             }
-            if (GATHER && !P1ONLY) requestForces(m, T, slots);
+            if (!P1ONLY && !forcesBulk(m)) requestForces(m, T, slots);
             return;
         }
         if (tid < m.y) {
