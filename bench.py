@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (baseline/ref_cuda)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dt-fs", type=float, default=1.0, help="time step in fs (BASELINE: 1 fs)")
+    ap.add_argument("--free-per-body", type=float, default=2.5, help="mixed workload: free atoms per rigid body (BASELINE config 4: 2.5)")
     return ap.parse_args()
 
 
@@ -77,8 +78,9 @@ def make_workload(args, seed):
         name = f"{args.molecules} rigid TIP3P waters ({3*args.molecules} atoms), mode {args.mode}, integrator-only, fixed synthetic forces ({'sign alternating per step' if args.forces == 'alternating' else 'constant'})"
     else:
         nb = max(args.molecules // 5, 1)
-        sysd = synth.mixed_system(nb, int(2.5 * nb), seed=seed)
-        name = f"mixed: {nb} rigid bodies of 3-60 atoms + {int(2.5*nb)} free atoms, mode {args.mode}"
+        nf = int(args.free_per_body * nb)
+        sysd = synth.mixed_system(nb, nf, seed=seed)
+        name = f"mixed: {nb} rigid bodies of 3-60 atoms + {nf} free atoms, mode {args.mode}"
     return sysd, name
 
 
@@ -582,11 +584,10 @@ def run_b200_arm(args):
             raise SystemExit(f"bench.py: the timed kernels disagree with the CPU oracle: {parity}")
 
     value = world * nB * args.steps / (ms * 1e-3)
-    # kernels launched inside the timed region (librbk's launch structure, rbk_kernels.cu launchPart1 / launchPart2 /
-    # launchPart2Part1): free atoms have their own launch; large bodies split part 1 into rotation + position kernels
-    fr = 1 if nF > 0 else 0
-    per_p1, per_p2 = fr + (2 if large else 1 if nB else 0), fr + (1 if nB else 0)
-    per_pp = fr + (3 if large else 1 if nB else 0)
+    # kernels launched inside the timed region: the library's own count per call (rbk_debug_launches_per_call; launch
+    # structure in rbk_kernels.cu launchPart1 / launchPart2 / launchPart2Part1: large bodies split part 1 into rotation +
+    # position kernels, free atoms have their own launch unless they ride along in the large-body Part 2 kernel)
+    per_p1, per_p2, per_pp = system.launches_per_call()
     gpu_launches = args.steps * (per_p1 + per_p2) if args.no_fuse else per_p1 + (args.steps - 1) * per_pp + per_p2
 
     # ---- roofline.  Two byte counts per launch, both stated:
@@ -618,7 +619,7 @@ def run_b200_arm(args):
     else:
         dom = ("part1", p1_bytes, t1) if t1 >= t2 else ("part2", p2_bytes, t2)
     ach = dom[1] / (dom[2] * 1e-3) / 1e9
-    kernel_name = {"part2Part1": "rbk::part2Part1Kernel" if not large else "rbk_part2_part1 call = part2LargeKernel + part1Kernel (rotation) + atomPositionKernel + freeAtomsKernel<3>",
+    kernel_name = {"part2Part1": "rbk::part2Part1Kernel" if not large else "rbk_part2_part1 call = part2LargeKernel (bodies' Part 2 + the free atoms' Part 2 and Part 1 riding along) + part1Kernel (rotation) + atomPositionKernel",
                    "part1": "rbk_part1 call", "part2": "rbk_part2 call"}[dom[0]]
     traffic = ncu_traffic(f"{dom[0]}_mode{args.mode}_{args.workload}{args.molecules}_{args.layout}{'_shuffle_' + args.shuffle if args.shuffle else ''}")
     work_ach = (work1 + work2) / (dom[2] * 1e-3) / 1e9 if tf is not None else None

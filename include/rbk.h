@@ -45,6 +45,9 @@ int         rbk_debug_copy_counters(const rbk_system* sys, long long* out);
 /* Diagnostics: the Taylor order the mode-0 water kernels will use at their next launch (11, 13 or 16; DESIGN.md, "series
  * ladder").  The choice is made on the device from the previous launch's convergence statistics. */
 int         rbk_debug_series_order(rbk_system* sys, int* out, void* stream);
+/* Diagnostics: kernel launches one call makes on the current system with fp64 arrays - out[3] = rbk_part1, rbk_part2,
+ * rbk_part2_part1 (launch structure: DESIGN.md section 4; benchmarks report their launch counts from this). */
+int         rbk_debug_launches_per_call(const rbk_system* sys, int* out);
 
 /* ---- host model -------------------------------------------------------------------------- */
 

@@ -24,6 +24,7 @@ SIGNATURES = {
     "rbk_last_error": (C.c_char_p, []),
     "rbk_debug_series_order": (C.c_int, [C.c_void_p, _ip, C.c_void_p]),
     "rbk_debug_copy_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
+    "rbk_debug_launches_per_call": (C.c_int, [C.c_void_p, _ip]),
     "rbk_create": (C.c_int, [C.c_int, _ip, _dp, C.c_char_p, C.c_int, _ip, C.c_int, C.POINTER(C.c_void_p)]),
     "rbk_destroy": (None, [C.c_void_p]),
     "rbk_get_counts": (C.c_int, [C.c_void_p, _ip]),

@@ -81,6 +81,7 @@ struct rbk_system {
     int* hRung = nullptr;            // mapped pinned: the kernels' published rung, read by the launchers as a hint
     rbk::TileMaps tileMaps{};        // TMA descriptors of the one-warp-tile pipeline (valid when dev.tileMaps != NULL)
     int* dAtomLoc = nullptr;
+    int* dBodyRun = nullptr;             // caller slot of each body's first atom (storage order), valid when dev.bodyRun != NULL
     int* dPluginLoc = nullptr;           // plugin-order atom -> caller slot, as last set (rbk_reorder_openmm moves forces with it)
     long long* dForcePacked = nullptr;   // scratch of rbk_reorder_openmm
     // Storage order of the bodies / free atoms on the device.  When every body has the same size and the caller keeps each
@@ -123,7 +124,7 @@ struct rbk_system {
 
     ~rbk_system() {
         cudaFree(dState); cudaFree(dDxyz); cudaFree(dLocalBody); cudaFree(dLoc); cudaFree(dTileMeta); cudaFree(dBodyTileMeta); cudaFree(dWarpTileMeta); cudaFree(dTileCounter); cudaFree(dSeriesCtl);
-        cudaFree(dAtomLoc); cudaFree(dPluginLoc); cudaFree(dForcePacked); cudaFree(dGather); cudaFree(dScratch); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dAtomInvMass); cudaFree(dDofSum); cudaFree(dKinPartial);
+        cudaFree(dAtomLoc); cudaFree(dBodyRun); cudaFree(dPluginLoc); cudaFree(dForcePacked); cudaFree(dGather); cudaFree(dScratch); cudaFree(dFreeInvMass); cudaFree(dSavedPos); cudaFree(dAtomMass); cudaFree(dAtomInvMass); cudaFree(dDofSum); cudaFree(dKinPartial);
         cudaFree(dKinCounter); cudaFree(dKinOut); cudaFree(refined.rdot); cudaFree(refined.qdot); cudaFree(refined.posDot); cudaFree(mPos); cudaFree(mVel); cudaFree(mForce); cudaFree(mForce2);
         if (side.stream) cudaStreamDestroy(side.stream);
         if (side.fork) cudaEventDestroy(side.fork);
@@ -190,12 +191,12 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     }
     loc[nB] = nB ? h.body[nB-1].loc + h.body[nB-1].N : 0;
     // atom tiles (define the per-atom body byte) and body tiles
-    auto cut = [&](int atomCap, bool fillLocal) {
+    auto cut = [&](int atomCap, int bodyCap, bool fillLocal) {
         std::vector<int4> out;
         int first = 0, inTile = 0, atomsInTile = 0;
         for (int b = 0; b < nB; b++) {
             const int n = h.body[b].N;
-            if (inTile > 0 && (inTile == rbk::kBlock || atomsInTile + n > atomCap)) {
+            if (inTile > 0 && (inTile == bodyCap || atomsInTile + n > atomCap)) {
                 out.push_back(make_int4(first, inTile, loc[first], atomsInTile));
                 first = b;
                 inTile = 0;
@@ -211,7 +212,8 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     // large bodies: smaller atom tiles keep a tile's coordinates L1-resident between the two atom phases of part 2
     const bool large = nB > 0 && (long long) nA > (long long) rbk::kSplitAtomsPerBody*nB;
     const int atomCap = large ? rbk::kLargeBodyTileAtoms : rbk::kTileAtoms;
-    std::vector<int4> meta = cut(atomCap, true), bodyMeta = cut(rbk::kMaxTileAtoms, false);
+    // (large bodies: at most kBlock - 8 bodies per atom tile - part2LargeKernel keeps a few threads for the tile's plane copies)
+    std::vector<int4> meta = cut(atomCap, large ? rbk::kBlock - 8 : rbk::kBlock, true), bodyMeta = cut(rbk::kMaxTileAtoms, rbk::kBlock, false);
 
     d.numBodies = nB;
     d.numFree = nF;
@@ -262,6 +264,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(copyAsync(sys->dBodyTileMeta, bodyMeta.data(), bodyMeta.size()*sizeof(int4), cudaMemcpyHostToDevice, st));
     RBK_CUDA(devAlloc(sys->dAtomLoc, (size_t) std::max(h.numActualAtoms, 1)));
     RBK_CUDA(devAlloc(sys->dPluginLoc, (size_t) std::max(h.numActualAtoms, 1)));
+    RBK_CUDA(devAlloc(sys->dBodyRun, (size_t) std::max(nB, 1)));
     sys->uniformBodySize = maxSize;
     for (int b = 0; b < nB; b++) if (h.body[b].N != maxSize) sys->uniformBodySize = 0;
     sys->bodyOrder.resize(nB); sys->bodyPos.resize(nB); sys->freeOrder.resize(nF); sys->freePos.resize(nF);
@@ -314,6 +317,12 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     d.fullLadderOnly = full && full[0] == '1';
     d.tileMaps = d.numWarpTiles > 0 && encodeTileMaps(sys) ? &sys->tileMaps : nullptr;
     d.atomLoc = nullptr;
+    d.bodyRun = nullptr;
+    d.numSlots = nF + nA;
+    const char* noBulk = std::getenv("RBK_NO_BULK_PART2");
+    d.noBulkPart2 = noBulk && noBulk[0] == '1';
+    const char* noRide = std::getenv("RBK_NO_FREE_RIDE");
+    d.noFreeRide = noRide && noRide[0] == '1';
     const char* keepW = std::getenv("RBK_KEEP_VELM_W");        // =1: never write velm.w (partial-sector velocity stores; A/B runs)
     d.atomInvMass = keepW && keepW[0] == '1' ? nullptr : sys->dAtomInvMass;
     d.freeInvMass = sys->dFreeInvMass;
@@ -429,8 +438,22 @@ int setLocation(rbk_system* sys, const int* location, cudaStream_t st) {
     bool identity = true;
     for (int i = 0; i < n && identity; i++) identity = table[i] == i;
     if (!identity) RBK_CUDA(copyAsync(sys->dAtomLoc, table.data(), (size_t) n*sizeof(int), cudaMemcpyHostToDevice, st));
+    // bodies whose atoms the caller keeps in consecutive slots, in order: large-body Part 2 fetches each body's forces as one run
+    std::vector<int> run(nB);
+    bool runs = sys->dev.splitPart1 != 0;            // (only that kernel uses the table)
+    int numSlots = 0;
+    for (int i = 0; i < n; i++) numSlots = std::max(numSlots, table[i] + 1);
+    for (int s = 0; s < nB && runs; s++) {
+        const HostBody& hb = h.body[sys->sorted ? sys->bodyOrder[s] : s];
+        const int* a = table.data() + storageBodyAtom(sys, sys->sorted ? sys->bodyOrder[s] : s, 0) + nF;
+        run[s] = a[0];
+        for (int j = 1; j < hb.N && runs; j++) runs = a[j] == a[0] + j;
+    }
+    if (runs && nB > 0) RBK_CUDA(copyAsync(sys->dBodyRun, run.data(), (size_t) nB*sizeof(int), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));             // `location` is the caller's
     sys->dev.atomLoc = identity ? nullptr : sys->dAtomLoc;
+    sys->dev.bodyRun = runs && nB > 0 ? sys->dBodyRun : nullptr;
+    sys->dev.numSlots = numSlots;
     return RBK_OK;
 }
 
@@ -466,6 +489,12 @@ int rbk_debug_series_order(rbk_system* sys, int* out, void* stream) {
 int rbk_debug_copy_counters(const rbk_system*, long long* out) {
     if (!out) return fail(RBK_EINVAL, "rbk_debug_copy_counters: NULL argument");
     for (int i = 0; i < 4; i++) out[i] = g_copies[i].load();
+    return RBK_OK;
+}
+int rbk_debug_launches_per_call(const rbk_system* sys, int* out) {
+    if (!sys || !out) return fail(RBK_EINVAL, "rbk_debug_launches_per_call: NULL argument");
+    if (!sys->allocated) return fail(RBK_ESTATE, "rbk_debug_launches_per_call: call rbk_upload first");
+    rbk::launchesPerCall(sys->dev, out);
     return RBK_OK;
 }
 const char* rbk_last_error(void) { return g_error.c_str(); }
@@ -710,6 +739,8 @@ namespace {
 // The handle's second stream (large-body systems with free atoms only; created on first use, NULL when it cannot be)
 const rbk::SideStream* sideStream(rbk_system* sys) {
     if (!(sys->dev.splitPart1 && sys->dev.numFree > 0 && sys->dev.numTiles > 0)) return nullptr;
+    static const bool disabled = [] { const char* e = std::getenv("RBK_NO_SIDE_STREAM"); return e && e[0] == '1'; }();
+    if (disabled) return nullptr;                            // A/B measurements: free atoms in the caller's stream, before the body kernels
     if (!sys->side.stream) {
         rbk::SideStream s{nullptr, nullptr, nullptr};
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -85,6 +85,26 @@ template <bool NATIVE> __device__ __forceinline__ d3 asStored(const AtomView& A,
     if (A.fmt == FMT_REAL4_F32) return {(double) (float) v.x, (double) (float) v.y, (double) (float) v.z};
     return v;
 }
+// Bring atom i's entry of A towards the SM (L2 prefetch of the sectors it occupies) - issued a tile ahead of the loads by kernels
+// that cannot keep those loads in flight themselves.
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetchAtom(const AtomView& A, long long i) {
+    if (A.fmt == FMT_F64) {
+        const double* p = A.p + i*A.sa;
+        if (A.sc == 1) { prefetchL2(p); prefetchL2(p + 2); }                  // 24 bytes, may straddle two sectors
+        else { prefetchL2(p); prefetchL2(p + A.sc); prefetchL2(p + 2*A.sc); }
+    }
+    else if (A.fmt == FMT_POSQ_MIXED) {
+        prefetchL2(reinterpret_cast<const float4*>(A.p) + i);
+        prefetchL2(reinterpret_cast<const float4*>(A.aux) + i);
+    }
+    else if (A.fmt == FMT_REAL4_F64) prefetchL2(A.p + 4*i);
+    else if (A.fmt == FMT_REAL4_F32) prefetchL2(reinterpret_cast<const float4*>(A.p) + i);
+    else {
+        const long long* f = reinterpret_cast<const long long*>(A.p) + i;    // FMT_FORCE_FIXED
+        prefetchL2(f); prefetchL2(f + A.sc); prefetchL2(f + 2*A.sc);
+    }
+}
 // plugin-order atom slot -> index in the caller's arrays
 __device__ __forceinline__ long long atomSlot(const DeviceSystem& S, int pluginIndex) {
     return S.atomLoc ? (long long) S.atomLoc[pluginIndex] : (long long) pluginIndex;

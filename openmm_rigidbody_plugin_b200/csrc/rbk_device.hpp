@@ -27,7 +27,7 @@ constexpr int kBlock = 128;            // threads per CTA = max bodies per tile
 // so that its thread-per-body phase runs full warps.  For small bodies (water) the two coincide.
 constexpr int kTileAtoms = 512;
 #ifndef RBK_LARGE_PER_THREAD
-#define RBK_LARGE_PER_THREAD 2
+#define RBK_LARGE_PER_THREAD 3         // (config 4, Part 2 alone: 256-atom tiles 127 us, 384 112 us, 512 120 us)
 #endif
 constexpr int kLargePerThread = RBK_LARGE_PER_THREAD;          // atoms per thread of the large-body atom kernels
 constexpr int kLargeBodyTileAtoms = kBlock*kLargePerThread;    // atom-tile cap when bodies are large: a tile's forces and
@@ -68,6 +68,11 @@ struct DeviceSystem {
     const int4* warpTileMeta;    // per one-warp tile (subdivision of the atom tiles), same fields
     const TileMaps* tileMaps;    // HOST pointer (kernel-parameter copies are made at launch); NULL = no TMA tensor path
     const int* atomLoc;
+    const int* bodyRun;          // per body (storage order): caller slot of its first atom when EVERY body's atoms sit in consecutive
+                                 // slots, in order (NULL otherwise) - large-body Part 2 then moves whole runs with TMA bulk copies
+    int numSlots;                // 1 + the largest caller slot any atom of the system occupies (the arrays are at least this long)
+    int noFreeRide;              // RBK_NO_FREE_RIDE=1: the free atoms of large-body systems always get their own launch (A/B measurements, tests)
+    int noBulkPart2;             // RBK_NO_BULK_PART2=1: large-body Part 2 always takes the per-atom request kernel (A/B measurements, tests)
     SeriesControl* seriesCtl;
     const volatile int* hostRung;    // HOST pointer: the rung as the kernels last published it (mapped pinned memory) ...
     int* hostRungDevice;             // ... and the device alias they write it through
@@ -143,6 +148,7 @@ cudaError_t launchPotentialRefinement(const DeviceSystem& S, const RefinedState&
 // false when launchPart2Part1 skips the F / tau stores of its bodies (S.lazyForceTorque and the one-pass kernel is used)
 bool part2Part1LeavesForceTorque(const DeviceSystem& S);
 int part1LaunchesPerStep(const DeviceSystem& S);   // 1 (fused) or 2 (rotation kernel + atom kernel)
+void launchesPerCall(const DeviceSystem& S, int out[3]);   // kernel launches of launchPart1, launchPart2, launchPart2Part1
 cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, unsigned* counter, double* out, cudaStream_t st);
 
 } // namespace rbk

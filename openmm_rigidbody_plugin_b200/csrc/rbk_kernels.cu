@@ -410,291 +410,6 @@ __global__ void __launch_bounds__(kBlock, RBK_P2_MINBLOCKS) part2Kernel(const De
 }
 
 // ------------------------------------------------------------------------------------------------
-// Part 2 for large-body systems (mean body size > kSplitAtomsPerBody; atom tiles of <= kLargeBodyTileAtoms atoms).
-//
-// The bucket for big bodies of the size-bucketed reduction: with tens of atoms per body a shuffle scan spends
-// 5 levels x 6 doubles of SHFL/select/add on every 32 atoms (ncu on config 4: 28 % of the executed instructions,
-// issue-bound at 3.4 TB/s).  Here a tile's forces and body-frame coordinates are staged in shared memory; the atoms'
-// threads turn the coordinates into space-frame arms delta = A^T(q) d in place, and then a GROUP OF LANES PER BODY
-// (16 or 8) walks the body's atoms - lane g takes atoms g, g+lanes, ... in order (within a lane the reference's own
-// summation order, RigidBody::forceAndTorque, openmmapi/src/RigidBody.cpp:174-183) - and a fixed butterfly over the
-// group finishes the sums: a few shuffles per BODY instead of per 32 atoms, no atomics, deterministic.  The arms stay
-// in shared memory for the velocity phase, so the body-frame coordinates are read once and rotated once.
-// A body larger than a tile is alone in its tile and is reduced by the whole CTA (strided partial sums, fixed tree).
-// ------------------------------------------------------------------------------------------------
-// Persistent CTAs (one wave) walk the tiles round-robin behind a three-deep cp.async pipeline: while tile i is processed,
-// tile i+1's coordinates, forces, body bytes and body state arrive in the other shared-memory stage, tile i+2's per-body
-// offsets and first slots in a small ring, and tile i+3's descriptor - so no request ever waits for a load it depends on
-// (the one-CTA-per-tile version of this kernel spent its life in five dependent phases, and a request that looked every
-// atom up in atomLoc stalled on that load: ncu, 34 % of the samples; moving whole-body runs instead cost 27 % of the
-// executed instructions).  The atoms' array slots therefore travel with the per-body offsets, two tiles ahead.
-// Five CTAs per SM (shared memory: two 256-atom stages + rings, ~38 KB each).  Measured on config 4 (tile atoms x CTAs/SM):
-// 256x5 0.272 ms/step, 256x6 0.292, 384x4 0.285, 512x3 0.276; the shuffle-scan part2Kernel 0.279 - 0.291.
-#ifndef RBK_P2L_THREADS
-#define RBK_P2L_THREADS 128
-#endif
-constexpr int kP2LThreads = RBK_P2L_THREADS;        // (256 threads per tile measured slower: 0.346 vs 0.313 ms/step on config 4)
-constexpr int kP2LStatePlanes = 15;                 // q4 p3 pi4 invm invI3
-struct Part2LargeLayout {                           // byte offsets inside one stage / the CTA's shared memory
-    int f, st, key, stageBytes, acc, ring, ringBytes, meta, total;
-};
-__host__ __device__ inline Part2LargeLayout part2LargeLayout(int NB) {
-    constexpr int A = kLargeBodyTileAtoms;
-    Part2LargeLayout L;
-    L.f = 3*A*8;                                    // d[3][A] sits at offset 0
-    L.st = L.f + 3*A*8;
-    L.key = L.st + kP2LStatePlanes*NB*8;
-    L.stageBytes = (L.key + A + 16 + 127) & ~127;
-    L.acc = 2*L.stageBytes;
-    L.ring = L.acc + 6*NB*8;                        // 3 x { int loc[NB + 4]; int slot[A]; }
-    L.ringBytes = (NB + 4 + A)*4;
-    L.meta = (L.ring + 3*L.ringBytes + 15) & ~15;   // int4[4]
-    L.total = L.meta + 4*16;
-    return L;
-}
-
-// 88 registers (ptxas would take 94 of the 102 that five CTAs allow): 5 x 128 x 88 leaves 9216 registers per SM, room
-// for two of the 64-thread free-atom CTAs that run on the side stream next to this kernel (config 4: 0.264 -> 0.254 ms/step;
-// 80 registers slow this kernel down: 0.290).
-#ifndef RBK_P2L_MAXNREG
-#define RBK_P2L_MAXNREG 88
-#endif
-#define RBK_P2L_REGCAP __maxnreg__(RBK_P2L_MAXNREG)
-template <bool NATIVE>
-__global__ void RBK_P2L_REGCAP part2LargeKernel(const DeviceSystem S, const double dt, const AtomView pos,
-                                                                             const AtomView vel, const AtomView force) {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    constexpr int A = kLargeBodyTileAtoms;
-    constexpr int kBlock = kP2LThreads, kWarps = kP2LThreads/32;          // shadow the file-level constants inside this kernel
-    const int NB = S.stageBodies;
-    const Part2LargeLayout L = part2LargeLayout(NB);
-    double* const sAcc = reinterpret_cast<double*>(smemRaw + L.acc);      // [6][NB] (F, tau), later (v_cm, omega_space)
-    int4* const sMeta = reinterpret_cast<int4*>(smemRaw + L.meta);        // ring of 4 tile descriptors
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x, numTiles = S.numTiles;
-    const size_t ld = S.bodyStride, as = S.atomStride;
-    const int* const atomLoc = S.atomLoc;
-
-    auto ringLoc = [&](int i) { return reinterpret_cast<int*>(smemRaw + L.ring + (i % 3)*L.ringBytes); };
-    auto ringSlot = [&](int i) { return ringLoc(i) + NB + 4; };
-    // per-body atom offsets and per-atom array slots of this CTA's i-th tile
-    auto requestBodies = [&](int i) {
-        const int4 m = sMeta[i & 3];
-        if (tid < m.y) cpAsync4(ringLoc(i) + tid, S.loc + m.x + tid);
-        if (atomLoc != nullptr && m.w <= A) {
-            const int* g = atomLoc + S.numFree + m.z;
-            int* r = ringSlot(i);
-            for (int j = tid; j < m.w; j += kBlock) cpAsync4(r + j, g + j);
-        }
-    };
-    // coordinates, forces, body bytes and body state of this CTA's i-th tile
-    auto requestData = [&](int i, int stage) {
-        const int4 m = sMeta[i & 3];
-        unsigned char* T = smemRaw + stage*L.stageBytes;
-        double* sD = reinterpret_cast<double*>(T);
-        double* sF = reinterpret_cast<double*>(T + L.f);
-        double* sSt = reinterpret_cast<double*>(T + L.st);
-        const int nb = m.y, a0 = m.z, na = m.w;
-        if (tid < nb) {
-            const double* g = S.state + (size_t) (m.x + tid);
-#pragma unroll
-            for (int k = 0; k < 4; k++) cpAsync8(&sSt[k*NB + tid], g + (PL_Q + k)*ld);
-#pragma unroll
-            for (int k = 0; k < 3; k++) cpAsync8(&sSt[(4 + k)*NB + tid], g + (PL_P + k)*ld);
-#pragma unroll
-            for (int k = 0; k < 4; k++) cpAsync8(&sSt[(7 + k)*NB + tid], g + (PL_PI + k)*ld);
-            cpAsync8(&sSt[11*NB + tid], g + PL_INVM*ld);
-#pragma unroll
-            for (int k = 0; k < 3; k++) cpAsync8(&sSt[(12 + k)*NB + tid], g + (PL_INVI + k)*ld);
-        }
-        if (na > A) return;                                      // one body larger than a tile: its atoms are read in place
-        for (int j = tid; j < na; j += kBlock) {
-            const double* g = S.dxyz + (size_t) (a0 + j);
-            cpAsync8(&sD[j], g);
-            cpAsync8(&sD[A + j], g + as);
-            cpAsync8(&sD[2*A + j], g + 2*as);
-        }
-        const int* slots = ringSlot(i);
-        for (int j = tid; j < na; j += kBlock) {
-            const int slot = atomLoc != nullptr ? slots[j] : S.numFree + a0 + j;
-            if (NATIVE) {
-                const double* fp = force.p + slot*force.sa;
-                cpAsync8(&sF[3*j], fp);
-                cpAsync8(&sF[3*j + 1], fp + force.sc);
-                cpAsync8(&sF[3*j + 2], fp + 2*force.sc);
-            }
-            else {
-                const d3 f = loadAtom<false>(force, slot);
-                sF[3*j] = f.x; sF[3*j + 1] = f.y; sF[3*j + 2] = f.z;
-            }
-        }
-        const int first = a0 & ~3;                               // 4-byte granules of the byte array
-        for (int w = tid; 4*w < a0 + na - first; w += kBlock) cpAsync4(T + L.key + 4*w, S.localBody + first + 4*w);
-    };
-
-    const int tile0 = blockIdx.x;
-    if (tile0 >= numTiles) return;
-    if (tid < 3 && tile0 + tid*G < numTiles) sMeta[tid] = S.tileMeta[tile0 + tid*G];
-    __syncthreads();
-    requestBodies(0);
-    if (tile0 + G < numTiles) requestBodies(1);
-    cpCommit();
-    cpWait<0>();
-    __syncthreads();
-    requestData(0, 0);
-    cpCommit();
-    int it = 0;
-    for (int tile = tile0; tile < numTiles; tile += G, it++) {
-        const int cur = it & 1;
-        cpWait<0>();                                             // tile `it`, the bodies of it+1 and the descriptor of it+2 have landed
-        __syncthreads();
-        const int4 m = sMeta[it & 3];
-        if (tile + G < numTiles) requestData(it + 1, cur ^ 1);
-        if (tile + 2*G < numTiles) requestBodies(it + 2);
-        if (tid == 0 && tile + 3*G < numTiles) cpAsync16(&sMeta[(it + 3) & 3], S.tileMeta + tile + 3*G);
-        cpCommit();
-
-        unsigned char* T = smemRaw + cur*L.stageBytes;
-        double* const sD = reinterpret_cast<double*>(T);          // [3][A] body-frame coordinates, then the arms delta
-        double* const sF = reinterpret_cast<double*>(T + L.f);    // [3*A] forces xyzxyz...
-        double* const sSt = reinterpret_cast<double*>(T + L.st);  // [15][NB]
-        const int* const sLoc = ringLoc(it);
-        const int* const sSlot = ringSlot(it);
-        const unsigned char* const sKey = T + L.key + (m.z & 3);
-        const int nb = m.y, a0 = m.z, na = m.w;
-
-        if (na > A) {                                            // ---- one body larger than a tile: CTA-wide reduction
-            double* s = S.state + (size_t) m.x;
-            const d4 q = {sSt[0], sSt[NB], sSt[2*NB], sSt[3*NB]};
-            double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int a = a0 + tid; a < a0 + na; a += kBlock) {
-                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-                const d3 f = loadAtom<NATIVE>(force, atomSlot(S, S.numFree + a));
-                const d3 t = cross(bodyToSpace(q, d), f);
-                v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], off);
-            if (lane == 0)
-#pragma unroll
-                for (int k = 0; k < 6; k++) sF[warp*6 + k] = v[k];
-            __syncthreads();
-            if (tid == 0) {
-#pragma unroll
-                for (int w = 1; w < kWarps; w++)
-#pragma unroll
-                    for (int k = 0; k < 6; k++) v[k] += sF[w*6 + k];
-                const d3 F = {v[0], v[1], v[2]}, tau = {v[3], v[4], v[5]};
-                d3 p = {sSt[4*NB], sSt[5*NB], sSt[6*NB]};
-                d4 pi = {sSt[7*NB], sSt[8*NB], sSt[9*NB], sSt[10*NB]};
-                d3 vcm, om;
-                bodyPart2(dt, F, tau, sSt[11*NB], d3{sSt[12*NB], sSt[13*NB], sSt[14*NB]}, q, p, pi, vcm, om);
-                storePlane3(s + PL_P*ld, ld, p);
-                storePlane4(s + PL_PI*ld, ld, pi);
-                storePlane3(s + PL_F*ld, ld, F);
-                storePlane3(s + PL_TAU*ld, ld, tau);
-                sD[0] = vcm.x; sD[1] = vcm.y; sD[2] = vcm.z; sD[3] = om.x; sD[4] = om.y; sD[5] = om.z;
-            }
-            __syncthreads();
-            const d3 vcm = {sD[0], sD[1], sD[2]}, om = {sD[3], sD[4], sD[5]};
-            for (int a = a0 + tid; a < a0 + na; a += kBlock) {
-                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
-                storeAtom<NATIVE>(vel, atomSlot(S, S.numFree + a), atomVelocity(vcm, om, bodyToSpace(q, d)));
-            }
-            __syncthreads();
-            continue;
-        }
-
-        // ---- B: thread per atom: arms delta = A^T(q) d, in place
-        for (int j = tid; j < na; j += kBlock) {
-            {
-                const int k = sKey[j];
-                const d4 q = {sSt[k], sSt[NB + k], sSt[2*NB + k], sSt[3*NB + k]};
-                const d3 delta = bodyToSpace(q, d3{sD[j], sD[A + j], sD[2*A + j]});
-                sD[j] = delta.x; sD[A + j] = delta.y; sD[2*A + j] = delta.z;
-            }
-        }
-        __syncthreads();
-
-        // ---- B2: a lane group per body - 16 lanes when the tile holds at most kBlock/16 bodies (the usual case for large
-        // bodies), else 8: lane g sums atoms g, g+lanes, ... of its body in order, then a fixed butterfly over the group
-        const int lg = nb <= kBlock/16 ? 4 : 3, lanes = 1 << lg;
-        for (int b0 = 0; b0 < nb; b0 += kBlock >> lg) {
-            if (b0 + ((warp*32) >> lg) >= nb) break;             // warp-uniform: none of this warp's bodies exists
-            const int b = b0 + (tid >> lg), g = tid & (lanes - 1);
-            double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            if (b < nb) {
-                const int j1 = (b + 1 < nb ? sLoc[b + 1] : a0 + na) - a0;
-                for (int j = sLoc[b] - a0 + g; j < j1; j += lanes) {
-                    const d3 delta = {sD[j], sD[A + j], sD[2*A + j]};
-                    const d3 f = {sF[3*j], sF[3*j + 1], sF[3*j + 2]};
-                    const d3 t = cross(delta, f);
-                    v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
-                }
-            }
-            if (lg == 4) {                                       // warp-uniform
-#pragma unroll
-                for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], 8);
-            }
-#pragma unroll
-            for (int off = 4; off > 0; off >>= 1)
-#pragma unroll
-                for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], off);
-            if (b < nb && g == 0)
-#pragma unroll
-                for (int k = 0; k < 6; k++) sAcc[k*NB + b] = v[k];
-        }
-        __syncthreads();
-
-        if (tid < nb) {                                          // ---- C: thread per body, second kick
-            const d3 F = {sAcc[tid], sAcc[NB + tid], sAcc[2*NB + tid]};
-            const d3 tau = {sAcc[3*NB + tid], sAcc[4*NB + tid], sAcc[5*NB + tid]};
-            const d4 q = {sSt[tid], sSt[NB + tid], sSt[2*NB + tid], sSt[3*NB + tid]};
-            d3 p = {sSt[4*NB + tid], sSt[5*NB + tid], sSt[6*NB + tid]};
-            d4 pi = {sSt[7*NB + tid], sSt[8*NB + tid], sSt[9*NB + tid], sSt[10*NB + tid]};
-            const double invm = sSt[11*NB + tid];
-            const d3 invI = {sSt[12*NB + tid], sSt[13*NB + tid], sSt[14*NB + tid]};
-            d3 vcm, om;
-            bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
-            double* s = S.state + (size_t) (m.x + tid);
-            storePlane3(s + PL_P*ld, ld, p);
-            storePlane4(s + PL_PI*ld, ld, pi);
-            storePlane3(s + PL_F*ld, ld, F);
-            storePlane3(s + PL_TAU*ld, ld, tau);
-            sAcc[tid] = vcm.x; sAcc[NB + tid] = vcm.y; sAcc[2*NB + tid] = vcm.z;
-            sAcc[3*NB + tid] = om.x; sAcc[4*NB + tid] = om.y; sAcc[5*NB + tid] = om.z;
-        }
-        __syncthreads();
-
-        for (int j = tid; j < na; j += kBlock) {                 // ---- D: thread per atom, velocities
-            {
-                const int k = sKey[j];
-                const d3 delta = {sD[j], sD[A + j], sD[2*A + j]};
-                const d3 vcm = {sAcc[k], sAcc[NB + k], sAcc[2*NB + k]};
-                const d3 om = {sAcc[3*NB + k], sAcc[4*NB + k], sAcc[5*NB + k]};
-                storeAtom<NATIVE>(vel, atomLoc != nullptr ? sSlot[j] : S.numFree + a0 + j, atomVelocity(vcm, om, delta));
-            }
-        }
-        __syncthreads();                                         // the stage, the ring slot and sAcc are reused
-    }
-    cpWait<0>();
-}
-
-template <bool NATIVE>
-cudaError_t launchPart2Large(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
-    const size_t smem = (size_t) part2LargeLayout(S.stageBodies).total;
-    static LaunchCache cache;                                  // persistent CTAs: one full wave, whatever fits
-    int blocks = 0;
-    cudaError_t e = cache.get(part2LargeKernel<NATIVE>, kP2LThreads, smem, blocks);
-    if (e != cudaSuccess) return e;
-    const int resident = S.numSMs*blocks;
-    part2LargeKernel<NATIVE><<<S.numTiles < resident ? S.numTiles : resident, kP2LThreads, smem, st>>>(S, dt, pos, vel, force);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
 // Step-fused kernel: Part 2 of step k + Part 1 of step k+1 in one pass (small-body systems).
 //
 // Nothing happens between the two halves in RigidBodyIntegrator::step, so a tile's bodies can take the
@@ -775,6 +490,451 @@ __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.as
 
 // stage plane k <-> global state plane: r p q pi are planes 0..13, then invm (20) and invI (24..26)
 __device__ __forceinline__ int fusedGlobalPlane(int k) { return k < 14 ? k : (k == 14 ? (int) PL_INVM : (int) PL_INVI + (k - 15)); }
+
+// ------------------------------------------------------------------------------------------------
+// Part 2 for large-body systems (mean body size > kSplitAtomsPerBody; atom tiles of <= kLargeBodyTileAtoms atoms).
+//
+// The bucket for big bodies of the size-bucketed reduction.  Persistent CTAs (one wave) walk the tiles round-robin behind a
+// three-deep pipeline: while tile i is processed, tile i+1's coordinates, forces, body bytes and body state arrive in the other
+// shared-memory stage, tile i+2's per-body offsets (and first slots / atom slots) in a small ring, and tile i+3's descriptor -
+// so no request ever waits for a load it depends on.  Per tile:
+//   B   thread per atom: arm delta = A^T(q) d (kept in registers for phase D), torque delta x f written over the coordinates;
+//   B2  thread per (body, component): its column of the staged forces / torques is added in atom order (four interleaved
+//       partial sums, RigidBody::forceAndTorque, openmmapi/src/RigidBody.cpp:174-183, up to that association) - no shuffles, no
+//       atomics, one instruction stream for all six components, deterministic and independent of how the forces came in;
+//       (a balanced variant - threads per chunk of consecutive atoms, partial sums per body - executed 30 % more instructions: 181 us vs 136)
+//   C   thread per body: second kick;   D   thread per atom: velocities.
+// A body larger than a tile is alone in its tile and is reduced by the whole CTA (strided partial sums, fixed tree).
+//
+// The tile's coordinate planes and body bytes are the handle's own data and always arrive as four TMA bulk copies on the
+// stage's mbarrier.  RUNS (S.bodyRun: the atoms of every body sit in consecutive slots of the caller's arrays, in order - what
+// OpenMM keeps through its atom re-orderings, which move whole molecules, and what any topology-ordered atom list looks
+// like): nothing is requested per atom - the forces of each body are ONE bulk copy (Vec3 rows) or three (planes: SoA doubles,
+// OpenMM's fixed-point long long) issued by the body's thread, and an atom's array slot is its tile index plus a per-body
+// constant.  Bulk copies move 16-byte granules between 16-byte aligned addresses: a run that starts at an odd 8-byte word is
+// copied from one word earlier and lands at an even word of the stage (per-body offset table fo); the array's last word is
+// fetched by an 8-byte cp.async when the rounded copy would pass the end of the caller's array.  !RUNS (atoms permuted one by
+// one, misaligned planes): per-thread 8-byte cp.async through a ring of array slots that travels two tiles ahead.
+// ncu on config 4, round 1 formulation (per-atom requests everywhere, 16-lane butterfly per body): 85 M warp-instructions, 33 % of
+// them request code, 32 % the butterfly, 150 us; RUNS: 66 M, 128 us.
+// ------------------------------------------------------------------------------------------------
+#ifndef RBK_P2L_THREADS
+#define RBK_P2L_THREADS 128
+#endif
+constexpr int kP2LThreads = RBK_P2L_THREADS;        // (256 threads per tile measured slower: 0.346 vs 0.313 ms/step on config 4)
+constexpr int kP2LStatePlanes = 15;                 // q4 p3 pi4 invm invI3
+constexpr int kP2LFree = 64;                        // most free atoms a tile takes along (see part2LargeKernel, freePhase)
+template <int NB, bool RUNS> struct Part2LargeLayout {     // byte offsets inside one stage / the CTA's shared memory; pitches in doubles
+    static constexpr int A = kLargeBodyTileAtoms;
+    static constexpr int dp = A + 2;                // coordinate plane: the copy starts at an even atom
+    static constexpr int fp = RUNS ? A + 2*NB + 2 : A;      // force plane: every body's run starts at an even word, two spare words each
+    static constexpr int f = 3*dp*8;                // d[3][dp] sits at offset 0
+    static constexpr int st = f + 3*fp*8;
+    static constexpr int key = st + kP2LStatePlanes*NB*8;
+    static constexpr int fo = key + A + 32;         // int fo[NB]: staged word of atom j, component c = fo[body] + j*fs + c*fc
+    static constexpr int rd = fo + NB*4;            // int rd[NB]: array slot of atom j = j + rd[body]
+    static constexpr int stageBytes = (rd + NB*4 + 127) & ~127;
+    static constexpr int acc = 2*stageBytes;        // double acc[6][NB]
+    static constexpr int ringFree = NB + 4 + (RUNS ? NB + 4 : A);      // 3 x { int loc[NB + 4]; int run[NB + 4] | int slot[A]; int freeSlot[kP2LFree]; }
+    static constexpr int ringInts = ringFree + kP2LFree;
+    static constexpr int ring = acc + 6*NB*8;
+    static constexpr int meta = (ring + 3*ringInts*4 + 15) & ~15;      // int4[4]
+    static constexpr int bar = meta + 4*16;         // two mbarriers
+    static constexpr int total = bar + 16;
+};
+// the request code works on 32-bit shared-memory addresses (one conversion per kernel instead of one per instruction)
+__device__ __forceinline__ void cpAsync8s(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsync4s(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void bulkCopyS(unsigned smem, const void* gmem, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem), "l"(gmem), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbarArriveS(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTxS(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+// Register cap: five / four / three resident CTAs of 128 threads (tiles of 256 / 384 / 512 atoms).
+#ifndef RBK_P2L_MAXNREG
+#define RBK_P2L_MAXNREG (RBK_LARGE_PER_THREAD <= 2 ? 96 : RBK_LARGE_PER_THREAD == 3 ? 128 : 168)
+#endif
+// NB: body capacity of a tile's stage (S.stageBodies rounded up to one of the instantiated sizes): compile-time, so that the
+// shared-memory layout is a set of immediates.
+// freePhase != 0: the FREE atoms ride along (2 = their Part 2, 3 = Part 2 + Part 1 of the next step, as freeAtomsKernel): tile t
+// takes the t-th slice of the free-atom list, at most kP2LFree atoms - their slots come through the ring two tiles ahead, the
+// last threads of the CTA load them when the sums start (phase B2, where those warps have little or nothing to do), and
+// finish them next to the thread-per-body kick (phase C, one busy warp).  No separate launch, no second stream, and the
+// sectors a free atom shares with the body atoms around it are in flight at the same time.
+template <bool NATIVE, int NB, bool RUNS>
+__global__ void __maxnreg__(RBK_P2L_MAXNREG) part2LargeKernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel,
+                                                              const AtomView force, const int freePhase) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    typedef Part2LargeLayout<NB, RUNS> L;
+    constexpr int A = kLargeBodyTileAtoms;
+    constexpr int kBlock = kP2LThreads, kWarps = kP2LThreads/32;          // shadow the file-level constants inside this kernel
+    static_assert(kLargeBodyTileAtoms == kLargePerThread*kP2LThreads, "a thread keeps the arms of its kLargePerThread atoms in registers");
+    static_assert(NB % 4 == 0 && NB <= kP2LThreads - 8, "body threads and the four plane-copy threads are different threads");
+    double* const sAcc = reinterpret_cast<double*>(smemRaw + L::acc);     // [6][NB] (F, tau), later (v_cm, omega_space)
+    int4* const sMeta = reinterpret_cast<int4*>(smemRaw + L::meta);       // ring of 4 tile descriptors
+    int* const sRing = reinterpret_cast<int*>(smemRaw + L::ring);
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smemRaw + L::bar);
+    const unsigned sBase = smemAddr(smemRaw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, numTiles = S.numTiles;
+    const size_t ld = S.bodyStride, as = S.atomStride;
+    const int* const atomLoc = S.atomLoc;
+    const bool rows = !RUNS || force.sa == 3;                             // staged as Vec3 rows; otherwise three planes (RUNS, force.sc apart)
+    const int fs = rows ? 3 : 1, fc = rows ? 1 : L::fp;
+    const bool fixedPoint = RUNS && !NATIVE && force.fmt == FMT_FORCE_FIXED;
+    // free atoms of tile t: [freeFirst(t), freeFirst(t + 1)) - an even split of the list in 2^-20 fixed point
+    const unsigned long long freeRatio = freePhase ? ((unsigned long long) S.numFree << 20)/(unsigned) numTiles : 0ull;
+    auto freeFirst = [&](int t) { return t >= numTiles ? S.numFree : (int) (((unsigned long long) t*freeRatio) >> 20); };
+
+    // per-body atom offsets (one more than bodies: the end of the last one) and first slots | atom slots of a tile -> ring entry r
+    auto requestBodies = [&](int4 m, int r, int t) {
+        const unsigned dst = sBase + L::ring + (r*L::ringInts + tid)*4;
+        if (tid <= m.y) cpAsync4s(dst, S.loc + m.x + tid);
+        if (freePhase && atomLoc != nullptr) {
+            const int k0 = freeFirst(t);
+            if (tid < freeFirst(t + 1) - k0) cpAsync4s(dst + L::ringFree*4, atomLoc + k0 + tid);
+        }
+        if (RUNS) {
+            if (tid < m.y) cpAsync4s(dst + (NB + 4)*4, S.bodyRun + m.x + tid);
+        }
+        else if (atomLoc != nullptr && m.w <= A) {
+            const int* g = atomLoc + S.numFree + m.z;
+            for (int j = tid; j < m.w; j += kBlock) cpAsync4s(dst + (NB + 4 + j - tid)*4, g + j);
+        }
+    };
+    // coordinates, forces, body bytes and body state of the tile whose offsets are in ring entry r; every thread arrives on the
+    // stage's barrier, the ones that start bulk copies with their byte counts
+    auto requestData = [&](int4 m, int r, int stage) {
+        const unsigned T = sBase + stage*L::stageBytes, sbar = sBase + L::bar + 8*stage;
+        const int nb = m.y, a0 = m.z, na = m.w;
+        if (tid < nb) {
+            const double* g = S.state + (size_t) (m.x + tid);
+            const unsigned dst = T + L::st + 8*tid;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cpAsync8s(dst + k*NB*8, g + (PL_Q + k)*ld);
+#pragma unroll
+            for (int k = 0; k < 3; k++) cpAsync8s(dst + (4 + k)*NB*8, g + (PL_P + k)*ld);
+#pragma unroll
+            for (int k = 0; k < 4; k++) cpAsync8s(dst + (7 + k)*NB*8, g + (PL_PI + k)*ld);
+            cpAsync8s(dst + 11*NB*8, g + PL_INVM*ld);
+#pragma unroll
+            for (int k = 0; k < 3; k++) cpAsync8s(dst + (12 + k)*NB*8, g + (PL_INVI + k)*ld);
+        }
+        if (na > A) { mbarArriveS(sbar); return; }               // one body larger than a tile: its atoms are read in place
+        const int* const ring = sRing + r*L::ringInts;
+        if (!RUNS)
+            for (int j = tid; j < na; j += kBlock) {             // per-atom force requests through the slot ring
+                const long long slot = atomLoc != nullptr ? ring[NB + 4 + j] : S.numFree + a0 + j;
+                if (NATIVE) {
+                    const double* fp = force.p + slot*force.sa;
+                    const unsigned dst = T + L::f + 24*j;
+                    cpAsync8s(dst, fp);
+                    cpAsync8s(dst + 8, fp + force.sc);
+                    cpAsync8s(dst + 16, fp + 2*force.sc);
+                }
+                else {
+                    const d3 f = loadAtom<false>(force, slot);
+                    double* sF = reinterpret_cast<double*>(smemRaw + stage*L::stageBytes + L::f);
+                    sF[3*j] = f.x; sF[3*j + 1] = f.y; sF[3*j + 2] = f.z;
+                }
+            }
+        if (RUNS && tid < nb) {
+            const int j0 = ring[tid] - a0, n = ring[tid + 1] - ring[tid];
+            const long long slot0 = ring[NB + 4 + tid];
+            int* const tables = reinterpret_cast<int*>(smemRaw + stage*L::stageBytes + L::fo);
+            tables[NB + tid] = (int) slot0 - j0;
+            if (rows) {
+                const long long w0 = 3*slot0;
+                const int ph = (int) (w0 & 1), s = (3*j0 + 2*tid + 1) & ~1;
+                int words = (ph + 3*n + 1) & ~1, tail = 0;
+                if (w0 - ph + words > 3LL*S.numSlots) { words -= 2; tail = 1; }      // the rounded copy would pass the end of the array
+                const double* src = force.p + (w0 - ph);
+                tables[tid] = s + ph - 3*j0;
+                mbarExpectTxS(sbar, 8u*words);
+                bulkCopyS(T + L::f + 8*s, src, 8u*words, sbar);
+                if (tail) cpAsync8s(T + L::f + 8*(s + words), src + words);
+            }
+            else {
+                const int ph = (int) (slot0 & 1), s = (j0 + 2*tid + 1) & ~1, words = (ph + n + 1) & ~1;
+                const double* src = force.p + (slot0 - ph);
+                tables[tid] = s + ph - j0;
+                mbarExpectTxS(sbar, 24u*words);
+#pragma unroll
+                for (int c = 0; c < 3; c++) bulkCopyS(T + L::f + 8*(c*L::fp + s), src + c*force.sc, 8u*words, sbar);
+            }
+        }
+        else if (tid >= kBlock - 3) {
+            const int c = kBlock - 1 - tid, first = a0 & ~1;
+            const unsigned bytes = 8u*(((a0 + na + 1) & ~1) - first);
+            mbarExpectTxS(sbar, bytes);
+            bulkCopyS(T + 8*c*L::dp, S.dxyz + c*as + first, bytes, sbar);
+        }
+        else if (tid == kBlock - 4) {
+            const int first = a0 & ~15;
+            const unsigned bytes = ((a0 + na + 15) & ~15) - first;
+            mbarExpectTxS(sbar, bytes);
+            bulkCopyS(T + L::key, S.localBody + first, bytes, sbar);
+        }
+        else mbarArriveS(sbar);
+    };
+
+    const int tile0 = blockIdx.x;
+    if (tile0 >= numTiles) return;
+    if (tid == 0) {
+        mbarInit(&bar[0], kBlock);
+        mbarInit(&bar[1], kBlock);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 3 && tile0 + tid*G < numTiles) sMeta[tid] = S.tileMeta[tile0 + tid*G];
+    __syncthreads();
+    requestBodies(sMeta[0], 0, tile0);
+    if (tile0 + G < numTiles) requestBodies(sMeta[1], 1, tile0 + G);
+    cpCommit();
+    cpWait<0>();
+    __syncthreads();
+    requestData(sMeta[0], 0, 0);
+    cpCommit();
+    int it = 0, r0 = 0;                                          // r0 = it % 3: ring entry of the current tile
+    for (int tile = tile0; tile < numTiles; tile += G, it++) {
+        const int cur = it & 1;
+        const int r1 = r0 == 2 ? 0 : r0 + 1, r2 = r1 == 2 ? 0 : r1 + 1;
+        cpWait<0>();                                             // state (and forces) of tile `it`, the bodies of it+1, the descriptor of it+2 have landed
+        mbarWait(&bar[cur], (it >> 1) & 1);                      // ... and its coordinates, body bytes (and forces)
+        __syncthreads();
+        const int4 m = sMeta[it & 3];
+        if (tile + G < numTiles) requestData(sMeta[(it + 1) & 3], r1, cur ^ 1);
+        if (tile + 2*G < numTiles) requestBodies(sMeta[(it + 2) & 3], r2, tile + 2*G);
+        if (tid == 0 && tile + 3*G < numTiles) cpAsync16(&sMeta[(it + 3) & 3], S.tileMeta + tile + 3*G);
+        cpCommit();
+        if (freePhase && tile + G < numTiles) {                  // the free atoms of the NEXT tile: towards L2 now, loaded a tile later
+            const int k = freeFirst(tile + G) + (kBlock - 1 - tid);
+            if (k < freeFirst(tile + G + 1)) {
+                const long long slot = atomLoc != nullptr ? sRing[r1*L::ringInts + L::ringFree + kBlock - 1 - tid] : k;
+                prefetchAtom(force, slot);
+                prefetchAtom(pos, slot);
+                prefetchAtom(vel, slot);
+                prefetchL2(S.freeInvMass + k);
+                if (freePhase & 2) { prefetchL2(S.savedPos + k); prefetchL2(S.savedPos + k + S.freeStride); prefetchL2(S.savedPos + k + 2*S.freeStride); }
+            }
+        }
+
+        unsigned char* T = smemRaw + cur*L::stageBytes;
+        double* const sD = reinterpret_cast<double*>(T) + (m.z & 1);          // [3][dp] body-frame coordinates, then the torques delta x f
+        double* const sF = reinterpret_cast<double*>(T + L::f);               // forces: rows xyzxyz... | as copied (rows or planes, per-body offsets)
+        double* const sSt = reinterpret_cast<double*>(T + L::st);             // [15][NB]
+        const int* const sFo = reinterpret_cast<const int*>(T + L::fo);
+        const int* const sRd = sFo + NB;
+        const int* const sLoc = sRing + r0*L::ringInts;
+        const int* const sSlot = sLoc + NB + 4;                               // !RUNS: array slots of the tile's atoms
+        const unsigned char* const sKey = T + L::key + (m.z & 15);
+        const int nb = m.y, a0 = m.z, na = m.w;
+        r0 = r1;
+
+        // the free atom this thread takes along (the CTA's last threads, one each)
+        const int freeK = freePhase ? freeFirst(tile) + (kBlock - 1 - tid) : 0;
+        const bool freeMine = freePhase && freeK < freeFirst(tile + 1);
+        long long freeSlot = 0;
+        d3 freeF, freeX, freeV, freeSaved;
+        double freeInvm = 0.0;
+        auto freeLoad = [&]() {
+            freeSlot = atomLoc != nullptr ? sLoc[L::ringFree + kBlock - 1 - tid] : freeK;
+            freeF = loadAtom<NATIVE>(force, freeSlot);
+            freeInvm = S.freeInvMass[freeK];
+            freeX = loadAtom<NATIVE>(pos, freeSlot);
+            freeV = loadAtom<NATIVE>(vel, freeSlot);
+            if (freePhase & 2) freeSaved = loadPlane3(S.savedPos + freeK, S.freeStride);
+        };
+        auto freeFinish = [&]() {
+            if (freePhase & 2) freePart2(dt, freeF, freeInvm, freeX, freeSaved, freeV);
+            if (freePhase & 1) {
+                freePart1(dt, freeF, freeInvm, freeX, freeV);
+                storeAtom<NATIVE>(pos, freeSlot, freeX);
+                storePlane3(S.savedPos + freeK, S.freeStride, asStored<NATIVE>(pos, freeX));
+            }
+            if (!NATIVE && vel.fmt == FMT_REAL4_F64 && S.atomInvMass != nullptr) {      // whole double4, w = 1/m (see part2Part1Kernel)
+                double2* out = reinterpret_cast<double2*>(vel.p + 4*freeSlot);
+                out[0] = make_double2(freeV.x, freeV.y);
+                out[1] = make_double2(freeV.z, freeInvm);
+            }
+            else storeAtom<NATIVE>(vel, freeSlot, freeV);
+        };
+
+        if (na > A) {                                            // ---- one body larger than a tile: CTA-wide reduction, atoms read in place
+            double* s = S.state + (size_t) m.x;
+            const long long slot0 = RUNS ? sLoc[NB + 4] : 0;
+            auto slotOf = [&](int j) { return RUNS ? slot0 + j : atomSlot(S, S.numFree + a0 + j); };
+            const d4 q = {sSt[0], sSt[NB], sSt[2*NB], sSt[3*NB]};
+            double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int j = tid; j < na; j += kBlock) {
+                const int a = a0 + j;
+                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+                const d3 f = loadAtom<NATIVE>(force, slotOf(j));
+                const d3 t = cross(bodyToSpace(q, d), f);
+                v[0] += f.x; v[1] += f.y; v[2] += f.z; v[3] += t.x; v[4] += t.y; v[5] += t.z;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(kFull, v[k], off);
+            if (lane == 0)
+#pragma unroll
+                for (int k = 0; k < 6; k++) sF[warp*6 + k] = v[k];
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll
+                for (int w = 1; w < kWarps; w++)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) v[k] += sF[w*6 + k];
+                const d3 F = {v[0], v[1], v[2]}, tau = {v[3], v[4], v[5]};
+                d3 p = {sSt[4*NB], sSt[5*NB], sSt[6*NB]};
+                d4 pi = {sSt[7*NB], sSt[8*NB], sSt[9*NB], sSt[10*NB]};
+                d3 vcm, om;
+                bodyPart2(dt, F, tau, sSt[11*NB], d3{sSt[12*NB], sSt[13*NB], sSt[14*NB]}, q, p, pi, vcm, om);
+                storePlane3(s + PL_P*ld, ld, p);
+                storePlane4(s + PL_PI*ld, ld, pi);
+                storePlane3(s + PL_F*ld, ld, F);
+                storePlane3(s + PL_TAU*ld, ld, tau);
+                sAcc[0] = vcm.x; sAcc[1] = vcm.y; sAcc[2] = vcm.z; sAcc[3] = om.x; sAcc[4] = om.y; sAcc[5] = om.z;
+            }
+            __syncthreads();
+            const d3 vcm = {sAcc[0], sAcc[1], sAcc[2]}, om = {sAcc[3], sAcc[4], sAcc[5]};
+            for (int j = tid; j < na; j += kBlock) {
+                const int a = a0 + j;
+                const d3 d = {S.dxyz[a], S.dxyz[a + as], S.dxyz[a + 2*as]};
+                storeAtom<NATIVE>(vel, slotOf(j), atomVelocity(vcm, om, bodyToSpace(q, d)));
+            }
+            if (freeMine) { freeLoad(); freeFinish(); }
+            fenceProxyAsync();
+            __syncthreads();
+            continue;
+        }
+
+        // ---- B: thread per atom: arm delta = A^T(q) d (kept in registers), torque delta x f over the coordinates
+        d3 delta[kLargePerThread];
+        int key[kLargePerThread];
+#pragma unroll
+        for (int u = 0; u < kLargePerThread; u++) {
+            const int j = tid + u*kBlock;
+            if (j < na) {
+                const int k = sKey[j];
+                key[u] = k;
+                const d4 q = {sSt[k], sSt[NB + k], sSt[2*NB + k], sSt[3*NB + k]};
+                delta[u] = bodyToSpace(q, d3{sD[j], sD[L::dp + j], sD[2*L::dp + j]});
+                double* fw = sF + (RUNS ? sFo[k] + j*fs : 3*j);
+                d3 f = {fw[0], fw[fc], fw[2*fc]};
+                if (fixedPoint) {                                // fixed point -> double once, in place (the sums read doubles)
+                    f = {stagedForce<NATIVE>(force, f.x), stagedForce<NATIVE>(force, f.y), stagedForce<NATIVE>(force, f.z)};
+                    fw[0] = f.x; fw[fc] = f.y; fw[2*fc] = f.z;
+                }
+                const d3 t = cross(delta[u], f);
+                sD[j] = t.x; sD[L::dp + j] = t.y; sD[2*L::dp + j] = t.z;
+            }
+        }
+        __syncthreads();
+
+        // ---- B2: thread per (body, component): the column of forces / torques of the body in atom order, four interleaved
+        // partial sums (atoms 0 4 8 .., 1 5 9 .., ..) so that the chain of dependent additions is a quarter of the body
+        if (freeMine) freeLoad();                                // (in flight while the sums run)
+        for (int idx = tid; idx < 6*nb; idx += kBlock) {
+            const int b = idx/6, c = idx - 6*b;
+            const int j0 = sLoc[b] - a0, n = sLoc[b + 1] - sLoc[b];
+            const double* ptr = c < 3 ? sF + (RUNS ? sFo[b] : 0) + j0*fs + c*fc : sD + (c - 3)*L::dp + j0;
+            const int stride = c < 3 ? fs : 1;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int i = 0;
+            for (; i + 4 <= n; i += 4, ptr += 4*stride) {
+                s0 += ptr[0]; s1 += ptr[stride]; s2 += ptr[2*stride]; s3 += ptr[3*stride];
+            }
+            if (i < n) s0 += ptr[0];
+            if (i + 1 < n) s1 += ptr[stride];
+            if (i + 2 < n) s2 += ptr[2*stride];
+            sAcc[c*NB + b] = (s0 + s1) + (s2 + s3);
+        }
+        __syncthreads();
+
+        if (tid < nb) {                                          // ---- C: thread per body, second kick
+            const d3 F = {sAcc[tid], sAcc[NB + tid], sAcc[2*NB + tid]};
+            const d3 tau = {sAcc[3*NB + tid], sAcc[4*NB + tid], sAcc[5*NB + tid]};
+            const d4 q = {sSt[tid], sSt[NB + tid], sSt[2*NB + tid], sSt[3*NB + tid]};
+            d3 p = {sSt[4*NB + tid], sSt[5*NB + tid], sSt[6*NB + tid]};
+            d4 pi = {sSt[7*NB + tid], sSt[8*NB + tid], sSt[9*NB + tid], sSt[10*NB + tid]};
+            const double invm = sSt[11*NB + tid];
+            const d3 invI = {sSt[12*NB + tid], sSt[13*NB + tid], sSt[14*NB + tid]};
+            d3 vcm, om;
+            bodyPart2(dt, F, tau, invm, invI, q, p, pi, vcm, om);
+            double* s = S.state + (size_t) (m.x + tid);
+            storePlane3(s + PL_P*ld, ld, p);
+            storePlane4(s + PL_PI*ld, ld, pi);
+            storePlane3(s + PL_F*ld, ld, F);
+            storePlane3(s + PL_TAU*ld, ld, tau);
+            sAcc[tid] = vcm.x; sAcc[NB + tid] = vcm.y; sAcc[2*NB + tid] = vcm.z;
+            sAcc[3*NB + tid] = om.x; sAcc[4*NB + tid] = om.y; sAcc[5*NB + tid] = om.z;
+        }
+        if (freeMine) freeFinish();
+        __syncthreads();
+
+#pragma unroll
+        for (int u = 0; u < kLargePerThread; u++) {              // ---- D: thread per atom, velocities
+            const int j = tid + u*kBlock;
+            if (j < na) {
+                const int k = key[u];
+                const d3 vcm = {sAcc[k], sAcc[NB + k], sAcc[2*NB + k]};
+                const d3 om = {sAcc[3*NB + k], sAcc[4*NB + k], sAcc[5*NB + k]};
+                const long long slot = RUNS ? j + sRd[k] : (atomLoc != nullptr ? sSlot[j] : S.numFree + a0 + j);
+                storeAtom<NATIVE>(vel, slot, atomVelocity(vcm, om, delta[u]));
+            }
+        }
+        fenceProxyAsync();                                       // the next bulk copies into this stage come after these accesses
+        __syncthreads();                                         // the stage, the ring entry and sAcc are reused
+    }
+    cpWait<0>();
+}
+
+template <bool NATIVE, int NB, bool RUNS>
+cudaError_t launchPart2LargeShape(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, int freePhase, cudaStream_t st) {
+    const size_t smem = (size_t) Part2LargeLayout<NB, RUNS>::total;
+    static LaunchCache cache;
+    int blocks = 0;                                            // persistent CTAs: one full wave, whatever fits
+    cudaError_t e = cache.get(part2LargeKernel<NATIVE, NB, RUNS>, kP2LThreads, smem, blocks);
+    if (e != cudaSuccess) return e;
+    const int resident = S.numSMs*blocks;
+    part2LargeKernel<NATIVE, NB, RUNS><<<S.numTiles < resident ? S.numTiles : resident, kP2LThreads, smem, st>>>(S, dt, pos, vel, force, freePhase);
+    return cudaGetLastError();
+}
+
+template <bool NATIVE, bool RUNS>
+cudaError_t launchPart2LargeRuns(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, int freePhase, cudaStream_t st) {
+    if (S.stageBodies <= 16) return launchPart2LargeShape<NATIVE, 16, RUNS>(S, dt, pos, vel, force, freePhase, st);
+    if (S.stageBodies <= 32) return launchPart2LargeShape<NATIVE, 32, RUNS>(S, dt, pos, vel, force, freePhase, st);
+    if (S.stageBodies <= 64) return launchPart2LargeShape<NATIVE, 64, RUNS>(S, dt, pos, vel, force, freePhase, st);
+    return launchPart2LargeShape<NATIVE, kP2LThreads - 8, RUNS>(S, dt, pos, vel, force, freePhase, st);
+}
+
+// Can the free atoms ride along in part2LargeKernel?  (An even split of the list over the tiles, at most kP2LFree - 1 each.)
+inline bool freeAtomsRide(const DeviceSystem& S) {
+    return S.splitPart1 && S.numTiles > 0 && S.numFree > 0 && !S.noFreeRide && (long long) S.numFree <= (long long) (kP2LFree - 2)*S.numTiles;
+}
+
+// freePhase: 0 = bodies only, 2 / 3 = the free atoms ride along (the caller has checked freeAtomsRide)
+template <bool NATIVE>
+cudaError_t launchPart2Large(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, int freePhase, cudaStream_t st) {
+    // bodies that are runs of the caller's arrays, forces as Vec3 rows or as three 16-byte aligned planes: bulk copies per body
+    const bool rows = force.sa == 3 && force.sc == 1 && force.fmt == FMT_F64;
+    const bool planes = force.sa == 1 && (force.sc & 1) == 0 && force.sc >= S.numSlots && (force.fmt == FMT_F64 || force.fmt == FMT_FORCE_FIXED);
+    if (S.bodyRun != nullptr && !S.noBulkPart2 && (rows || planes) && (reinterpret_cast<size_t>(force.p) & 15) == 0)
+        return launchPart2LargeRuns<NATIVE, true>(S, dt, pos, vel, force, freePhase, st);
+    return launchPart2LargeRuns<NATIVE, false>(S, dt, pos, vel, force, freePhase, st);
+}
 
 // STAGES = 2: the next tile is staged while the current one is processed (exact rotation: registers allow two CTAs of
 // 128 threads per SM anyway).  STAGES = 1: the next tile is requested when the current one is finished and the
@@ -1199,38 +1359,63 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
 // the persistent body kernels.  PHASE 1 = part 1 (half kick + drift), 2 = part 2 (half kick + constraint
 // displacement), 3 = part 2 of this step followed by part 1 of the next.
 // ------------------------------------------------------------------------------------------------
-template <int PHASE, bool NATIVE>
+// PER atoms per thread (k, k + blockDim, ...): every load of all of them is issued before the first is used - the side-stream
+// launches get one or two small CTAs per SM next to a persistent body kernel and live on the loads they keep in flight.
+template <int PHASE, bool NATIVE, int PER>
 __global__ void __launch_bounds__(256) freeAtomsKernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel,
                                                        const AtomView force) {
-    const int k = blockIdx.x*blockDim.x + threadIdx.x;
-    if (k >= S.numFree) return;
-    const long long gi = atomSlot(S, k);
-    const d3 f = loadAtom<NATIVE>(force, gi);
-    const double invm = S.freeInvMass[k];
-    d3 x = loadAtom<NATIVE>(pos, gi), v = loadAtom<NATIVE>(vel, gi);
-    if (PHASE & 2) freePart2(dt, f, invm, x, loadPlane3(S.savedPos + k, S.freeStride), v);
-    if (PHASE & 1) {
-        freePart1(dt, f, invm, x, v);
-        storeAtom<NATIVE>(pos, gi, x);
-        storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x));
+    const int k0 = blockIdx.x*blockDim.x*PER + threadIdx.x;
+    long long gi[PER];
+    d3 f[PER], x[PER], v[PER], saved[PER];
+    double invm[PER];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        const int k = k0 + u*blockDim.x;
+        gi[u] = k < S.numFree ? atomSlot(S, k) : 0;
     }
-    if (!NATIVE && vel.fmt == FMT_REAL4_F64 && S.atomInvMass != nullptr) {      // whole double4, w = 1/m (see part2Part1Kernel)
-        double2* out = reinterpret_cast<double2*>(vel.p + 4*gi);
-        out[0] = make_double2(v.x, v.y);
-        out[1] = make_double2(v.z, invm);
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        const int k = k0 + u*blockDim.x;
+        if (k < S.numFree) {
+            f[u] = loadAtom<NATIVE>(force, gi[u]);
+            invm[u] = S.freeInvMass[k];
+            x[u] = loadAtom<NATIVE>(pos, gi[u]);
+            v[u] = loadAtom<NATIVE>(vel, gi[u]);
+            if (PHASE & 2) saved[u] = loadPlane3(S.savedPos + k, S.freeStride);
+        }
     }
-    else storeAtom<NATIVE>(vel, gi, v);
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        const int k = k0 + u*blockDim.x;
+        if (k >= S.numFree) continue;
+        if (PHASE & 2) freePart2(dt, f[u], invm[u], x[u], saved[u], v[u]);
+        if (PHASE & 1) {
+            freePart1(dt, f[u], invm[u], x[u], v[u]);
+            storeAtom<NATIVE>(pos, gi[u], x[u]);
+            storePlane3(S.savedPos + k, S.freeStride, asStored<NATIVE>(pos, x[u]));
+        }
+        if (!NATIVE && vel.fmt == FMT_REAL4_F64 && S.atomInvMass != nullptr) {      // whole double4, w = 1/m (see part2Part1Kernel)
+            double2* out = reinterpret_cast<double2*>(vel.p + 4*gi[u]);
+            out[0] = make_double2(v[u].x, v[u].y);
+            out[1] = make_double2(v[u].z, invm[u]);
+        }
+        else storeAtom<NATIVE>(vel, gi[u], v[u]);
+    }
 }
 
 #ifndef RBK_SIDE_FREE_THREADS
 #define RBK_SIDE_FREE_THREADS 64
 #endif
 constexpr int kSideFreeThreads = RBK_SIDE_FREE_THREADS;                // CTA size of the free-atom launch that shares the SMs with the body kernels
+#ifndef RBK_SIDE_FREE_PER
+#define RBK_SIDE_FREE_PER 2
+#endif
+constexpr int kSideFreePer = RBK_SIDE_FREE_PER;                        // ... and its atoms per thread
 
 template <int PHASE, bool NATIVE>
 cudaError_t launchFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, cudaStream_t st) {
     if (S.numFree == 0) return cudaSuccess;
-    freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
+    freeAtomsKernel<PHASE, NATIVE, 1><<<(S.numFree + 255)/256, 256, 0, st>>>(S, dt, pos, vel, force);
     return cudaGetLastError();
 }
 
@@ -1245,7 +1430,8 @@ inline cudaError_t sideFork(const SideStream* side, cudaStream_t st) {
 }
 template <int PHASE, bool NATIVE>
 cudaError_t sideFree(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, const SideStream* side) {
-    freeAtomsKernel<PHASE, NATIVE><<<(S.numFree + kSideFreeThreads - 1)/kSideFreeThreads, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
+    constexpr int perBlock = kSideFreeThreads*kSideFreePer;
+    freeAtomsKernel<PHASE, NATIVE, kSideFreePer><<<(S.numFree + perBlock - 1)/perBlock, kSideFreeThreads, 0, side->stream>>>(S, dt, pos, vel, force);
     const cudaError_t e = cudaGetLastError();
     return e != cudaSuccess ? e : cudaEventRecord(side->join, side->stream);
 }
@@ -1465,7 +1651,9 @@ cudaError_t launchPart1Delta(const DeviceSystem& S, double dt, AtomView pos, Ato
 namespace {
 template <bool NATIVE>
 cudaError_t launchPart2Formats(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st,
-                               const SideStream* side = nullptr) {
+                               const SideStream* side = nullptr, int ridePhase = 2) {
+    // large bodies: the free atoms ride along in the body kernel when their list splits into small enough slices
+    if (freeAtoms && freeAtomsRide(S)) return launchPart2Large<NATIVE>(S, dt, pos, vel, force, ridePhase, st);
     const bool overlap = freeAtoms && sideUsable(S, side);
     if (overlap) {
         cudaError_t e = sideFork(side, st);
@@ -1476,7 +1664,7 @@ cudaError_t launchPart2Formats(const DeviceSystem& S, double dt, AtomView pos, A
         if (e != cudaSuccess) return e;
     }
     if (S.numTiles > 0 && S.splitPart1) {
-        cudaError_t e = launchPart2Large<NATIVE>(S, dt, pos, vel, force, st);
+        cudaError_t e = launchPart2Large<NATIVE>(S, dt, pos, vel, force, 0, st);
         if (e != cudaSuccess || !overlap) return e;
         e = sideFree<2, NATIVE>(S, dt, pos, vel, force, side);
         return e != cudaSuccess ? e : sideJoin(side, st);
@@ -1502,6 +1690,12 @@ cudaError_t launchPart2Part1(const DeviceSystem& S, double dt, AtomView pos, Ato
         // free atoms' small CTAs run in the registers the body kernels leave unused and in their tails (disjoint atoms,
         // no data dependence); the caller's stream continues when both are done.
         const bool native = nativeIO(pos, vel, force);
+        if (freeAtomsRide(S)) {                                // ... or ride along in the body kernel, both halves at once
+            cudaError_t e = native ? launchPart2Formats<true>(S, dt, pos, vel, force, true, st, nullptr, 3)
+                                   : launchPart2Formats<false>(S, dt, pos, vel, force, true, st, nullptr, 3);
+            if (e != cudaSuccess) return e;
+            return native ? launchPart1Formats<true>(S, dt, pos, vel, force, false, st) : launchPart1Formats<false>(S, dt, pos, vel, force, false, st);
+        }
         const bool overlap = sideUsable(S, side);
         if (overlap) {
             cudaError_t e = sideFork(side, st);
@@ -1542,5 +1736,13 @@ cudaError_t launchKinetic(const DeviceSystem& S, AtomView vel, double* partial, 
 }
 
 int part1LaunchesPerStep(const DeviceSystem& S) { return (S.splitPart1 && S.numTiles > 0) ? 2 : 1; }
+
+void launchesPerCall(const DeviceSystem& S, int out[3]) {
+    const int bodies = S.numTiles > 0, freeAtoms = S.numFree > 0, large = bodies && S.splitPart1;
+    const int ride = freeAtomsRide(S);                         // large bodies: the free atoms ride along in part2LargeKernel
+    out[0] = freeAtoms + (large ? 2 : bodies);                 // [free] + rotation kernel + atomPositionKernel | one kernel
+    out[1] = (freeAtoms && !ride) + bodies;
+    out[2] = (freeAtoms && !ride) + (large ? 3 : bodies);
+}
 
 } // namespace rbk

@@ -131,6 +131,12 @@ class DeviceRigidBodySystem:
         check(self.lib.rbk_debug_series_order(self.h, _i(out), _stream(stream)))
         return int(out[0])
 
+    def launches_per_call(self):
+        """Kernel launches of part1, part2, part2_part1 on this system (rbk_debug_launches_per_call)."""
+        out = np.zeros(3, np.int32)
+        check(self.lib.rbk_debug_launches_per_call(self.h, _i(out)))
+        return tuple(int(x) for x in out)
+
     # ---- device
     def upload(self, stream=None):
         check(self.lib.rbk_upload(self.h, _stream(stream)))

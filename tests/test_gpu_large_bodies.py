@@ -75,6 +75,74 @@ def test_bodies_at_and_over_the_tile_capacity(mode):
     _run_pair(sysd, mode, "soa", False, fused=False, dt=0.0005)
 
 
+@pytest.mark.parametrize("bulk", [True, False])
+@pytest.mark.parametrize("layout,n_free", [("vec3", 400), ("soa", 400), ("soa", 401)])
+def test_bodies_as_runs_of_slots_whole_molecules_permuted(layout, n_free, bulk, monkeypatch):
+    """Whole bodies permuted (every body stays a run of consecutive slots, in any order, starting at even and odd slots):
+    part2LargeRunsKernel - TMA bulk copies per body, serial sums - and, with RBK_NO_BULK_PART2=1, the per-atom request
+    kernel on the same arrays.  SoA planes with an even stride take the three-copies-per-body path, with an odd stride
+    (misaligned planes) the per-atom kernel whatever the switch says."""
+    monkeypatch.setenv("RBK_NO_BULK_PART2", "0" if bulk else "1")
+    rng = np.random.Generator(np.random.Philox(key=311))
+    sysd = _system(rng.integers(3, 61, size=700), n_free, seed=312)
+    if (len(sysd["masses"]) % 2 == 1) != (n_free == 401):
+        sysd = _system(np.concatenate([rng.integers(3, 61, size=700), [4]]), n_free, seed=312)
+    for mode, fused in ((0, True), (3, False)):
+        _run_pair(sysd, mode, layout, "molecules", fused=fused, tol=5e-10)
+
+
+@pytest.mark.parametrize("last", [3, 4, 60])
+def test_last_run_ends_with_the_array(last):
+    """No free atoms, identity atom map, the last body's forces end exactly where the Vec3 array ends: when that is at an odd
+    8-byte word, the bulk copy stops 16 bytes early and the last word comes by cp.async - nothing is read past the array
+    (compute-sanitizer run: tools/gpu_sanitize.sh)."""
+    rng = np.random.Generator(np.random.Philox(key=313))
+    for extra in (0, 1):
+        sizes = np.concatenate([rng.integers(9, 61, size=300), [3 + extra, last]])
+        sysd = _system(sizes, 0, seed=314)
+        _run_pair(sysd, 0, "vec3", False, fused=True, tol=5e-10)
+
+
+def test_sums_follow_the_atom_order():
+    """The per-body force / torque sums add the atoms in the reference's order (RigidBody::forceAndTorque,
+    openmmapi/src/RigidBody.cpp:174-183) up to the association into chunks of consecutive atoms: the body force agrees with
+    the oracle's to a few ulps of the largest term, whatever the layout the forces came in."""
+    rng = np.random.Generator(np.random.Philox(key=315))
+    sysd = _system(rng.integers(9, 61, size=400), 100, seed=316)
+    o = CpuStepper("oracle", sysd["bodyIndices"], sysd["masses"], 0)
+    common.init_like_reference(o, sysd)
+    o.step(0.001, 1)
+    ob = o.bodies()
+    ref = None
+    for layout, shuffle in (("vec3", False), ("soa", True), ("vec3", "molecules")):
+        s = GpuStepper(sysd["bodyIndices"], sysd["masses"], 0, layout=layout, shuffle=shuffle)
+        common.init_like_reference(s, sysd)
+        s.step(0.001, 1)
+        b = s.bodies()
+        assert common.rel_inf(b["force"], ob["force"]) <= 1e-14
+        assert common.rel_inf(b["torque"], ob["torque"]) <= 2e-12
+        if ref is None:
+            ref = b
+        else:
+            assert np.array_equal(b["force"], ref["force"]) and np.array_equal(b["torque"], ref["torque"])
+        s.close()
+
+
+@pytest.mark.parametrize("layout,shuffle", [("vec3", False), ("vec3", "molecules"), ("soa", True)])
+def test_free_atoms_ride_along_in_the_body_kernel(layout, shuffle, monkeypatch):
+    """Large-body systems with few enough free atoms per tile take them along in part2LargeKernel (Part 2, and Part 2 + Part 1
+    in fused steps) instead of launching freeAtomsKernel: same arithmetic, bit-identical arrays, both against the oracle."""
+    rng = np.random.Generator(np.random.Philox(key=321))
+    sysd = common.synth.mixed_system(900, 2300, seed=322)
+    outs = []
+    for ride in ("0", "1"):
+        monkeypatch.setenv("RBK_NO_FREE_RIDE", ride)
+        for fused in (True, False):
+            outs.append(_run_pair(sysd, 0, layout, shuffle, fused=fused, steps=4))
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1])
+
+
 def test_bit_reproducible_large_bodies():
     rng = np.random.Generator(np.random.Philox(key=305))
     sysd = _system(rng.integers(3, 61, size=800), 300, seed=306)

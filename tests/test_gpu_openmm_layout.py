@@ -137,7 +137,8 @@ class OpenMMArrays:
 
 
 @pytest.mark.parametrize("precision", [RBK_OPENMM_MIXED, RBK_OPENMM_DOUBLE])
-@pytest.mark.parametrize("case,mode", [("water", 0), ("water", 3), ("small_mixed", 0), ("medium_mixed", 0), ("large_mixed", 0)])
+@pytest.mark.parametrize("case,mode", [("water", 0), ("water", 3), ("small_mixed", 0), ("medium_mixed", 0), ("large_mixed", 0),
+                                       ("large_mixed_molecules", 0), ("large_mixed_molecules", 2)])
 def test_openmm_fused_stepping_and_reorder_vs_oracle(case, mode, precision):
     """The CUDA-platform flow on the OpenMM formats against the CPU ORACLE (not against this repo's own fp64 path):
     part1, [rbk_part2_part1_openmm, atoms reordered every other step through rbk_reorder_openmm] x n, part2 - with the
@@ -166,8 +167,9 @@ def test_openmm_fused_stepping_and_reorder_vs_oracle(case, mode, precision):
     s = build(sysd, mode)
     index = s.atom_index()
     # water: whole molecules are permuted, as OpenMM's reorderAtoms does (the handle re-sorts its bodies each time);
-    # the other cases: every atom on its own, the general gather path
-    permutation = (lambda: common.molecule_permutation(sysd["bodyIndices"], int(rng.integers(1 << 30)))) if case == "water" else (lambda: rng.permutation(n))
+    # large_mixed_molecules: the same for bodies of 3-60 atoms - every body stays a run of slots and large-body Part 2 moves
+    # whole runs of the fixed-point force planes with bulk copies; the other cases: every atom on its own, the general gather path
+    permutation = (lambda: common.molecule_permutation(sysd["bodyIndices"], int(rng.integers(1 << 30)))) if case in ("water", "large_mixed_molecules") else (lambda: rng.permutation(n))
     A = OpenMMArrays(sysd, permutation(), padded, precision, Fq)
     s.set_atom_location(A.order[index].astype(np.int32))
     s.part1_openmm(dt, *A.args())
