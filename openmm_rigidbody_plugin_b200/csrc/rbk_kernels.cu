@@ -556,6 +556,20 @@ __device__ __forceinline__ void bulkCopyS(unsigned smem, const void* gmem, unsig
 __device__ __forceinline__ void mbarArriveS(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+__device__ __forceinline__ void cpAsync16s(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void mbarWaitS(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void mbarExpectTxS(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
@@ -597,13 +611,10 @@ __global__ void __maxnreg__(RBK_P2L_MAXNREG) part2LargeKernel(const DeviceSystem
     auto freeFirst = [&](int t) { return t >= numTiles ? S.numFree : (int) (((unsigned long long) t*freeRatio) >> 20); };
 
     // per-body atom offsets (one more than bodies: the end of the last one) and first slots | atom slots of a tile -> ring entry r
-    auto requestBodies = [&](int4 m, int r, int t) {
+    auto requestBodies = [&](int4 m, int r, int2 freeRange) {
         const unsigned dst = sBase + L::ring + (r*L::ringInts + tid)*4;
         if (tid <= m.y) cpAsync4s(dst, S.loc + m.x + tid);
-        if (freePhase && atomLoc != nullptr) {
-            const int k0 = freeFirst(t);
-            if (tid < freeFirst(t + 1) - k0) cpAsync4s(dst + L::ringFree*4, atomLoc + k0 + tid);
-        }
+        if (freePhase && atomLoc != nullptr && tid < freeRange.y - freeRange.x) cpAsync4s(dst + L::ringFree*4, atomLoc + freeRange.x + tid);
         if (RUNS) {
             if (tid < m.y) cpAsync4s(dst + (NB + 4)*4, S.bodyRun + m.x + tid);
         }
@@ -697,8 +708,11 @@ __global__ void __maxnreg__(RBK_P2L_MAXNREG) part2LargeKernel(const DeviceSystem
     }
     if (tid < 3 && tile0 + tid*G < numTiles) sMeta[tid] = S.tileMeta[tile0 + tid*G];
     __syncthreads();
-    requestBodies(sMeta[0], 0, tile0);
-    if (tile0 + G < numTiles) requestBodies(sMeta[1], 1, tile0 + G);
+    // free-atom ranges of this CTA's current, next and next-but-one tile (rolled along: two evaluations per tile)
+    auto freeRangeOf = [&](int t) { return make_int2(freeFirst(t), freeFirst(t + 1)); };
+    int2 freeCur = freeRangeOf(tile0), freeNext = freeRangeOf(tile0 + G), freeAfter = freeRangeOf(tile0 + 2*G);
+    requestBodies(sMeta[0], 0, freeCur);
+    if (tile0 + G < numTiles) requestBodies(sMeta[1], 1, freeNext);
     cpCommit();
     cpWait<0>();
     __syncthreads();
@@ -709,16 +723,16 @@ __global__ void __maxnreg__(RBK_P2L_MAXNREG) part2LargeKernel(const DeviceSystem
         const int cur = it & 1;
         const int r1 = r0 == 2 ? 0 : r0 + 1, r2 = r1 == 2 ? 0 : r1 + 1;
         cpWait<0>();                                             // state (and forces) of tile `it`, the bodies of it+1, the descriptor of it+2 have landed
-        mbarWait(&bar[cur], (it >> 1) & 1);                      // ... and its coordinates, body bytes (and forces)
+        mbarWaitS(sBase + L::bar + 8*cur, (it >> 1) & 1);        // ... and its coordinates, body bytes (and forces)
         __syncthreads();
         const int4 m = sMeta[it & 3];
         if (tile + G < numTiles) requestData(sMeta[(it + 1) & 3], r1, cur ^ 1);
-        if (tile + 2*G < numTiles) requestBodies(sMeta[(it + 2) & 3], r2, tile + 2*G);
-        if (tid == 0 && tile + 3*G < numTiles) cpAsync16(&sMeta[(it + 3) & 3], S.tileMeta + tile + 3*G);
+        if (tile + 2*G < numTiles) requestBodies(sMeta[(it + 2) & 3], r2, freeAfter);
+        if (tid == 0 && tile + 3*G < numTiles) cpAsync16s(sBase + L::meta + 16*((it + 3) & 3), S.tileMeta + tile + 3*G);
         cpCommit();
         if (freePhase && tile + G < numTiles) {                  // the free atoms of the NEXT tile: towards L2 now, loaded a tile later
-            const int k = freeFirst(tile + G) + (kBlock - 1 - tid);
-            if (k < freeFirst(tile + G + 1)) {
+            const int k = freeNext.x + (kBlock - 1 - tid);
+            if (k < freeNext.y) {
                 const long long slot = atomLoc != nullptr ? sRing[r1*L::ringInts + L::ringFree + kBlock - 1 - tid] : k;
                 prefetchAtom(force, slot);
                 prefetchAtom(pos, slot);
@@ -741,8 +755,11 @@ __global__ void __maxnreg__(RBK_P2L_MAXNREG) part2LargeKernel(const DeviceSystem
         r0 = r1;
 
         // the free atom this thread takes along (the CTA's last threads, one each)
-        const int freeK = freePhase ? freeFirst(tile) + (kBlock - 1 - tid) : 0;
-        const bool freeMine = freePhase && freeK < freeFirst(tile + 1);
+        const int freeK = freeCur.x + (kBlock - 1 - tid);
+        const bool freeMine = freePhase && freeK < freeCur.y;
+        freeCur = freeNext;
+        freeNext = freeAfter;
+        if (freePhase) freeAfter = freeRangeOf(tile + 3*G);
         long long freeSlot = 0;
         d3 freeF, freeX, freeV, freeSaved;
         double freeInvm = 0.0;
