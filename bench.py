@@ -601,12 +601,14 @@ def run_b200_arm(args):
     # per body: state planes read + written (8 B each) + 4 B prefix offset; per atom: body-frame coordinates 24, body byte 1,
     # [slot 4], force, velocity, position in this layout; per free atom: v, f, x, 1/m (+ savedPos) in, v, x (+ savedPos) out
     p1_bytes = (192 + 4 + 112) * nB + (24 + 1 + loc4 + wpos) * nA + (loc4 + 2 * wvel + rfor + 2 * wpos + 8 + 24) * nF
-    p2_bytes = (120 + 4 + 104) * nB + (24 + 1 + loc4 + rfor + wvel) * nA + (loc4 + 2 * wvel + rfor + wpos + 24 + 8) * nF
+    p2_bytes = (120 + 4 + 104) * nB + (24 + 1 + (loc4 if (not large or args.shuffle == "atoms") else 0) + rfor + wvel) * nA + (loc4 + 2 * wvel + rfor + wpos + 24 + 8) * nF
     free_pp = (loc4 + 2 * wvel + rfor + 2 * wpos + 24 + 8 + 24) * nF
     if large:
         # one rbk_part2_part1 call = part2LargeKernel (state in 120 + 4, out 104; per atom d, byte, slot, f in, v out) +
         # rotation kernel (in 192, out 112) + atomPositionKernel (r, q in 56; per atom d, byte, slot in, x out) + free atoms
-        pp_bytes = (124 + 104 + 192 + 112 + 56) * nB + (2 * (24 + 1 + loc4) + rfor + wvel + wpos) * nA + free_pp
+        # (bodies that are runs of slots - everything but --shuffle atoms: part2LargeKernel reads one slot per body, not per atom)
+        loc4_p2 = loc4 if args.shuffle == "atoms" else 0
+        pp_bytes = (124 + 104 + 192 + 112 + 56) * nB + (2 * (24 + 1) + loc4 + loc4_p2 + rfor + wvel + wpos) * nA + free_pp
     else:
         # the one-pass kernel: r p q pi 1/m 1/I in (144 + 4), r p q pi out (112) [+ F tau out (48) when the stores are kept]
         ft = 0 if system_lazy_ft() else 48

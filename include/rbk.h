@@ -42,8 +42,9 @@ const char* rbk_last_error(void);
 /* Diagnostics: host<->device copies issued by librbk in this process so far - out[4] = H2D calls, H2D bytes, D2H calls,
  * D2H bytes.  The device entry points (rbk_part1/2*, rbk_part2_part1*, rbk_free_*) must not move any of them. */
 int         rbk_debug_copy_counters(const rbk_system* sys, long long* out);
-/* Diagnostics: the Taylor order the mode-0 water kernels will use at their next launch (11, 13 or 16; DESIGN.md, "series
- * ladder").  The choice is made on the device from the previous launch's convergence statistics. */
+/* Diagnostics: the Taylor order the mode-0 kernels will use at their next launch: 11, 13 or 16 for systems of bodies of <= 4
+ * atoms ("series ladder": chosen on the device from the previous launch's convergence statistics), the fixed order
+ * 12 otherwise. */
 int         rbk_debug_series_order(rbk_system* sys, int* out, void* stream);
 /* Diagnostics: kernel launches one call makes on the current system with fp64 arrays - out[3] = rbk_part1, rbk_part2,
  * rbk_part2_part1 (launch structure: DESIGN.md section 4; benchmarks report their launch counts from this). */
@@ -126,9 +127,10 @@ int rbk_part2(rbk_system* sys, double dt, const double* pos, double* vel, const 
  * this call (the next rbk_part2 or rbk_part2_part1 recomputes them before anything reads them).  On return `vel` holds the velocities at the
  * end of step k and `pos` the positions after Part 1 of step k+1 (exactly the state the reference is in when it
  * evaluates forces).  Stream semantics: everything is ordered after the work already queued on `stream`, and `stream`
- * continues only when the whole call's work is done; for systems of large bodies WITH free atoms the free atoms are
- * integrated (here and in rbk_part1 / rbk_part2) on a second stream owned by the handle, forked from and joined back to `stream` with events (no host
- * synchronisation; the pattern is legal under stream capture). */
+ * continues only when the whole call's work is done; for systems of large bodies WITH free atoms the free atoms either
+ * ride along in the bodies' Part 2 kernel (here and in rbk_part2, when their list splits into at most 62 per atom tile) or are
+ * integrated on a second stream owned by the handle (rbk_part1; all three calls otherwise), forked from and joined back to
+ * `stream` with events (no host synchronisation; the pattern is legal under stream capture). */
 int rbk_part2_part1(rbk_system* sys, double dt, double* pos, double* vel, const double* force,
                     int layout, long long stride, void* stream);
 

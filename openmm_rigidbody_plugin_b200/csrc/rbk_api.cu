@@ -479,6 +479,10 @@ int rbk_version(void) { return RBK_VERSION; }
 int rbk_debug_series_order(rbk_system* sys, int* out, void* stream) {
     if (!sys || !out) return fail(RBK_EINVAL, "rbk_debug_series_order: NULL argument");
     if (!sys->allocated) return fail(RBK_ESTATE, "rbk_debug_series_order: call rbk_upload first");
+    if (sys->dev.numWarpTiles == 0) {                          // no one-warp tiles: the kernels of this system run the fixed order
+        *out = rbk::kSeriesOrder;
+        return RBK_OK;
+    }
     rbk::SeriesControl ctl;
     RBK_CUDA(cudaMemcpyAsync(&ctl, sys->dSeriesCtl, sizeof(ctl), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
     RBK_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
