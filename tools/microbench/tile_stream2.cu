@@ -2,6 +2,7 @@
 //   MODE 0  by per-lane 8-byte stores (three per atom and array, rows of 24 bytes)            - what the kernels do
 //   MODE 1  through shared memory and ONE bulk store per array and tile (cp.async.bulk.global.shared::cta, 2304 bytes)
 //   MODE 2  not at all (reads + state writes only), MODE 3 no reads of forces / coordinates (writes only) - the two halves
+//   MODE 4  every lane writes the 72 contiguous bytes of ITS body's three atoms: four 16-byte stores + one 8-byte store per array
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tile_stream2 tile_stream2.cu && ./tile_stream2
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -41,6 +42,25 @@ __global__ void __launch_bounds__(32, 8) stream(double* state, size_t ld, const 
                 const size_t at = (size_t) t*96 + j*32 + lane;
 #pragma unroll
                 for (int c = 0; c < 3; c++) { pos[3*at + c] = a[3*j + c] + g[3*j + c]; vel[3*at + c] = a[3*j + c] - g[3*j + c]; }
+            }
+        }
+        else if (MODE == 4) {
+            double* const out[2] = {pos + (size_t) t*288 + 9*lane, vel + (size_t) t*288 + 9*lane};
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                double x[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) x[k] = w ? a[k] - g[k] : a[k] + g[k];
+                if (lane & 1) {                                   // 72*lane is 8 mod 16: one word, then four aligned pairs
+                    out[w][0] = x[0];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) *reinterpret_cast<double2*>(out[w] + 1 + 2*k) = make_double2(x[1 + 2*k], x[2 + 2*k]);
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) *reinterpret_cast<double2*>(out[w] + 2*k) = make_double2(x[2*k], x[2*k + 1]);
+                    out[w][8] = x[8];
+                }
             }
         }
         else if (MODE == 1) {
@@ -99,6 +119,7 @@ int main() {
     run<1>("bulk stores from shared memory", st + in + out, state, ld, d, as, f, pos, vel, numTiles);
     run<2>("no atom outputs", st + in, state, ld, d, as, f, pos, vel, numTiles);
     run<3>("no atom inputs", st + out, state, ld, d, as, f, pos, vel, numTiles);
+    run<4>("72 contiguous bytes per lane, 16-byte stores", st + in + out, state, ld, d, as, f, pos, vel, numTiles);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
