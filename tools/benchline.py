@@ -1,5 +1,5 @@
-import json,sys
+"""stdin -> the JSON line(s) a bench.py run printed (launchers such as torchrun / NCCL add lines of their own around it)."""
+import sys
 for line in sys.stdin:
-    line=line.strip()
-    if not line.startswith("{"): continue
-    d=json.loads(line); print(d["value"], d["ms_per_step"], {k:round(v["ms"],4) for k,v in d["roofline"]["kernels"].items()}, round(d["roofline"]["step"]["frac"],3))
+    if line.lstrip().startswith("{"):
+        sys.stdout.write(line.strip() + "\n")
