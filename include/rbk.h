@@ -43,8 +43,8 @@ const char* rbk_last_error(void);
  * D2H bytes.  The device entry points (rbk_part1/2*, rbk_part2_part1*, rbk_free_*) must not move any of them. */
 int         rbk_debug_copy_counters(const rbk_system* sys, long long* out);
 /* Diagnostics: the Taylor order the mode-0 kernels will use at their next launch: 11, 13 or 16 for systems of bodies of <= 4
- * atoms ("series ladder": chosen on the device from the previous launch's convergence statistics), the fixed order
- * 12 otherwise. */
+ * atoms, 12, 13 or 16 for systems of large bodies ("series ladder": chosen on the device from the previous launch's
+ * convergence statistics), the fixed order 12 otherwise. */
 int         rbk_debug_series_order(rbk_system* sys, int* out, void* stream);
 /* Diagnostics: kernel launches one call makes on the current system with fp64 arrays - out[3] = rbk_part1, rbk_part2,
  * rbk_part2_part1 (launch structure: DESIGN.md section 4; benchmarks report their launch counts from this). */

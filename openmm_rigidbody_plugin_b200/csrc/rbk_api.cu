@@ -305,7 +305,7 @@ int allocateDevice(rbk_system* sys, cudaStream_t st) {
     RBK_CUDA(cudaMemsetAsync(sys->dTileCounter, 0, sizeof(int), st));
     d.tileCounter = sys->dTileCounter;
     RBK_CUDA(devAlloc(sys->dSeriesCtl, 1));
-    const rbk::SeriesControl ctl0 = {1, 0u, 0u, 0u};           // start on the middle rung (order 13); the kernels move it
+    const rbk::SeriesControl ctl0 = {1, 0u, 0u, 0u, 1};           // start on the middle rung (order 13); the kernels move it
     RBK_CUDA(copyAsync(sys->dSeriesCtl, &ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, st));
     RBK_CUDA(cudaStreamSynchronize(st));
     d.seriesCtl = sys->dSeriesCtl;
@@ -479,14 +479,16 @@ int rbk_version(void) { return RBK_VERSION; }
 int rbk_debug_series_order(rbk_system* sys, int* out, void* stream) {
     if (!sys || !out) return fail(RBK_EINVAL, "rbk_debug_series_order: NULL argument");
     if (!sys->allocated) return fail(RBK_ESTATE, "rbk_debug_series_order: call rbk_upload first");
-    if (sys->dev.numWarpTiles == 0) {                          // no one-warp tiles: the kernels of this system run the fixed order
+    const bool bodyTiles = sys->dev.splitPart1 && sys->dev.numTiles > 0;      // large bodies: the rotation kernel's ladder 12 / 13 / 16
+    if (sys->dev.numWarpTiles == 0 && !bodyTiles) {            // four-warp atom tiles: the fixed order
         *out = rbk::kSeriesOrder;
         return RBK_OK;
     }
     rbk::SeriesControl ctl;
     RBK_CUDA(cudaMemcpyAsync(&ctl, sys->dSeriesCtl, sizeof(ctl), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
     RBK_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
-    *out = rbk::kSeriesLadder[ctl.rung < 0 ? 0 : (ctl.rung > 2 ? 2 : ctl.rung)];
+    const int rung = ctl.rung < 0 ? 0 : (ctl.rung > 2 ? 2 : ctl.rung);
+    *out = bodyTiles && rung == 0 ? rbk::kSeriesOrder : rbk::kSeriesLadder[rung];
     return RBK_OK;
 }
 

@@ -49,6 +49,8 @@ struct TileMaps;
 struct SeriesControl {
     int rung;
     unsigned done, fails, lower;
+    int published;               // the value last written to the host's copy of the rung (mapped pinned memory): written again only
+                                 // when it changes - a store to host memory at the end of a kernel costs ~3 us of PCIe round trip
 };
 
 struct DeviceSystem {

@@ -121,9 +121,16 @@ __device__ __forceinline__ int globalPlane(int k) {
     return k < 14 ? k : (k < 17 ? (int) PL_F + (k - 14) : (k < 20 ? (int) PL_TAU + (k - 17) : (k == 20 ? (int) PL_INVM : (int) PL_INVI + (k - 21))));
 }
 
-template <bool EXACT, bool FUSED, bool NATIVE>
+// RUNG >= 0 (exact rotation, body-tile kernel of large-body systems): ONE rung of a series ladder of orders 12 / 13 / 16
+// compiled in, picked by the launcher from the host's copy of the rung (see part2Part1Kernel, LADDER); the kernel counts the
+// bodies whose check failed at its order / would fail one rung lower and its last CTA moves the rung.  The lowest rung is the
+// fixed order of the other four-warp kernels (12, not the water kernels' 11): in a 128-thread tile a body on the retry path
+// holds up its whole CTA, so failures cost more than a lower order saves.  RUNG < 0: fixed order, no control block.
+template <bool EXACT, bool FUSED, bool NATIVE, int RUNG = -1>
 __global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT)
 part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
+    static_assert(RUNG < 0 || (EXACT && !FUSED), "the ladder variant is the exact-rotation body-tile kernel");
+    unsigned ladderFails = 0u, ladderLower = 0u;               // bodies of this thread (RUNG >= 0)
     extern __shared__ __align__(128) unsigned char smemRaw[];
     Part1Smem& sm = *reinterpret_cast<Part1Smem*>(smemRaw);
     const int tid = threadIdx.x;
@@ -197,7 +204,18 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
                 const d3 tau = {B[17][tid], B[18][tid], B[19][tid]};
                 const double invm = B[20][tid];
                 const d3 invI = {B[21][tid], B[22][tid], B[23][tid]};
-                bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
+                if (RUNG >= 0) {
+                    unsigned flags = 0u;
+                    p = p + F*(0.5*dt);
+                    pi = pi + quatC(q, tau)*dt;
+                    r = r + p*(invm*dt);
+                    if (RUNG == 0) exactRotationRung<kSeriesOrder, 0>(dt, invI, q, pi, flags);
+                    else if (RUNG == 1) exactRotationRung<13, kSeriesOrder>(dt, invI, q, pi, flags);
+                    else exactRotationRung<16, 13>(dt, invI, q, pi, flags);
+                    ladderFails += flags & 1u;
+                    ladderLower += (flags >> 1) & 1u;
+                }
+                else bodyPart1<EXACT>(dt, S.rotationMode, F, tau, invm, invI, r, p, q, pi);
                 double* s = S.state + (size_t) (m.x + tid);
                 storePlane3(s + PL_R*ld, ld, r);
                 storePlane3(s + PL_P*ld, ld, p);
@@ -235,7 +253,38 @@ part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const Ato
         }
         cpWait<0>();
     }
-
+    if (RUNG >= 0 && tile0 < numTiles) {
+        // publish the counts; the last CTA of the launch moves the rung for the next launch (same policy as part2Part1Kernel)
+        SeriesControl* c = S.seriesCtl;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            ladderFails += __shfl_xor_sync(kFull, ladderFails, off);
+            ladderLower += __shfl_xor_sync(kFull, ladderLower, off);
+        }
+        if ((tid & 31) == 0 && (ladderFails | ladderLower)) {
+            if (ladderFails) atomicAdd(&c->fails, ladderFails);
+            if (ladderLower) atomicAdd(&c->lower, ladderLower);
+            __threadfence();                                   // the counts are visible before this CTA's `done`
+        }
+        __syncthreads();
+        if (tid == 0 && atomicAdd(&c->done, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const volatile unsigned* counts = &c->fails;       // (both loads in flight together: one round trip at the launch's tail)
+            const unsigned fails = counts[0], lower = counts[1];
+            const double n = (double) S.numBodies;
+            int next = RUNG;
+            if ((double) fails > 4.0e-4*n && RUNG < 2) next = RUNG + 1;
+            else if (RUNG > 0 && (double) lower < 1.0e-4*n) next = RUNG - 1;
+            c->rung = next;
+            if (next != c->published) {                        // the host's hint for its choice of kernel (mapped pinned memory)
+                *S.hostRungDevice = next;
+                c->published = next;
+            }
+            c->fails = 0u;
+            c->lower = 0u;
+            c->done = 0u;
+        }
+    }
 }
 
 // Positions of the body atoms from the updated (r, q): one CTA per atom tile, thread per atom.
@@ -1352,18 +1401,24 @@ part2Part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, cons
         // publish this CTA's counts; the last CTA of the launch moves the rung for the next launch: up when more than 4e-4
         // of the bodies needed the retry path, down when fewer than 1e-4 would need it one rung lower
         SeriesControl* c = S.seriesCtl;
-        if (ladderFails) atomicAdd(&c->fails, ladderFails);
-        if (ladderLower) atomicAdd(&c->lower, ladderLower);
-        __threadfence();
+        if (ladderFails | ladderLower) {                       // (rare; the fence orders the counts before this CTA's `done` -
+            if (ladderFails) atomicAdd(&c->fails, ladderFails);       // a CTA without counts must not wait for its own last
+            if (ladderLower) atomicAdd(&c->lower, ladderLower);       // position / velocity stores to drain)
+            __threadfence();
+        }
         if (atomicAdd(&c->done, 1u) == gridDim.x - 1) {
             __threadfence();
-            const unsigned fails = atomicAdd(&c->fails, 0u), lower = atomicAdd(&c->lower, 0u);
+            const volatile unsigned* counts = &c->fails;       // (both loads in flight together: one round trip at the launch's tail)
+            const unsigned fails = counts[0], lower = counts[1];
             const double n = (double) S.numBodies;
             int next = rung;
             if ((double) fails > 4.0e-4*n && rung < 2) next = rung + 1;
             else if (rung > 0 && (double) lower < 1.0e-4*n) next = rung - 1;
             c->rung = next;
-            *S.hostRungDevice = next;                          // the host's hint for its choice of kernel (mapped pinned memory)
+            if (next != c->published) {                        // the host's hint for its choice of kernel (mapped pinned memory)
+                *S.hostRungDevice = next;
+                c->published = next;
+            }
             c->fails = 0u;
             c->lower = 0u;
             c->done = 0u;
@@ -1551,9 +1606,15 @@ template <bool EXACT, bool FUSED, bool NATIVE>
 cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, AtomView vel, AtomView force, bool freeAtoms, cudaStream_t st,
                                const SideStream* side = nullptr) {
     const size_t smem = FUSED ? sizeof(Part1Smem) : offsetof(Part1Smem, d);
-    static LaunchCache cache;
+    // exact rotation on body tiles (large bodies): the kernel compiled for the rung the device last published (a hint that may be a
+    // launch old; every rung is a complete algorithm - bodies that fail its check take the retry path)
+    const int rung = (EXACT && !FUSED) ? (S.fullLadderOnly ? 2 : *S.hostRung) : -1;
+    static LaunchCache cache, cacheRung[3];
     int blocks = 0;
-    cudaError_t e = cache.get(part1Kernel<EXACT, FUSED, NATIVE>, kBlock, smem, blocks);
+    cudaError_t e = rung < 0 ? cache.get(part1Kernel<EXACT, FUSED, NATIVE>, kBlock, smem, blocks)
+                  : rung == 0 ? cacheRung[0].get(part1Kernel<EXACT, false, true, EXACT && !FUSED ? 0 : -1>, kBlock, smem, blocks)
+                  : rung == 1 ? cacheRung[1].get(part1Kernel<EXACT, false, true, EXACT && !FUSED ? 1 : -1>, kBlock, smem, blocks)
+                              : cacheRung[2].get(part1Kernel<EXACT, false, true, EXACT && !FUSED ? 2 : -1>, kBlock, smem, blocks);
     if (e != cudaSuccess) return e;
     // persistent CTAs: one wave that fills every SM
     const bool overlap = !FUSED && freeAtoms && sideUsable(S, side);
@@ -1563,7 +1624,11 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
     const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
     if (tiles > 0) {
-        part1Kernel<EXACT, FUSED, NATIVE><<<tiles < resident ? tiles : resident, kBlock, smem, st>>>(S, dt, pos, vel, force);
+        const int grid = tiles < resident ? tiles : resident;
+        if (rung < 0) part1Kernel<EXACT, FUSED, NATIVE><<<grid, kBlock, smem, st>>>(S, dt, pos, vel, force);
+        else if (rung == 0) part1Kernel<EXACT, false, true, EXACT && !FUSED ? 0 : -1><<<grid, kBlock, smem, st>>>(S, dt, pos, vel, force);
+        else if (rung == 1) part1Kernel<EXACT, false, true, EXACT && !FUSED ? 1 : -1><<<grid, kBlock, smem, st>>>(S, dt, pos, vel, force);
+        else part1Kernel<EXACT, false, true, EXACT && !FUSED ? 2 : -1><<<grid, kBlock, smem, st>>>(S, dt, pos, vel, force);
         e = launchResult(S, st);
         if (e != cudaSuccess) return e;
     }
