@@ -49,6 +49,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RBK_P1_MINBLOCKS_EXACT
 #define RBK_P1_MINBLOCKS_EXACT 2
 #endif
+#ifndef RBK_P1_MINBLOCKS_ROTATION
+#define RBK_P1_MINBLOCKS_ROTATION 2     // the body-tile rotation kernel of large-body systems (RUNG >= 0)
+#endif
 #ifndef RBK_P1_MINBLOCKS_SPLIT
 #define RBK_P1_MINBLOCKS_SPLIT 3
 #endif
@@ -127,7 +130,7 @@ __device__ __forceinline__ int globalPlane(int k) {
 // fixed order of the other four-warp kernels (12, not the water kernels' 11): in a 128-thread tile a body on the retry path
 // holds up its whole CTA, so failures cost more than a lower order saves.  RUNG < 0: fixed order, no control block.
 template <bool EXACT, bool FUSED, bool NATIVE, int RUNG = -1>
-__global__ void __launch_bounds__(kBlock, EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT)
+__global__ void __launch_bounds__(kBlock, EXACT ? (RUNG >= 0 ? RBK_P1_MINBLOCKS_ROTATION : RBK_P1_MINBLOCKS_EXACT) : RBK_P1_MINBLOCKS_SPLIT)
 part1Kernel(const DeviceSystem S, const double dt, const AtomView pos, const AtomView vel, const AtomView force) {
     static_assert(RUNG < 0 || (EXACT && !FUSED), "the ladder variant is the exact-rotation body-tile kernel");
     unsigned ladderFails = 0u, ladderLower = 0u;               // bodies of this thread (RUNG >= 0)
@@ -1622,7 +1625,7 @@ cudaError_t launchPart1Variant(const DeviceSystem& S, double dt, AtomView pos, A
     else if (freeAtoms) e = launchFree<1, NATIVE>(S, dt, pos, vel, force, st);
     if (e != cudaSuccess) return e;
     const int tiles = FUSED ? S.numTiles : S.numBodyTiles;
-    const int resident = S.numSMs*(EXACT ? RBK_P1_MINBLOCKS_EXACT : RBK_P1_MINBLOCKS_SPLIT);
+    const int resident = S.numSMs*(EXACT ? (rung >= 0 ? RBK_P1_MINBLOCKS_ROTATION : RBK_P1_MINBLOCKS_EXACT) : RBK_P1_MINBLOCKS_SPLIT);
     if (tiles > 0) {
         const int grid = tiles < resident ? tiles : resident;
         if (rung < 0) part1Kernel<EXACT, FUSED, NATIVE><<<grid, kBlock, smem, st>>>(S, dt, pos, vel, force);
