@@ -56,6 +56,18 @@ def test_identity_atom_map_no_free_atoms(mode, layout):
     _run_pair(sysd, mode, layout, False, fused=False)
 
 
+@pytest.mark.parametrize("layout", ["vec3", "soa"])
+def test_identity_atom_map_free_atoms_first(layout):
+    """Free atoms in front of the bodies in the caller's arrays: plugin order = caller order, no atomLoc table at all - the free
+    atoms that ride along in part2LargeKernel take their slots from their list index."""
+    rng = np.random.Generator(np.random.Philox(key=331))
+    sysd = _system(rng.integers(9, 61, size=400), 600, seed=332)
+    order = np.concatenate([np.flatnonzero(sysd["bodyIndices"] <= 0), np.flatnonzero(sysd["bodyIndices"] > 0)])
+    sysd = {k: np.ascontiguousarray(v[order]) for k, v in sysd.items()}
+    _run_pair(sysd, 0, layout, False, fused=True)
+    _run_pair(sysd, 3, layout, False, fused=False)
+
+
 @pytest.mark.parametrize("shuffle", [False, True])
 def test_many_tiny_bodies_between_big_ones(shuffle):
     """Mean size > 8 but long runs of 3-atom bodies: up to 85 bodies in one 256-atom tile."""
